@@ -1,0 +1,239 @@
+/* poco_b200 -- C ABI of the B200-native POCO per-crop inference hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own -- every dense
+ * op on the path is a torch.nn call (pocolib/models/poco.py:99-129) -- so each entry point below
+ * names the reference computation it replaces.  All pointers are DEVICE pointers unless stated,
+ * `stream` is a cudaStream_t passed as void*, every call is asynchronous on that stream, returns
+ * 0 on success and a non-zero code otherwise (never throws); poco_last_error() gives the message
+ * of the last failure on the calling thread.  No torch types cross this boundary.
+ *
+ * Activation tensors use the "planar-8 padded" fp16 layout  [C/8][N][H+2][W+2][8]:
+ *   element (n,c,y,x) lives at  ((c/8)*plane_stride + n*(H+2)*(W+2) + (y+1)*(W+2) + (x+1))*8 + c%8
+ * with a zero 1-pixel halo per crop that kernels never write.  The caller must keep
+ * POCO_ACT_GUARD_BYTES of readable (zeroed) memory before `data` and after the last plane.
+ */
+#ifndef POCO_B200_H
+#define POCO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POCO_ACT_GUARD_BYTES 8192
+#define POCO_MAX_FUSE_INPUTS 4
+
+typedef struct poco_act {
+    void* data;           /* fp16, plane 0 / padded pixel 0 */
+    int64_t plane_stride; /* pixels per plane: N*(H+2)*(W+2) */
+    int32_t C, N, H, W;   /* channels (multiple of 8), crops, unpadded height / width */
+} poco_act;
+
+/* conv + folded BatchNorm + optional residual add + optional ReLU.
+ * Replaces nn.Conv2d -> nn.BatchNorm2d(eval) -> (+= residual) -> nn.ReLU chains, e.g.
+ * BasicBlock/Bottleneck (backbone/hrnet.py:42-58, :79-99; resnet.py:100-121), transition and fuse
+ * convs (hrnet.py:198-240, :345-384), output-stage convs (hrnet.py:437-450), the PARE conv branches
+ * (head/pare_head.py:468-491).  weight: fp16 [kh*kw][Cin/8][Cout][8] with the BN scale folded in,
+ * bias: fp32 [Cout] (BN shift + conv bias).  Cin, Cout multiples of 16. */
+typedef struct poco_conv {
+    poco_act in, out;
+    const void* weight;
+    const float* bias;
+    const void* residual; /* fp16, same geometry as out (or NULL) */
+    int64_t res_plane_stride;
+    int32_t kh, kw, stride, pad;
+    int32_t relu; /* 0 none; 1 ReLU after the residual add; 2 ReLU before the residual add */
+    int32_t impl; /* 0 = tcgen05 implicit GEMM (product path); 1 = CUDA-core debug kernel */
+} poco_conv;
+
+/* batch['img'] f32 NCHW [N,3,H,W] -> planar-8 fp16 with channels padded to 16 (poco.py:100 input) */
+typedef struct poco_pack_image {
+    const float* img;
+    poco_act out;
+} poco_pack_image;
+
+/* out = relu?( sum_k nearest_upsample(in[k], 2^shift[k]) ): the HRNet multi-resolution fuse
+ * (hrnet.py:257-264 with the nn.Upsample(mode='nearest') of :206-208 folded into the index) */
+typedef struct poco_fuse_sum {
+    poco_act out;
+    poco_act in[POCO_MAX_FUSE_INPUTS];
+    int32_t shift[POCO_MAX_FUSE_INPUTS];
+    int32_t n_in;
+    int32_t relu;
+} poco_fuse_sum;
+
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (hrnet.py:440) */
+typedef struct poco_upsample2x {
+    poco_act in, out;
+} poco_upsample2x;
+
+/* nn.MaxPool2d(3, 2, 1) (resnet.py:156, :205) */
+typedef struct poco_maxpool {
+    poco_act in, out;
+} poco_maxpool;
+
+/* global average pool -> f32 [N, C] with leading dimension ld (cliff_head.py:95-97,
+ * hrnet_cls.py:479-482) */
+typedef struct poco_avgpool {
+    poco_act in;
+    float* out;
+    int64_t ld;
+} poco_avgpool;
+
+/* planar-8 fp16 -> f32 NCHW [N, C_valid, H, W] (feature export / tests) */
+typedef struct poco_unpack {
+    poco_act in;
+    float* out;
+    int32_t c_valid;
+} poco_unpack;
+
+/* y = act(x W^T + b) (+ res), fp32 row-major.  Replaces nn.Linear call sites: cliff_head.py:103-113,
+ * poco_head.py:122-141, nf_head.py:82, pare_head.py:905-906.  act: 0 none, 1 sigmoid. */
+typedef struct poco_linear {
+    const float* x;
+    int64_t ldx;
+    const float* w; /* [O][I] */
+    const float* b; /* [O] or NULL */
+    const float* res;
+    int64_t ldres;
+    float* y;
+    int64_t ldy;
+    int32_t M, I, O;
+    int32_t act;
+} poco_linear;
+
+/* dst[r, c] = src[(bcast ? 0 : r), c]  (torch.cat / .expand plumbing of cliff_head.py:85-101) */
+typedef struct poco_copy2d {
+    const float* src;
+    int64_t lds;
+    float* dst;
+    int64_t ldd;
+    int32_t rows, cols;
+    int32_t bcast;
+} poco_copy2d;
+
+/* geometry.rot6d_to_rotmat (utils/geometry.py:247-261): x [rows*24? , 6] with row stride ldx ->
+ * out [n, 3, 3] contiguous.  n = number of 6-vectors; vector i starts at x + (i / per_row) * ldx +
+ * (i % per_row) * 6. */
+typedef struct poco_rot6d {
+    const float* x;
+    int64_t ldx;
+    int32_t per_row;
+    int32_t n;
+    float* out;
+} poco_rot6d;
+
+/* PARE head after the two conv branches (pare_head.py:754-826, :896-906, keypoint_attention.py:34-56,
+ * locallyconnected2d.py:27-37):
+ *   segm = conv1x1(part_feats) (+bias)           -> pred_segm_mask f32 [N,25,H,W]
+ *   attn = softmax_HW(segm[:,1:])                 (24 joints)
+ *   point_local[c,j] = sum_p attn[j,p] smpl_feats[c,p]      -> uncert_feat [N,128*24]
+ *   cam_shape[:,j]   = W_sf point_local[:,j] + b_sf  (the 1x1 smpl_final_layer commutes with the pooling)
+ *   pose6d[j,:] = LC(point_local), shape/cam = Linear(flatten(cam_shape)); rot6d -> pred_pose */
+typedef struct poco_pare_head {
+    poco_act part_feats, smpl_feats; /* 128 channels each */
+    const float* w_kp;   /* [25][128] */
+    const float* b_kp;   /* [25] */
+    const float* w_sf;   /* [64][128] */
+    const float* b_sf;   /* [64] */
+    const float* w_pose; /* [6][128][24] */
+    const float* w_shape; /* [10][1536] */
+    const float* b_shape;
+    const float* w_cam; /* [3][1536] */
+    const float* b_cam;
+    float* segm;        /* [N,25,H,W] */
+    float* uncert_feat; /* [N,3072] */
+    float* pose6d;      /* [N,24,6] */
+    float* rotmat;      /* [N,24,3,3] */
+    float* shape;       /* [N,10] */
+    float* cam;         /* [N,3] */
+    float* scratch;     /* poco_pare_scratch_floats(N,H,W) floats */
+} poco_pare_head;
+
+/* conditional RealNVP (layers/real_nvp.py:25-65; nets nf_head.py:13-17), fp32.
+ * params: packed by poco_b200.engine.pack_realnvp -- per coupling layer i: mask[D],
+ * then for net in (s, t): W0[H][D+CTX] b0[H] W1[H][H] b1[H] W2[D][H] b2[D].
+ * direction 0: log_prob (inverse pass, out = logp[R], optional z_out[R,D], logdet_out[R]);
+ * direction 1: forward_p (sampling pass, out = x[R,D]). */
+typedef struct poco_realnvp {
+    const float* x;   /* [R, D] */
+    const float* ctx; /* [R, CTX] (or NULL when CTX == 0) */
+    const float* params;
+    float* out;
+    float* z_out;
+    float* logdet_out;
+    int32_t R, D, CTX, HID, L;
+    int32_t direction;
+} poco_realnvp;
+
+typedef enum poco_op_kind {
+    POCO_OP_PACK_IMAGE = 1,
+    POCO_OP_CONV = 2,
+    POCO_OP_FUSE_SUM = 3,
+    POCO_OP_UPSAMPLE2X = 4,
+    POCO_OP_MAXPOOL = 5,
+    POCO_OP_AVGPOOL = 6,
+    POCO_OP_UNPACK = 7,
+    POCO_OP_LINEAR = 8,
+    POCO_OP_COPY2D = 9,
+    POCO_OP_ROT6D = 10,
+    POCO_OP_PARE_HEAD = 11,
+    POCO_OP_REALNVP = 12
+} poco_op_kind;
+
+typedef struct poco_op {
+    int32_t kind;
+    int32_t lane; /* execution lane (stream) inside a plan; 0 = main */
+    union {
+        poco_pack_image pack_image;
+        poco_conv conv;
+        poco_fuse_sum fuse_sum;
+        poco_upsample2x upsample2x;
+        poco_maxpool maxpool;
+        poco_avgpool avgpool;
+        poco_unpack unpack;
+        poco_linear linear;
+        poco_copy2d copy2d;
+        poco_rot6d rot6d;
+        poco_pare_head pare_head;
+        poco_realnvp realnvp;
+    } u;
+} poco_op;
+
+typedef struct poco_plan poco_plan;
+
+/* library / device */
+int poco_version(void);
+const char* poco_last_error(void);
+int poco_device_check(int device); /* 0 iff `device` is an sm_100 part */
+int64_t poco_kernel_launches(void); /* kernels launched by this library since load (bench evidence) */
+
+/* single ops (each equals poco_run_op on the matching poco_op) */
+int poco_run_op(const poco_op* op, void* stream);
+int poco_conv_run(const poco_conv* d, void* stream);
+int poco_pack_image_run(const poco_pack_image* d, void* stream);
+int poco_fuse_sum_run(const poco_fuse_sum* d, void* stream);
+int poco_upsample2x_run(const poco_upsample2x* d, void* stream);
+int poco_maxpool_run(const poco_maxpool* d, void* stream);
+int poco_avgpool_run(const poco_avgpool* d, void* stream);
+int poco_unpack_run(const poco_unpack* d, void* stream);
+int poco_linear_run(const poco_linear* d, void* stream);
+int poco_copy2d_run(const poco_copy2d* d, void* stream);
+int poco_rot6d_run(const poco_rot6d* d, void* stream);
+int poco_pare_head_run(const poco_pare_head* d, void* stream);
+int poco_realnvp_run(const poco_realnvp* d, void* stream);
+int64_t poco_pare_scratch_floats(int32_t N, int32_t H, int32_t W);
+
+/* a plan = the static layer schedule of one POCO.forward for one batch size (poco.py:99-129):
+ * ops are validated once at creation and replayed in order by poco_plan_run. */
+int poco_plan_create(const poco_op* ops, int32_t n_ops, poco_plan** out);
+int poco_plan_run(poco_plan* plan, void* stream);
+int32_t poco_plan_num_ops(const poco_plan* plan);
+int64_t poco_plan_flops(const poco_plan* plan); /* 2*MAC of conv/linear ops (algorithmic) */
+void poco_plan_destroy(poco_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POCO_B200_H */

@@ -30,6 +30,28 @@ _KEEP_SUFFIX = ('.mask', 'temperature', 'init_pose', 'init_shape', 'init_cam', '
 _DECODER_GAIN = {'decpose': 0.3, 'decshape': 0.3, 'deccam': 0.15}
 
 
+# BatchNorms whose output is ADDED to another path (the closing BN of a residual block, every BN of
+# an HRNet fuse layer) get a small gamma, as in trained residual networks: each block is then a small
+# perturbation of the identity and the network is not chaotic.  With gamma ~ U(0.5, 1.5) everywhere a
+# 1e-7 (fp32 re-association) perturbation of the input grows to 1e-3 at pred_pose, which would make
+# any reduced-precision parity test meaningless.
+import os as _os
+_RES_GAMMA = tuple(float(x) for x in _os.environ.get('POCO_SYNTH_RES_GAMMA', '0.15,0.35').split(','))
+
+
+def _adds_into_a_sum(bn_prefix, template):
+    parent, _, leaf = bn_prefix.rpartition('.')
+    if 'fuse_layers' in bn_prefix:
+        return True
+    if leaf == 'bn3':
+        return True
+    if leaf == 'bn2' and (parent + '.bn3.weight') not in template and (parent + '.conv2.weight') in template \
+            and (parent + '.conv3.weight') not in template and (parent + '.conv1.weight') in template \
+            and parent.split('.')[-1].isdigit():
+        return True          # BasicBlock (conv1/bn1/conv2/bn2 only)
+    return False
+
+
 def _rng(name, seed):
     return np.random.Generator(np.random.PCG64((zlib.crc32(name.encode()) ^ (seed * 2654435761)) & 0xFFFFFFFF))
 
@@ -62,7 +84,8 @@ def synth_state_dict(template, seed=0, calib=None):
         shape = tuple(t.shape)
         if prefix in bn:
             if leaf == 'weight':
-                v = r.uniform(0.5, 1.5, shape)
+                lo, hi = (_RES_GAMMA if _adds_into_a_sum(prefix, template) else (0.5, 1.5))
+                v = r.uniform(lo, hi, shape)
             elif leaf == 'bias':
                 v = 0.1 * r.standard_normal(shape)
             elif leaf == 'running_mean':

@@ -1,0 +1,8 @@
+"""poco_b200 -- B200-native (sm_100a) implementation of POCO's per-crop inference hot path.
+
+    from poco_b200 import POCO        # drop-in for `from pocolib.models import POCO`
+"""
+from ._lib import PocoError, kernel_launches  # noqa: F401
+from .poco import POCO  # noqa: F401
+
+__all__ = ['POCO', 'PocoError', 'kernel_launches']

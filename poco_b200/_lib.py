@@ -1,0 +1,166 @@
+"""ctypes binding of libpoco_b200.so (the C ABI declared in include/poco_b200.h).
+
+The product path has NO fallback: if the shared library is missing or an entry point fails, an
+exception is raised.  Structures below mirror include/poco_b200.h field by field.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpoco_b200.so')
+
+MAX_FUSE_INPUTS = 4
+ACT_GUARD_BYTES = 8192
+
+OP_PACK_IMAGE, OP_CONV, OP_FUSE_SUM, OP_UPSAMPLE2X, OP_MAXPOOL, OP_AVGPOOL, OP_UNPACK, OP_LINEAR, \
+    OP_COPY2D, OP_ROT6D, OP_PARE_HEAD, OP_REALNVP = range(1, 13)
+
+
+class Act(C.Structure):
+    _fields_ = [('data', C.c_void_p), ('plane_stride', C.c_int64),
+                ('C', C.c_int32), ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32)]
+
+
+class Conv(C.Structure):
+    _fields_ = [('in_', Act), ('out', Act), ('weight', C.c_void_p), ('bias', C.c_void_p),
+                ('residual', C.c_void_p), ('res_plane_stride', C.c_int64),
+                ('kh', C.c_int32), ('kw', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
+                ('relu', C.c_int32), ('impl', C.c_int32)]
+
+
+class PackImage(C.Structure):
+    _fields_ = [('img', C.c_void_p), ('out', Act)]
+
+
+class FuseSum(C.Structure):
+    _fields_ = [('out', Act), ('in_', Act * MAX_FUSE_INPUTS), ('shift', C.c_int32 * MAX_FUSE_INPUTS),
+                ('n_in', C.c_int32), ('relu', C.c_int32)]
+
+
+class Upsample2x(C.Structure):
+    _fields_ = [('in_', Act), ('out', Act)]
+
+
+class MaxPool(C.Structure):
+    _fields_ = [('in_', Act), ('out', Act)]
+
+
+class AvgPool(C.Structure):
+    _fields_ = [('in_', Act), ('out', C.c_void_p), ('ld', C.c_int64)]
+
+
+class Unpack(C.Structure):
+    _fields_ = [('in_', Act), ('out', C.c_void_p), ('c_valid', C.c_int32)]
+
+
+class Linear(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('ldx', C.c_int64), ('w', C.c_void_p), ('b', C.c_void_p),
+                ('res', C.c_void_p), ('ldres', C.c_int64), ('y', C.c_void_p), ('ldy', C.c_int64),
+                ('M', C.c_int32), ('I', C.c_int32), ('O', C.c_int32), ('act', C.c_int32)]
+
+
+class Copy2d(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('lds', C.c_int64), ('dst', C.c_void_p), ('ldd', C.c_int64),
+                ('rows', C.c_int32), ('cols', C.c_int32), ('bcast', C.c_int32)]
+
+
+class Rot6d(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('ldx', C.c_int64), ('per_row', C.c_int32), ('n', C.c_int32),
+                ('out', C.c_void_p)]
+
+
+class PareHead(C.Structure):
+    _fields_ = [('part_feats', Act), ('smpl_feats', Act),
+                ('w_kp', C.c_void_p), ('b_kp', C.c_void_p), ('w_sf', C.c_void_p), ('b_sf', C.c_void_p),
+                ('w_pose', C.c_void_p), ('w_shape', C.c_void_p), ('b_shape', C.c_void_p),
+                ('w_cam', C.c_void_p), ('b_cam', C.c_void_p),
+                ('segm', C.c_void_p), ('uncert_feat', C.c_void_p), ('pose6d', C.c_void_p),
+                ('rotmat', C.c_void_p), ('shape', C.c_void_p), ('cam', C.c_void_p), ('scratch', C.c_void_p)]
+
+
+class RealNVP(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('ctx', C.c_void_p), ('params', C.c_void_p), ('out', C.c_void_p),
+                ('z_out', C.c_void_p), ('logdet_out', C.c_void_p),
+                ('R', C.c_int32), ('D', C.c_int32), ('CTX', C.c_int32), ('HID', C.c_int32), ('L', C.c_int32),
+                ('direction', C.c_int32)]
+
+
+class _OpU(C.Union):
+    _fields_ = [('pack_image', PackImage), ('conv', Conv), ('fuse_sum', FuseSum), ('upsample2x', Upsample2x),
+                ('maxpool', MaxPool), ('avgpool', AvgPool), ('unpack', Unpack), ('linear', Linear),
+                ('copy2d', Copy2d), ('rot6d', Rot6d), ('pare_head', PareHead), ('realnvp', RealNVP)]
+
+
+class Op(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('lane', C.c_int32), ('u', _OpU)]
+
+
+_FIELD_OF_KIND = {OP_PACK_IMAGE: 'pack_image', OP_CONV: 'conv', OP_FUSE_SUM: 'fuse_sum',
+                  OP_UPSAMPLE2X: 'upsample2x', OP_MAXPOOL: 'maxpool', OP_AVGPOOL: 'avgpool',
+                  OP_UNPACK: 'unpack', OP_LINEAR: 'linear', OP_COPY2D: 'copy2d', OP_ROT6D: 'rot6d',
+                  OP_PARE_HEAD: 'pare_head', OP_REALNVP: 'realnvp'}
+_KIND_OF_TYPE = {PackImage: OP_PACK_IMAGE, Conv: OP_CONV, FuseSum: OP_FUSE_SUM, Upsample2x: OP_UPSAMPLE2X,
+                 MaxPool: OP_MAXPOOL, AvgPool: OP_AVGPOOL, Unpack: OP_UNPACK, Linear: OP_LINEAR,
+                 Copy2d: OP_COPY2D, Rot6d: OP_ROT6D, PareHead: OP_PARE_HEAD, RealNVP: OP_REALNVP}
+
+# every symbol include/poco_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    'poco_version', 'poco_last_error', 'poco_device_check', 'poco_kernel_launches', 'poco_run_op',
+    'poco_conv_run', 'poco_pack_image_run', 'poco_fuse_sum_run', 'poco_upsample2x_run', 'poco_maxpool_run',
+    'poco_avgpool_run', 'poco_unpack_run', 'poco_linear_run', 'poco_copy2d_run', 'poco_rot6d_run',
+    'poco_pare_head_run', 'poco_realnvp_run', 'poco_pare_scratch_floats',
+    'poco_plan_create', 'poco_plan_run', 'poco_plan_num_ops', 'poco_plan_flops', 'poco_plan_destroy',
+]
+
+_lib = None
+
+
+class PocoError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libpoco_b200.so; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PocoError(f'{LIB_PATH} is missing -- build it with `python -c "import __graft_entry__ as g; '
+                            f'g.build()"`; poco_b200 has no CPU / eager fallback')
+        L = C.CDLL(LIB_PATH)
+        L.poco_last_error.restype = C.c_char_p
+        L.poco_kernel_launches.restype = C.c_int64
+        L.poco_plan_flops.restype = C.c_int64
+        L.poco_plan_flops.argtypes = [C.c_void_p]
+        L.poco_plan_num_ops.argtypes = [C.c_void_p]
+        L.poco_pare_scratch_floats.restype = C.c_int64
+        L.poco_pare_scratch_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.poco_run_op.argtypes = [C.POINTER(Op), C.c_void_p]
+        L.poco_plan_create.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p)]
+        L.poco_plan_run.argtypes = [C.c_void_p, C.c_void_p]
+        L.poco_plan_destroy.argtypes = [C.c_void_p]
+        L.poco_device_check.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PocoError(lib().poco_last_error().decode())
+
+
+def make_op(desc, lane=0):
+    op = Op()
+    op.kind = _KIND_OF_TYPE[type(desc)]
+    op.lane = lane
+    setattr(op.u, _FIELD_OF_KIND[op.kind], desc)
+    return op
+
+
+def run_op(desc, stream):
+    """Run one op descriptor on a cudaStream_t handle (int)."""
+    op = desc if isinstance(desc, Op) else make_op(desc)
+    check(lib().poco_run_op(C.byref(op), C.c_void_p(stream)))
+
+
+def kernel_launches():
+    return int(lib().poco_kernel_launches())

@@ -1,0 +1,335 @@
+"""Architecture descriptions of the POCO hot path, written ONCE against a small backend protocol.
+
+Every function below walks a network (backbone or head) and calls backend methods
+(`conv_bn`, `fuse_sum`, `upsample2x`, `linear`, ...).  Two backends implement the protocol:
+
+  * `SpecBackend` (this file)      -- records parameter / buffer names and shapes.  poco_b200.POCO
+    uses it in __init__ to register tensors under the reference's state-dict names, so reference
+    checkpoints load unchanged (poco.py:131-154, train_utils.py:69-90).
+  * `engine.PlanBuilder`           -- emits op descriptors for libpoco_b200.so.
+
+Reference structure being described (no code shared with it -- the reference builds nn.Modules,
+we build a flat op schedule): hrnet.py:275-528, hrnet_cls.py:250-486, resnet.py:124-217,
+pare_head.py:36-389/:669-928, cliff_head.py:9-127, poco_head.py:15-154, nf_head.py:33-76.
+"""
+from collections import OrderedDict
+
+
+class SymAct:
+    """shape-only activation used by SpecBackend"""
+
+    def __init__(self, C, H, W):
+        self.C, self.H, self.W = C, H, W
+
+    def channels(self, c0, c1):
+        return SymAct(c1 - c0, self.H, self.W)
+
+
+class SpecBackend:
+    mode = 'spec'
+
+    def __init__(self):
+        self.spec = OrderedDict()       # name -> (shape, kind)  kind in {'param', 'buffer', 'long'}
+
+    def _p(self, name, shape, kind='param'):
+        self.spec[name] = (tuple(shape), kind)
+
+    def _bn(self, name, c):
+        self._p(name + '.weight', (c,))
+        self._p(name + '.bias', (c,))
+        self._p(name + '.running_mean', (c,), 'buffer')
+        self._p(name + '.running_var', (c,), 'buffer')
+        self._p(name + '.num_batches_tracked', (), 'long')
+
+    def pack_image(self, img, H, W):
+        return SymAct(16, H, W)
+
+    def conv_bn(self, x, conv, bn, cin, cout, k, stride=1, relu=True, residual=None, out=None, pad=None, bias=False):
+        convs = conv if isinstance(conv, (list, tuple)) else [conv]
+        bns = bn if isinstance(bn, (list, tuple)) else [bn] * len(convs)
+        each = cout // len(convs)
+        for cv, b_ in zip(convs, bns):
+            self._p(cv + '.weight', (each, cin, k, k))
+            if bias:
+                self._p(cv + '.bias', (each,))
+            if b_ is not None:
+                self._bn(b_, each)
+        pad = k // 2 if pad is None else pad
+        return SymAct(cout, (x.H + 2 * pad - k) // stride + 1, (x.W + 2 * pad - k) // stride + 1)
+
+    def param_only_conv(self, name, cin, cout, k, bias=True):
+        self._p(name + '.weight', (cout, cin, k, k))
+        if bias:
+            self._p(name + '.bias', (cout,))
+
+    def param_only_linear(self, name, i, o):
+        self._p(name + '.weight', (o, i))
+        self._p(name + '.bias', (o,))
+
+    def buffer(self, name, shape):
+        self._p(name, shape, 'buffer')
+
+    def param(self, name, shape):
+        self._p(name, shape)
+
+    def act(self, C, H, W):
+        return SymAct(C, H, W)
+
+    def fuse_sum(self, terms, relu, out=None):
+        a, s = terms[0]
+        return out or SymAct(a.C, a.H << s, a.W << s)
+
+    def upsample2x(self, x):
+        return SymAct(x.C, 2 * x.H, 2 * x.W)
+
+    def maxpool(self, x):
+        return SymAct(x.C, (x.H - 1) // 2 + 1, (x.W - 1) // 2 + 1)
+
+    def free(self, a):
+        pass
+
+
+# ------------------------------------------------------------------------------------------------
+# residual blocks
+# ------------------------------------------------------------------------------------------------
+def basic_block(b, x, name, cin, cout, free_input=True):
+    """conv3x3-BN-ReLU, conv3x3-BN, += x, ReLU  (hrnet.py:42-58); HRNet branches never downsample"""
+    y = b.conv_bn(x, name + '.conv1', name + '.bn1', cin, cout, 3)
+    o = b.conv_bn(y, name + '.conv2', name + '.bn2', cout, cout, 3, residual=x)
+    b.free(y)
+    if free_input:
+        b.free(x)
+    return o
+
+
+def bottleneck(b, x, name, cin, planes, stride=1, downsample=False, free_input=True):
+    """1x1 -> 3x3(stride) -> 1x1 x4, residual (v1.5)  (hrnet.py:79-99, resnet.py:100-121)"""
+    cout = planes * 4
+    y1 = b.conv_bn(x, name + '.conv1', name + '.bn1', cin, planes, 1)
+    y2 = b.conv_bn(y1, name + '.conv2', name + '.bn2', planes, planes, 3, stride)
+    b.free(y1)
+    r = x
+    if downsample:
+        r = b.conv_bn(x, name + '.downsample.0', name + '.downsample.1', cin, cout, 1, stride, relu=False)
+    o = b.conv_bn(y2, name + '.conv3', name + '.bn3', planes, cout, 1, residual=r)
+    b.free(y2)
+    if r is not x:
+        b.free(r)
+    if free_input:
+        b.free(x)
+    return o
+
+
+# ------------------------------------------------------------------------------------------------
+# HRNet trunk (shared by the pose variant and the classification variant)
+# ------------------------------------------------------------------------------------------------
+def hr_module(b, xs, name, chans):
+    """HighResolutionModule: 4 BasicBlocks per branch, then the multi-resolution fuse
+    (hrnet.py:188-266).  Inputs are consumed (freed)."""
+    nb = len(xs)
+    for i in range(nb):
+        x = xs[i]
+        for k in range(4):
+            x = basic_block(b, x, f'{name}.branches.{i}.{k}', chans[i], chans[i])
+        xs[i] = x
+    if nb == 1:
+        return xs
+    outs = []
+    for i in range(nb):
+        ups = []
+        for j in range(i + 1, nb):      # 1x1 conv + BN at low resolution; nearest upsample folded into the sum
+            z = b.conv_bn(xs[j], f'{name}.fuse_layers.{i}.{j}.0', f'{name}.fuse_layers.{i}.{j}.1',
+                          chans[j], chans[i], 1, relu=False)
+            ups.append((z, j - i))
+        if i == 0:
+            o = b.fuse_sum([(xs[0], 0)] + ups, relu=True)
+        else:
+            acc = b.fuse_sum([(xs[i], 0)] + ups, relu=False) if ups else xs[i]
+            for j in range(i):          # stride-2 conv chains; the running sum rides on the residual input
+                t = xs[j]
+                for k in range(i - j):
+                    f = f'{name}.fuse_layers.{i}.{j}.{k}'
+                    if k != i - j - 1:
+                        t2 = b.conv_bn(t, f + '.0', f + '.1', chans[j], chans[j], 3, 2, relu=True)
+                    else:
+                        t2 = b.conv_bn(t, f + '.0', f + '.1', chans[j], chans[i], 3, 2, relu=(j == i - 1), residual=acc)
+                        if acc is not xs[i]:
+                            b.free(acc)
+                        acc = t2
+                    if t is not xs[j]:
+                        b.free(t)
+                    t = t2
+            o = acc
+        for z, _ in ups:
+            b.free(z)
+        outs.append(o)
+    for x in xs:
+        b.free(x)
+    return outs
+
+
+def hrnet_trunk(b, img, widths, H=224, W=224, prefix='backbone.'):
+    p = prefix
+    x = b.pack_image(img, H, W)
+    y = b.conv_bn(x, p + 'conv1', p + 'bn1', 3, 64, 3, 2)
+    b.free(x)
+    x = b.conv_bn(y, p + 'conv2', p + 'bn2', 64, 64, 3, 2)
+    b.free(y)
+    for k in range(4):
+        x = bottleneck(b, x, f'{p}layer1.{k}', 64 if k == 0 else 256, 64, downsample=(k == 0))
+    # transition1: 256 -> [w0 @56 (3x3 s1), w1 @28 (3x3 s2)]
+    x0 = b.conv_bn(x, p + 'transition1.0.0', p + 'transition1.0.1', 256, widths[0], 3)
+    x1 = b.conv_bn(x, p + 'transition1.1.0.0', p + 'transition1.1.0.1', 256, widths[1], 3, 2)
+    b.free(x)
+    ys = hr_module(b, [x0, x1], p + 'stage2.0', widths[:2])
+    n_modules = {3: 4, 4: 3}
+    for st in (3, 4):
+        nbr = st
+        new = b.conv_bn(ys[-1], f'{p}transition{st - 1}.{nbr - 1}.0.0', f'{p}transition{st - 1}.{nbr - 1}.0.1',
+                        widths[nbr - 2], widths[nbr - 1], 3, 2)
+        ys = ys + [new]
+        for m in range(n_modules[st]):
+            ys = hr_module(b, ys, f'{p}stage{st}.{m}', widths[:nbr])
+    return ys
+
+
+def hrnet_pose(b, img, width=32, prefix='backbone.'):
+    """PoseHighResolutionNet with use_conv=True / downsample=False -> [N, 15*width, 56, 56]
+    (hrnet.py:466-528).  Each branch lands in its channel slice of one buffer, so torch.cat is free."""
+    widths = [width, 2 * width, 4 * width, 8 * width]
+    ys = hrnet_trunk(b, img, widths, prefix=prefix)
+    feats = b.act(sum(widths), ys[0].H, ys[0].W)
+    c0 = 0
+    b.fuse_sum([(ys[0], 0)], relu=False, out=feats.channels(0, widths[0]))
+    b.free(ys[0])
+    c0 += widths[0]
+    for br in range(1, 4):
+        t = ys[br]
+        for k in range(br):
+            u = b.upsample2x(t)
+            b.free(t)
+            name = f'{prefix}upsample_stage_{br + 1}'
+            last = k == br - 1
+            t = b.conv_bn(u, f'{name}.{4 * k + 1}', f'{name}.{4 * k + 2}', widths[br], widths[br], 3,
+                          out=feats.channels(c0, c0 + widths[br]) if last else None)
+            b.free(u)
+        c0 += widths[br]
+    if b.mode == 'spec':
+        b.param_only_conv(prefix + 'final_layer', widths[0], 24, 1)      # present in checkpoints, never executed
+    return feats
+
+
+def hrnet_cls(b, img, width=48, prefix='backbone.'):
+    """HighResolutionNet + classification head up to the 2048-channel 7x7 map (hrnet_cls.py:438-477);
+    the caller pools it."""
+    widths = [width, 2 * width, 4 * width, 8 * width]
+    ys = hrnet_trunk(b, img, widths, prefix=prefix)
+    head = [32, 64, 128, 256]
+    y = bottleneck(b, ys[0], f'{prefix}incre_modules.0.0', widths[0], head[0], downsample=True)
+    for i in range(3):
+        inc = bottleneck(b, ys[i + 1], f'{prefix}incre_modules.{i + 1}.0', widths[i + 1], head[i + 1], downsample=True)
+        d = f'{prefix}downsamp_modules.{i}'
+        # y = incre(x_{i+1}) + ReLU(BN(conv3x3 s2 (y)))  -> ReLU *before* the residual add (relu=2)
+        y2 = b.conv_bn(y, d + '.0', d + '.1', head[i] * 4, head[i + 1] * 4, 3, 2, relu=2, residual=inc, bias=True)
+        b.free(y)
+        b.free(inc)
+        y = y2
+    f = prefix + 'final_layer'
+    o = b.conv_bn(y, f + '.0', f + '.1', 1024, 2048, 1, bias=True)
+    b.free(y)
+    if b.mode == 'spec':
+        b.param_only_linear(prefix + 'classifier', 2048, 1000)           # unused (hrnet_cls.py:484)
+    return o
+
+
+def resnet50(b, img, prefix='backbone.'):
+    """torchvision-style ResNet-50 v1.5 trunk -> [N, 2048, 7, 7] (resnet.py:201-217)"""
+    p = prefix
+    x = b.pack_image(img, 224, 224)
+    y = b.conv_bn(x, p + 'conv1', p + 'bn1', 3, 64, 7, 2, pad=3)
+    b.free(x)
+    x = b.maxpool(y)
+    b.free(y)
+    cin = 64
+    for li, (planes, blocks) in enumerate(((64, 3), (128, 4), (256, 6), (512, 3)), start=1):
+        for k in range(blocks):
+            stride = 2 if (k == 0 and li > 1) else 1
+            x = bottleneck(b, x, f'{p}layer{li}.{k}', cin, planes, stride, downsample=(k == 0))
+            cin = planes * 4
+    return x
+
+
+# name -> (builder, output channels)
+BACKBONES = {
+    'hrnet_w32': (lambda b, img: hrnet_pose(b, img, 32), 480),
+    'hrnet_w48_cls': (lambda b, img: hrnet_cls(b, img, 48), 2048),
+    'resnet50': (resnet50, 2048),
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# head parameter specs (the op emission for heads lives in poco.py, next to the output plumbing)
+# ------------------------------------------------------------------------------------------------
+def pare_head_convs(b, feats, cin, prefix='head.'):
+    """the two conv branches of pare_head (_make_conv_layer, pare_head.py:468-491).  Their first
+    convs read the same input, so they run as ONE conv with the output channels concatenated."""
+    kd, sd = prefix + 'keypoint_deconv_layers', prefix + 'smpl_deconv_layers'
+    t = b.conv_bn(feats, [kd + '.0', sd + '.0'], [kd + '.1', sd + '.1'], cin, 256, 3)
+    part = b.conv_bn(t.channels(0, 128), kd + '.3', kd + '.4', 128, 128, 3)
+    smpl = b.conv_bn(t.channels(128, 256), sd + '.3', sd + '.4', 128, 128, 3)
+    b.free(t)
+    return part, smpl
+
+
+def pare_head_spec(b, prefix='head.'):
+    b.param_only_conv(prefix + 'keypoint_final_layer', 128, 25, 1)
+    b.param_only_conv(prefix + 'smpl_final_layer', 128, 64, 1)
+    b.buffer(prefix + 'temperature', ())
+    b.buffer(prefix + 'init_pose', (1, 144))
+    b.buffer(prefix + 'init_shape', (1, 10))
+    b.buffer(prefix + 'init_cam', (1, 3))
+    b.param_only_linear(prefix + 'shape_mlp', 64 * 24, 10)
+    b.param_only_linear(prefix + 'cam_mlp', 64 * 24, 3)
+    b.param(prefix + 'pose_mlp.weight', (1, 6, 128, 24, 1, 1))
+
+
+def cliff_head_spec(b, nfeat, prefix='head.'):
+    b.param_only_linear(prefix + 'fc1', nfeat + 3 + 144 + 13, 1024)
+    b.param_only_linear(prefix + 'fc2', 1024, 1024)
+    b.param_only_linear(prefix + 'decpose', 1024, 144)
+    b.param_only_linear(prefix + 'decshape', 1024, 10)
+    b.param_only_linear(prefix + 'deccam', 1024, 3)
+    b.buffer(prefix + 'init_pose', (1, 144))
+    b.buffer(prefix + 'init_shape', (1, 10))
+    b.buffer(prefix + 'init_cam', (1, 3))
+
+
+def poco_head_layers(nfeat, num_neurons, uncert_inp_type, n_out=24):
+    """Layer list of poco_head (poco_head.py:15-82): returns (pose_net, [(name, in, out), ...])."""
+    inp = nfeat + (216 if uncert_inp_type == 'feat-pose' else 0)
+    nn_ = [inp] + list(num_neurons) + [n_out]
+    pre = []
+    if 'pose-net' in uncert_inp_type:
+        pre = [('uncert_fc_poseNet', 216, nn_[1]), ('uncert_fc_featNet', nn_[0], nn_[1])]
+        nn_ = nn_[1:]
+        nn_[0] *= 2
+    layers = [(f'uncert_fc{i + 1}', nn_[i], nn_[i + 1]) for i in range(len(nn_) - 1)]
+    return pre, layers
+
+
+def poco_head_spec(b, nfeat, num_neurons, uncert_inp_type, prefix='uncert_head.'):
+    pre, layers = poco_head_layers(nfeat, num_neurons, uncert_inp_type)
+    for name, i, o in pre + layers:
+        b.param_only_linear(prefix + name, i, o)
+
+
+def flow_head_spec(b, nfeat, context_dim, cond, num_flow_layers, num_rv=9, hid=64, prefix='flow_head.'):
+    ctx = context_dim if cond else 0
+    if cond:
+        b.param_only_linear(prefix + 'cond_layer', nfeat, context_dim)
+    b.buffer(prefix + 'flow.mask', (2 * num_flow_layers, num_rv))
+    for net in ('t', 's'):
+        for i in range(2 * num_flow_layers):
+            b.param_only_linear(f'{prefix}flow.{net}.{i}.0', num_rv + ctx, hid)
+            b.param_only_linear(f'{prefix}flow.{net}.{i}.2', hid, hid)
+            b.param_only_linear(f'{prefix}flow.{net}.{i}.4', hid, num_rv)

@@ -1,0 +1,98 @@
+// poco_b200 -- C-ABI entry points that are not tied to one kernel file: error reporting, device
+// check, op dispatch and the plan (static layer schedule) executor.
+#include <cstring>
+#include <vector>
+
+#include "internal.h"
+
+namespace poco {
+
+std::atomic<int64_t> g_launches{0};
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+}  // namespace poco
+
+using namespace poco;
+
+struct poco_plan {
+    std::vector<poco_op> ops;
+    int64_t flops = 0;
+};
+
+extern "C" int poco_version(void) { return 100; }
+
+extern "C" const char* poco_last_error(void) { return g_error.c_str(); }
+
+extern "C" int64_t poco_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" int poco_device_check(int device) {
+    cudaDeviceProp prop;
+    POCO_CUDA(cudaGetDeviceProperties(&prop, device));
+    POCO_CHECK(prop.major == 10, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                     ", poco_b200 kernels are sm_100a only");
+    return 0;
+}
+
+extern "C" int poco_conv_run(const poco_conv* d, void* stream) {
+    if (check_act(d->in, "in") || check_act(d->out, "out")) return 1;
+    POCO_CHECK(d->weight && d->bias, "null weight / bias");
+    POCO_CHECK(d->kh >= 1 && d->kw >= 1 && d->pad >= 0, "bad kernel geometry");
+    POCO_CHECK(!d->residual || d->res_plane_stride >= int64_t(d->out.N) * (d->out.H + 2) * (d->out.W + 2),
+               "residual plane stride too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return d->impl == 1 ? conv_ref_launch(d, s) : conv_tc_launch(d, s);
+}
+
+extern "C" int poco_run_op(const poco_op* op, void* stream) {
+    switch (op->kind) {
+        case POCO_OP_PACK_IMAGE: return poco_pack_image_run(&op->u.pack_image, stream);
+        case POCO_OP_CONV: return poco_conv_run(&op->u.conv, stream);
+        case POCO_OP_FUSE_SUM: return poco_fuse_sum_run(&op->u.fuse_sum, stream);
+        case POCO_OP_UPSAMPLE2X: return poco_upsample2x_run(&op->u.upsample2x, stream);
+        case POCO_OP_MAXPOOL: return poco_maxpool_run(&op->u.maxpool, stream);
+        case POCO_OP_AVGPOOL: return poco_avgpool_run(&op->u.avgpool, stream);
+        case POCO_OP_UNPACK: return poco_unpack_run(&op->u.unpack, stream);
+        case POCO_OP_LINEAR: return poco_linear_run(&op->u.linear, stream);
+        case POCO_OP_COPY2D: return poco_copy2d_run(&op->u.copy2d, stream);
+        case POCO_OP_ROT6D: return poco_rot6d_run(&op->u.rot6d, stream);
+        case POCO_OP_PARE_HEAD: return poco_pare_head_run(&op->u.pare_head, stream);
+        case POCO_OP_REALNVP: return poco_realnvp_run(&op->u.realnvp, stream);
+        default: break;
+    }
+    set_error("poco_run_op: unknown op kind " + std::to_string(op->kind));
+    return 1;
+}
+
+extern "C" int poco_plan_create(const poco_op* ops, int32_t n_ops, poco_plan** out) {
+    POCO_CHECK(ops != nullptr && n_ops > 0 && out != nullptr, "bad arguments");
+    poco_plan* p = new poco_plan();
+    p->ops.assign(ops, ops + n_ops);
+    for (const poco_op& op : p->ops) {
+        if (op.kind == POCO_OP_CONV) p->flops += conv_flops(&op.u.conv);
+        if (op.kind == POCO_OP_LINEAR) p->flops += 2ll * op.u.linear.M * op.u.linear.I * op.u.linear.O;
+        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_REALNVP) {
+            delete p;
+            set_error("poco_plan_create: unknown op kind " + std::to_string(op.kind));
+            return 1;
+        }
+    }
+    *out = p;
+    return 0;
+}
+
+extern "C" int poco_plan_run(poco_plan* plan, void* stream) {
+    POCO_CHECK(plan != nullptr, "null plan");
+    for (size_t i = 0; i < plan->ops.size(); ++i) {
+        const int rc = poco_run_op(&plan->ops[i], stream);
+        if (rc != 0) {
+            set_error("op " + std::to_string(i) + " (kind " + std::to_string(plan->ops[i].kind) + "): " + g_error);
+            return rc;
+        }
+    }
+    return 0;
+}
+
+extern "C" int32_t poco_plan_num_ops(const poco_plan* plan) { return plan ? int32_t(plan->ops.size()) : 0; }
+extern "C" int64_t poco_plan_flops(const poco_plan* plan) { return plan ? plan->flops : 0; }
+extern "C" void poco_plan_destroy(poco_plan* plan) { delete plan; }

@@ -1,0 +1,159 @@
+// poco_b200 -- shared device helpers (sm_100a only): mbarrier, bulk-copy (TMA engine, UBLKCP),
+// cp.async, tcgen05 (UMMA / TMEM) wrappers and the activation-layout index math.
+//
+// Activation layout ("planar-8 padded", fp16):   [C/8][N][H+2][W+2][8]
+//   * one *plane* holds 8 consecutive channels of every pixel of every crop (16 B per pixel);
+//   * every crop carries a 1-pixel zero halo that no kernel ever writes, so a 3x3/pad-1 window of
+//     output pixel q (q = padded-linear index inside the plane) is the 9 linear shifts
+//     q + (r-1)*(W+2) + (s-1): an implicit-GEMM A-tile is a *contiguous* 1-D run of the plane and is
+//     fetched with ONE bulk copy per plane -- no im2col, no tensor map;
+//   * 16 B per pixel is exactly the 8x16B core-matrix row of the UMMA no-swizzle K-major canonical
+//     layout, so the landed bytes are MMA-ready (SBO = 128 B, LBO = plane pitch in shared memory).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if !defined(__CUDA_ARCH_FEAT_SM100_ALL) && defined(__CUDA_ARCH__)
+#error "poco_b200 kernels are written for sm_100a only (compile with -gencode arch=compute_100a,code=sm_100a)"
+#endif
+
+namespace poco {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// async copies
+// ---------------------------------------------------------------------------------------------
+// 1-D bulk copy global -> shared, executed by the TMA engine (SASS: UBLKCP), completes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+// 16-byte cp.async (LDGSTS) with zero-fill when !valid
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const uint32_t sz = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// tcgen05.commit: the mbarrier is arrived-on once all previously issued MMAs of this thread retire
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate, M=128, K=16 per instruction
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor, no-swizzle K-major canonical layout (cute::UMMA::SmemDescriptor):
+//   core matrix = 8 rows x 16 B (rows 16 B apart); SBO = byte pitch between 8-row groups (M/N dir);
+//   LBO = byte pitch between the two 16-byte K halves of one K=16 MMA.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);            // [0,14)  start address >> 4
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;   // [16,30) leading-dim byte offset >> 4
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;   // [32,46) stride-dim byte offset >> 4
+    d |= 1ull << 46;                                                // [46,48) descriptor version (sm_100)
+    // base_offset [49,52) = 0, lbo_mode [52] = 0, layout_type [61,64) = 0 (SWIZZLE_NONE)
+    return d;
+}
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): fp16 x fp16 -> fp32, K-major A and B
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4)            // c_format = F32
+           | (0u << 7)          // a_format = F16
+           | (0u << 10)         // b_format = F16
+           | (0u << 15)         // a_major = K
+           | (0u << 16)         // b_major = K
+           | ((N >> 3) << 17)   // n_dim
+           | ((M >> 4) << 24);  // m_dim
+}
+
+// TMEM -> registers: 32 lanes x 16 consecutive fp32 columns (one row per thread)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t v) {
+    return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+
+}  // namespace poco

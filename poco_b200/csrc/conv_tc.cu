@@ -1,0 +1,467 @@
+// poco_b200 -- conv + folded-BN + residual + ReLU as a tcgen05 implicit GEMM (sm_100a).
+//
+// Replaces every nn.Conv2d -> nn.BatchNorm2d(eval) -> (+residual) -> nn.ReLU chain of the reference
+// backbones and the PARE conv branches (hrnet.py:42-58, :79-99, :198-240, :345-384, :437-450;
+// hrnet_cls.py:306-353; resnet.py:100-121, :201-217; pare_head.py:468-491).
+//
+// GEMM view:  D[M = output pixels, N = Cout] = A[M, K = taps*Cin] * W[N, K]^T, fp16 x fp16 -> fp32.
+//   * M index = padded-linear pixel index q of the OUTPUT plane; one CTA tile = 128 consecutive q.
+//     Halo / out-of-range rows are computed and discarded (MMA rows are independent).
+//   * accumulators: TMEM, 128 lanes x n_tile fp32 columns, double buffered (epilogue of tile i
+//     overlaps the MMAs of tile i+1); one elected thread issues tcgen05.mma (M=128, N=n_tile, K=16).
+//   * operands: shared memory in the UMMA no-swizzle K-major canonical layout.  The planar-8
+//     activation layout already *is* that layout (16 B per pixel per plane), so
+//       MODE_LINEAR (3x3/s1/p1 and 1x1/s1): ONE bulk copy (TMA engine, UBLKCP) per 8-channel plane
+//         brings the tile plus its (W+2)+1 pixel halo; the 9 taps are 9 shifted descriptors into the
+//         same bytes -- the input is read from L2/HBM once, not 9 times;
+//       MODE_GATHER (stride 2, 7x7, anything else): 128 producer threads cp.async one 16-byte pixel
+//         each per plane and tap (zero-fill outside the image).
+//     Weights [tap][Cin/8][Cout][8] are kept resident in shared memory for the whole persistent CTA
+//     when they fit, else streamed per K-chunk with bulk copies.
+//   * epilogue (4 warps): tcgen05.ld 16 columns at a time -> +bias (BN shift) -> +residual -> ReLU ->
+//     fp16 -> 16-byte stores, 512 contiguous bytes per warp; halo pixels are never written.
+//   * persistent grid: <= one CTA per SM, static round-robin over M tiles; mbarrier pipelines
+//     smem full/empty (producer <-> MMA) and tmem full/empty (MMA <-> epilogue).
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace poco {
+
+namespace {
+
+constexpr int kMaxStages = 8;
+constexpr int kTileM = 128;
+constexpr int kSmemBudget = 225 * 1024;   // of 227 KB usable per CTA
+constexpr int kHeaderBytes = 2048;        // barriers + bias
+constexpr int kGatherLag = 2;
+
+enum { MODE_LINEAR = 0, MODE_GATHER = 1 };
+
+struct ConvTcParams {
+    const __half* in;
+    long long in_plane;
+    int Hin, Win;
+    __half* out;
+    long long out_plane;
+    int Hout, Wout;
+    const __half* res;
+    long long res_plane;
+    const __half* w;
+    const float* bias;
+    int Cin, Cout;
+    int kh, kw, stride, pad;
+    int relu;
+    int kc, n_chunks;
+    int n_tile;
+    int w_resident;
+    int stages;
+    int num_m_tiles;
+    long long P_out;
+    int a_plane_bytes, a_copy_bytes, a_stage_bytes, w_stage_bytes, w_res_bytes;
+    int halo;
+    int tmem_cols;
+};
+
+struct SmemHeader {
+    unsigned long long full[kMaxStages];
+    unsigned long long empty[kMaxStages];
+    unsigned long long tmem_full[2];
+    unsigned long long tmem_empty[2];
+    unsigned long long w_ready;
+    uint32_t tmem_base;
+    uint32_t pad_[5];
+    float bias[256];
+};
+static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
+
+template <int MODE>
+struct Roles {
+    // MODE_LINEAR: warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+    // MODE_GATHER: warps 0-3 A producers, warp 4 MMA, warp 5 W producer, warps 6-9 epilogue
+    static constexpr int kProducerWarps = MODE == MODE_LINEAR ? 1 : 4;
+    static constexpr int kMmaWarp = MODE == MODE_LINEAR ? 1 : 4;
+    static constexpr int kWWarp = MODE == MODE_LINEAR ? 0 : 5;
+    static constexpr int kEpiWarp0 = MODE == MODE_LINEAR ? 2 : 6;
+    static constexpr int kThreads = (kEpiWarp0 + 4) * 32;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
+    uint8_t* w_res = smem + kHeaderBytes;
+    uint8_t* stage0 = w_res + p.w_res_bytes;
+    const int stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nb = blockIdx.y;                      // N block
+    const int taps = p.kh * p.kw;
+    const int planes_per_chunk = p.kc >> 3;
+    const int cin8 = p.Cin >> 3;
+    const int kiters = MODE == MODE_LINEAR ? p.n_chunks : p.n_chunks * taps;
+    const uint32_t slab_bytes = uint32_t(p.n_tile) * 16u;     // one (tap, 8-channel) weight slab
+    using R = Roles<MODE>;
+
+    // ---------------------------------------------------------------- setup
+    if (threadIdx.x == 0) {
+        const uint32_t full_count = MODE == MODE_LINEAR ? 1u : (128u + (p.w_resident ? 0u : 1u));
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(smem_u32(&hdr->full[i]), full_count);
+            mbar_init(smem_u32(&hdr->empty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&hdr->tmem_full[i]), 1);
+            mbar_init(smem_u32(&hdr->tmem_empty[i]), 4);
+        }
+        mbar_init(smem_u32(&hdr->w_ready), 1);
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) hdr->bias[i] = p.bias[nb * p.n_tile + i];
+    if (warp == R::kMmaWarp) tmem_alloc(smem_u32(&hdr->tmem_base), uint32_t(p.tmem_cols));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = hdr->tmem_base;
+    const uint32_t buf_cols = uint32_t(p.tmem_cols) >> 1;
+
+    const __half* wg = p.w + size_t(nb) * p.n_tile * 8;       // this N block's column offset inside a slab row
+
+    // ---------------------------------------------------------------- weight loader (shared by both modes)
+    auto load_resident_weights = [&]() {
+        mbar_arrive_expect_tx(smem_u32(&hdr->w_ready), uint32_t(p.w_res_bytes));
+        for (int s = 0; s < taps * cin8; ++s)
+            bulk_g2s(smem_u32(w_res) + uint32_t(s) * slab_bytes, wg + size_t(s) * p.Cout * 8, slab_bytes,
+                     smem_u32(&hdr->w_ready));
+    };
+
+    if (MODE == MODE_LINEAR && warp == 0) {
+        // ============================================================ producer (bulk copies)
+        if (lane == 0) {
+            if (p.w_resident) load_resident_weights();
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+                const long long q0 = (long long)tile * kTileM - p.halo;
+                for (int c = 0; c < p.n_chunks; ++c, ++it) {
+                    const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+                    mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
+                    const uint32_t bar = smem_u32(&hdr->full[slot]);
+                    const uint32_t tx = uint32_t(planes_per_chunk) * p.a_copy_bytes +
+                                        (p.w_resident ? 0u : uint32_t(p.w_stage_bytes));
+                    mbar_arrive_expect_tx(bar, tx);
+                    uint8_t* st = stage0 + size_t(slot) * stage_bytes;
+                    for (int j = 0; j < planes_per_chunk; ++j) {
+                        const __half* src = p.in + ((long long)(c * planes_per_chunk + j) * p.in_plane + q0) * 8;
+                        bulk_g2s(smem_u32(st) + uint32_t(j) * p.a_plane_bytes, src, uint32_t(p.a_copy_bytes), bar);
+                    }
+                    if (!p.w_resident) {
+                        const uint32_t ws = smem_u32(st) + p.a_stage_bytes;
+                        for (int t = 0; t < taps; ++t)
+                            for (int j = 0; j < planes_per_chunk; ++j)
+                                bulk_g2s(ws + uint32_t(t * planes_per_chunk + j) * slab_bytes,
+                                         wg + size_t(t * cin8 + c * planes_per_chunk + j) * p.Cout * 8, slab_bytes, bar);
+                    }
+                }
+            }
+        }
+    } else if (MODE == MODE_GATHER && warp < 4) {
+        // ============================================================ A producers (cp.async gather)
+        const int r = threadIdx.x;                 // row of the tile
+        const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
+        const int Wp_i = p.Win + 2, HpWp_i = (p.Hin + 2) * Wp_i;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+            const long long q = (long long)tile * kTileM + r;
+            const int n = int(q / HpWp_o);
+            const int rem = int(q - (long long)n * HpWp_o);
+            const int yo = rem / Wp_o - 1, xo = rem % Wp_o - 1;
+            const bool interior = q < p.P_out && yo >= 0 && yo < p.Hout && xo >= 0 && xo < p.Wout;
+            for (int t = 0; t < taps; ++t) {
+                const int yi = yo * p.stride + t / p.kw - p.pad;
+                const int xi = xo * p.stride + t % p.kw - p.pad;
+                const bool ok = interior && yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win;
+                const long long pix = ok ? ((long long)n * HpWp_i + (yi + 1) * Wp_i + (xi + 1)) : 0;
+                for (int c = 0; c < p.n_chunks; ++c, ++it) {
+                    const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+                    mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
+                    uint8_t* st = stage0 + size_t(slot) * stage_bytes;
+                    for (int j = 0; j < planes_per_chunk; ++j) {
+                        const __half* src = p.in + ((long long)(c * planes_per_chunk + j) * p.in_plane + pix) * 8;
+                        cp_async16(smem_u32(st) + uint32_t(j) * p.a_plane_bytes + uint32_t(r) * 16u, src, ok);
+                    }
+                    cp_async_commit();
+                    if (it >= uint32_t(kGatherLag)) {
+                        cp_async_wait<kGatherLag>();
+                        fence_proxy_async_smem();
+                        mbar_arrive(smem_u32(&hdr->full[(it - kGatherLag) % p.stages]));
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        for (uint32_t d = (it > uint32_t(kGatherLag) ? it - kGatherLag : 0u); d < it; ++d)
+            mbar_arrive(smem_u32(&hdr->full[d % p.stages]));
+    } else if (MODE == MODE_GATHER && warp == R::kWWarp) {
+        // ============================================================ W producer (bulk copies)
+        if (lane == 0) {
+            if (p.w_resident) {
+                load_resident_weights();
+            } else {
+                uint32_t it = 0;
+                for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x)
+                    for (int t = 0; t < taps; ++t)
+                        for (int c = 0; c < p.n_chunks; ++c, ++it) {
+                            const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+                            mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
+                            const uint32_t bar = smem_u32(&hdr->full[slot]);
+                            mbar_arrive_expect_tx(bar, uint32_t(p.w_stage_bytes));
+                            const uint32_t ws = smem_u32(stage0 + size_t(slot) * stage_bytes) + p.a_stage_bytes;
+                            for (int j = 0; j < planes_per_chunk; ++j)
+                                bulk_g2s(ws + uint32_t(j) * slab_bytes,
+                                         wg + size_t(t * cin8 + c * planes_per_chunk + j) * p.Cout * 8, slab_bytes, bar);
+                        }
+            }
+        }
+    } else if (warp == R::kMmaWarp) {
+        // ============================================================ MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(kTileM, uint32_t(p.n_tile));
+            if (p.w_resident) mbar_wait(smem_u32(&hdr->w_ready), 0);
+            uint32_t it = 0, tl = 0;
+            const int Wp = p.Wout + 2;
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
+                const uint32_t buf = tl & 1u;
+                mbar_wait(smem_u32(&hdr->tmem_empty[buf]), ((tl >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * buf_cols;
+                uint32_t acc = 0;
+                for (int ki = 0; ki < kiters; ++ki, ++it) {
+                    const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+                    mbar_wait(smem_u32(&hdr->full[slot]), ph);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(stage0 + size_t(slot) * stage_bytes);
+                    const uint32_t w_stage = a_base + p.a_stage_bytes;
+                    if (MODE == MODE_LINEAR) {
+                        const int c = ki;
+                        for (int t = 0; t < taps; ++t) {
+                            // tap (r,s): shift of (r-1) rows and (s-1) pixels inside the landed run
+                            const int shift = taps == 1 ? 0 : ((t / 3 - 1) * Wp + (t % 3 - 1));
+                            const uint32_t a_tap = a_base + uint32_t(p.halo + shift) * 16u;
+                            const uint32_t w_tap = p.w_resident
+                                ? smem_u32(w_res) + uint32_t(t * cin8 + c * planes_per_chunk) * slab_bytes
+                                : w_stage + uint32_t(t * planes_per_chunk) * slab_bytes;
+                            for (int k = 0; k < (planes_per_chunk >> 1); ++k) {
+                                const uint64_t da = umma_desc(a_tap + uint32_t(2 * k) * p.a_plane_bytes, p.a_plane_bytes, 128);
+                                const uint64_t db = umma_desc(w_tap + uint32_t(2 * k) * slab_bytes, slab_bytes, 128);
+                                umma_f16(d_tmem, da, db, idesc, acc);
+                                acc = 1;
+                            }
+                        }
+                    } else {
+                        const int t = ki / p.n_chunks, c = ki % p.n_chunks;
+                        const uint32_t w_tap = p.w_resident
+                            ? smem_u32(w_res) + uint32_t(t * cin8 + c * planes_per_chunk) * slab_bytes
+                            : w_stage;
+                        for (int k = 0; k < (planes_per_chunk >> 1); ++k) {
+                            const uint64_t da = umma_desc(a_base + uint32_t(2 * k) * p.a_plane_bytes, p.a_plane_bytes, 128);
+                            const uint64_t db = umma_desc(w_tap + uint32_t(2 * k) * slab_bytes, slab_bytes, 128);
+                            umma_f16(d_tmem, da, db, idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(smem_u32(&hdr->empty[slot]));      // smem slot free once these MMAs retire
+                }
+                umma_commit(smem_u32(&hdr->tmem_full[buf]));       // accumulator complete
+            }
+        }
+    } else if (warp >= R::kEpiWarp0) {
+        // ============================================================ epilogue (4 warps = 128 TMEM lanes)
+        const int lg = warp & 3;                        // TMEM lane group this warp may access
+        const int row = lg * 32 + lane;
+        const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
+        const int plane0 = (nb * p.n_tile) >> 3;
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
+            const uint32_t buf = tl & 1u;
+            const long long q = (long long)tile * kTileM + row;
+            const int rem = int(q % HpWp_o);
+            const int yy = rem / Wp_o, xx = rem % Wp_o;
+            const bool interior = q < p.P_out && yy >= 1 && yy <= p.Hout && xx >= 1 && xx <= p.Wout;
+            mbar_wait(smem_u32(&hdr->tmem_full[buf]), (tl >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * buf_cols + (uint32_t(lg * 32) << 16);
+            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + uint32_t(c0), v);
+                tmem_ld_wait();
+                if (interior) {
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + hdr->bias[c0 + i];
+                    const long long o0 = ((long long)(plane0 + (c0 >> 3)) * p.out_plane + q) * 8;
+                    if (p.relu == 2) {          // ReLU before the residual add (hrnet_cls.py:473-474)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                    }
+                    if (p.res != nullptr) {
+                        const long long r0 = ((long long)(plane0 + (c0 >> 3)) * p.res_plane + q) * 8;
+                        const uint4 ra = *reinterpret_cast<const uint4*>(p.res + r0);
+                        const uint4 rb = *reinterpret_cast<const uint4*>(p.res + r0 + p.res_plane * 8);
+                        const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 t2 = unpack_half2(rr[i]);
+                            f[2 * i] += t2.x;
+                            f[2 * i + 1] += t2.y;
+                        }
+                    }
+                    if (p.relu == 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                    }
+                    uint4 oa, ob;
+                    oa.x = pack_half2(f[0], f[1]);   oa.y = pack_half2(f[2], f[3]);
+                    oa.z = pack_half2(f[4], f[5]);   oa.w = pack_half2(f[6], f[7]);
+                    ob.x = pack_half2(f[8], f[9]);   ob.y = pack_half2(f[10], f[11]);
+                    ob.z = pack_half2(f[12], f[13]); ob.w = pack_half2(f[14], f[15]);
+                    *reinterpret_cast<uint4*>(p.out + o0) = oa;
+                    *reinterpret_cast<uint4*>(p.out + o0 + p.out_plane * 8) = ob;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
+        }
+    }
+
+    // ---------------------------------------------------------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == R::kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
+    }
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+
+int64_t conv_flops(const poco_conv* d) {
+    return 2ll * d->out.N * d->out.H * d->out.W * d->out.C * d->in.C * d->kh * d->kw;
+}
+
+int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
+    const poco_act &in = d->in, &out = d->out;
+    POCO_CHECK(in.C % 16 == 0 && out.C % 16 == 0, "Cin and Cout must be multiples of 16");
+    POCO_CHECK(in.N == out.N, "batch mismatch");
+    POCO_CHECK(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
+    POCO_CHECK((in.H + 2 * d->pad - d->kh) / d->stride + 1 == out.H && (in.W + 2 * d->pad - d->kw) / d->stride + 1 == out.W,
+               "output geometry does not match the convolution");
+    POCO_CHECK((kTileM + out.W + 3) * 16 <= POCO_ACT_GUARD_BYTES, "tile halo exceeds the activation guard");
+
+    ConvTcParams p{};
+    p.in = static_cast<const __half*>(in.data);
+    p.in_plane = in.plane_stride;
+    p.Hin = in.H; p.Win = in.W;
+    p.out = static_cast<__half*>(out.data);
+    p.out_plane = out.plane_stride;
+    p.Hout = out.H; p.Wout = out.W;
+    p.res = static_cast<const __half*>(d->residual);
+    p.res_plane = d->res_plane_stride;
+    p.w = static_cast<const __half*>(d->weight);
+    p.bias = d->bias;
+    p.Cin = in.C; p.Cout = out.C;
+    p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad;
+    p.relu = d->relu;
+    p.P_out = int64_t(out.N) * (out.H + 2) * (out.W + 2);
+    p.num_m_tiles = int((p.P_out + kTileM - 1) / kTileM);
+
+    // N blocking: largest multiple-of-16 divisor of Cout that is <= 256
+    int n_tile = 0;
+    for (int t = std::min(256, out.C); t >= 16; t -= 16)
+        if (out.C % t == 0) { n_tile = t; break; }
+    POCO_CHECK(n_tile > 0, "no valid N tile");
+    p.n_tile = n_tile;
+    const int n_blocks = out.C / n_tile;
+    int cols = 32;
+    while (cols < 2 * n_tile) cols <<= 1;
+    p.tmem_cols = cols;
+
+    const int taps = d->kh * d->kw;
+    const bool linear = d->stride == 1 && in.H == out.H && in.W == out.W &&
+                        ((d->kh == 3 && d->kw == 3 && d->pad == 1) || (d->kh == 1 && d->kw == 1 && d->pad == 0));
+    const int mode = linear ? MODE_LINEAR : MODE_GATHER;
+    const int budget = kSmemBudget - kHeaderBytes;
+    const int w_total = taps * in.C * n_tile * 2;
+
+    if (mode == MODE_LINEAR) {
+        p.halo = taps == 9 ? (out.W + 2) + 1 : 0;
+        p.a_copy_bytes = (kTileM + 2 * p.halo) * 16;
+        p.a_plane_bytes = round_up(p.a_copy_bytes, 128);
+    } else {
+        p.halo = 0;
+        p.a_copy_bytes = kTileM * 16;
+        p.a_plane_bytes = kTileM * 16;
+    }
+    // choose K chunk, residency and stage count
+    bool found = false;
+    const int kcs[4] = {64, 48, 32, 16};
+    for (int resident = 1; resident >= 0 && !found; --resident) {
+        if (resident && w_total > 112 * 1024) continue;
+        for (int ki = 0; ki < 4 && !found; ++ki) {
+            const int kc = kcs[ki];
+            if (in.C % kc != 0) continue;
+            const int a_stage = (kc / 8) * p.a_plane_bytes;
+            const int w_stage = resident ? 0 : (mode == MODE_LINEAR ? taps : 1) * kc * n_tile * 2;
+            const int avail = budget - (resident ? round_up(w_total, 128) : 0);
+            const int min_stages = mode == MODE_GATHER ? kGatherLag + 1 : 2;
+            int stages = std::min(mode == MODE_GATHER ? 6 : 4, avail / (a_stage + w_stage));
+            if (stages < min_stages) continue;
+            p.kc = kc; p.n_chunks = in.C / kc;
+            p.w_resident = resident;
+            p.w_res_bytes = resident ? round_up(w_total, 128) : 0;
+            p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
+            p.stages = stages;
+            found = true;
+        }
+    }
+    POCO_CHECK(found, "no shared-memory configuration fits this convolution");
+    // slabs are n_tile*16 bytes (a multiple of 256), so the resident region needs no padding and
+    // w_res_bytes is both the region size and the mbarrier transaction count
+    POCO_CHECK(!p.w_resident || p.w_res_bytes == w_total, "weight slab total must be 128-byte aligned");
+    const size_t smem = size_t(kHeaderBytes) + p.w_res_bytes + size_t(p.stages) * (p.a_stage_bytes + p.w_stage_bytes);
+    dim3 grid(std::max(1, std::min(p.num_m_tiles, num_sms() / n_blocks)), n_blocks);
+    const ConvTcParams& pk = p;
+    static std::once_flag once[2];
+    if (mode == MODE_LINEAR) {
+        std::call_once(once[0], [] {
+            cudaFuncSetAttribute(conv_tc_kernel<MODE_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        });
+        conv_tc_kernel<MODE_LINEAR><<<grid, Roles<MODE_LINEAR>::kThreads, smem, s>>>(pk);
+    } else {
+        std::call_once(once[1], [] {
+            cudaFuncSetAttribute(conv_tc_kernel<MODE_GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        });
+        conv_tc_kernel<MODE_GATHER><<<grid, Roles<MODE_GATHER>::kThreads, smem, s>>>(pk);
+    }
+    POCO_LAUNCHED();
+    return 0;
+}
+
+}  // namespace poco

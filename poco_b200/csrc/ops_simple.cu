@@ -1,0 +1,317 @@
+// poco_b200 -- bandwidth-bound layout / pooling / resampling kernels on the planar-8 padded fp16
+// activation layout, plus the CUDA-core debug convolution.  All of them move 16 bytes (8 channels
+// of one pixel) per thread access; consecutive threads touch consecutive pixels of a plane, so a
+// warp reads / writes 512 contiguous bytes.
+#include <algorithm>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace poco {
+
+namespace {
+
+struct Act {
+    __half* data;
+    long long plane;
+    int C, N, H, W;
+};
+inline Act mk(const poco_act& a) { return Act{static_cast<__half*>(a.data), a.plane_stride, a.C, a.N, a.H, a.W}; }
+
+__device__ __forceinline__ long long pix_index(const Act& a, int n, int y, int x) {
+    return (long long)n * (a.H + 2) * (a.W + 2) + (long long)(y + 1) * (a.W + 2) + (x + 1);
+}
+__device__ __forceinline__ uint4 ld16(const Act& a, int plane, long long pix) {
+    return *reinterpret_cast<const uint4*>(a.data + ((long long)plane * a.plane + pix) * 8);
+}
+__device__ __forceinline__ void st16(const Act& a, int plane, long long pix, uint4 v) {
+    *reinterpret_cast<uint4*>(a.data + ((long long)plane * a.plane + pix) * 8) = v;
+}
+__device__ __forceinline__ void unpack8(uint4 v, float* f) {
+    float2 t;
+    t = unpack_half2(v.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_half2(v.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_half2(v.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_half2(v.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 v;
+    v.x = pack_half2(f[0], f[1]); v.y = pack_half2(f[2], f[3]);
+    v.z = pack_half2(f[4], f[5]); v.w = pack_half2(f[6], f[7]);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug convolution (CUDA cores, fp32 accumulate): one thread = one output pixel x 8 output channels
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_ref_kernel(Act in, Act out, const __half* __restrict__ w, const float* __restrict__ bias,
+                                const __half* __restrict__ res, long long res_plane, int kh, int kw, int stride,
+                                int pad, int relu) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long)out.N * out.H * out.W;
+    if (idx >= npix) return;
+    const int co8 = blockIdx.y;
+    const int x = int(idx % out.W), y = int((idx / out.W) % out.H), n = int(idx / ((long long)out.W * out.H));
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bias[co8 * 8 + i];
+    const int cin8 = in.C >> 3;
+    for (int t = 0; t < kh * kw; ++t) {
+        const int yi = y * stride + t / kw - pad, xi = x * stride + t % kw - pad;
+        if (yi < 0 || yi >= in.H || xi < 0 || xi >= in.W) continue;
+        const long long ip = pix_index(in, n, yi, xi);
+        for (int c8 = 0; c8 < cin8; ++c8) {
+            float a[8];
+            unpack8(ld16(in, c8, ip), a);
+            const uint4* wp = reinterpret_cast<const uint4*>(w + ((long long)(t * cin8 + c8) * out.C + co8 * 8) * 8);
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                float wf[8];
+                unpack8(__ldg(wp + o), wf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[o] = fmaf(a[i], wf[i], acc[o]);
+            }
+        }
+    }
+    const long long op = pix_index(out, n, y, x);
+    if (relu == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    }
+    if (res != nullptr) {
+        float r[8];
+        unpack8(*reinterpret_cast<const uint4*>(res + ((long long)co8 * res_plane + op) * 8), r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += r[i];
+    }
+    if (relu == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    }
+    st16(out, co8, op, pack8(acc));
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_image_kernel(const float* __restrict__ img, Act out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long)out.N * out.H * out.W;
+    if (idx >= npix) return;
+    const int x = int(idx % out.W), y = int((idx / out.W) % out.H), n = int(idx / ((long long)out.W * out.H));
+    const long long hw = (long long)out.H * out.W;
+    const float* src = img + (long long)n * 3 * hw + (long long)y * out.W + x;
+    float f[8] = {src[0], src[hw], src[2 * hw], 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long op = pix_index(out, n, y, x);
+    st16(out, 0, op, pack8(f));
+    for (int pl = 1; pl < (out.C >> 3); ++pl) st16(out, pl, op, make_uint4(0, 0, 0, 0));
+}
+
+struct FuseArgs {
+    Act out;
+    Act in[POCO_MAX_FUSE_INPUTS];
+    int shift[POCO_MAX_FUSE_INPUTS];
+    int n_in, relu;
+};
+__global__ void fuse_sum_kernel(FuseArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long)a.out.N * a.out.H * a.out.W;
+    if (idx >= npix) return;
+    const int pl = blockIdx.y;
+    const int x = int(idx % a.out.W), y = int((idx / a.out.W) % a.out.H), n = int(idx / ((long long)a.out.W * a.out.H));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < a.n_in; ++k) {
+        float f[8];
+        unpack8(ld16(a.in[k], pl, pix_index(a.in[k], n, y >> a.shift[k], x >> a.shift[k])), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+    if (a.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    }
+    st16(a.out, pl, pix_index(a.out, n, y, x), pack8(acc));
+}
+
+// bilinear x2, align_corners=True: src = dst * (in-1)/(out-1)  (matches aten upsample_bilinear2d)
+__global__ void upsample2x_kernel(Act in, Act out, float sy, float sx) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long)out.N * out.H * out.W;
+    if (idx >= npix) return;
+    const int pl = blockIdx.y;
+    const int x = int(idx % out.W), y = int((idx / out.W) % out.H), n = int(idx / ((long long)out.W * out.H));
+    const float fy = sy * y, fx = sx * x;
+    const int y0 = min(int(fy), in.H - 1), x0 = min(int(fx), in.W - 1);
+    const int y1 = min(y0 + 1, in.H - 1), x1 = min(x0 + 1, in.W - 1);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    float a[8], b[8], c[8], d[8], o[8];
+    unpack8(ld16(in, pl, pix_index(in, n, y0, x0)), a);
+    unpack8(ld16(in, pl, pix_index(in, n, y0, x1)), b);
+    unpack8(ld16(in, pl, pix_index(in, n, y1, x0)), c);
+    unpack8(ld16(in, pl, pix_index(in, n, y1, x1)), d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+    st16(out, pl, pix_index(out, n, y, x), pack8(o));
+}
+
+__global__ void maxpool_kernel(Act in, Act out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long)out.N * out.H * out.W;
+    if (idx >= npix) return;
+    const int pl = blockIdx.y;
+    const int x = int(idx % out.W), y = int((idx / out.W) % out.H), n = int(idx / ((long long)out.W * out.H));
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int yi = 2 * y + dy, xi = 2 * x + dx;
+            if (yi < 0 || yi >= in.H || xi < 0 || xi >= in.W) continue;
+            float f[8];
+            unpack8(ld16(in, pl, pix_index(in, n, yi, xi)), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+        }
+    st16(out, pl, pix_index(out, n, y, x), pack8(m));
+}
+
+// one warp per (crop, plane): mean over H*W of 8 channels
+__global__ void avgpool_kernel(Act in, float* __restrict__ out, long long ld) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int planes = in.C >> 3;
+    if (warp >= in.N * planes) return;
+    const int n = warp / planes, pl = warp % planes;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int hw = in.H * in.W;
+    for (int i = lane; i < hw; i += 32) {
+        float f[8];
+        unpack8(ld16(in, pl, pix_index(in, n, i / in.W, i % in.W)), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[k] = v;
+    }
+    if (lane < 8) out[(long long)n * ld + pl * 8 + lane] = acc[lane] / float(hw);
+}
+
+__global__ void unpack_kernel(Act in, float* __restrict__ out, int c_valid) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long)in.N * in.H * in.W;
+    if (idx >= npix) return;
+    const int pl = blockIdx.y;
+    const int x = int(idx % in.W), y = int((idx / in.W) % in.H), n = int(idx / ((long long)in.W * in.H));
+    float f[8];
+    unpack8(ld16(in, pl, pix_index(in, n, y, x)), f);
+    const long long hw = (long long)in.H * in.W;
+    for (int i = 0; i < 8; ++i) {
+        const int c = pl * 8 + i;
+        if (c < c_valid) out[((long long)n * c_valid + c) * hw + (long long)y * in.W + x] = f[i];
+    }
+}
+
+inline unsigned blocks_for(long long n, int bs) { return unsigned((n + bs - 1) / bs); }
+
+}  // namespace
+
+int check_act(const poco_act& a, const char* what) {
+    POCO_CHECK(a.data != nullptr, std::string(what) + ": null data");
+    POCO_CHECK(a.C > 0 && a.C % 8 == 0, std::string(what) + ": channels must be a positive multiple of 8");
+    POCO_CHECK(a.N > 0 && a.H > 0 && a.W > 0, std::string(what) + ": empty tensor");
+    POCO_CHECK(a.plane_stride >= int64_t(a.N) * (a.H + 2) * (a.W + 2), std::string(what) + ": plane stride too small");
+    POCO_CHECK((reinterpret_cast<uintptr_t>(a.data) & 15) == 0, std::string(what) + ": data must be 16-byte aligned");
+    return 0;
+}
+
+int conv_ref_launch(const poco_conv* d, cudaStream_t s) {
+    POCO_CHECK(d->in.N == d->out.N, "batch mismatch");
+    POCO_CHECK((d->in.H + 2 * d->pad - d->kh) / d->stride + 1 == d->out.H &&
+                   (d->in.W + 2 * d->pad - d->kw) / d->stride + 1 == d->out.W,
+               "output geometry does not match the convolution");
+    const long long npix = (long long)d->out.N * d->out.H * d->out.W;
+    dim3 grid(blocks_for(npix, 128), d->out.C / 8);
+    conv_ref_kernel<<<grid, 128, 0, s>>>(mk(d->in), mk(d->out), static_cast<const __half*>(d->weight), d->bias,
+                                        static_cast<const __half*>(d->residual), d->res_plane_stride, d->kh, d->kw,
+                                        d->stride, d->pad, d->relu);
+    POCO_LAUNCHED();
+    return 0;
+}
+
+}  // namespace poco
+
+using namespace poco;
+
+extern "C" int poco_pack_image_run(const poco_pack_image* d, void* stream) {
+    if (check_act(d->out, "out")) return 1;
+    POCO_CHECK(d->img != nullptr, "null image");
+    const long long npix = (long long)d->out.N * d->out.H * d->out.W;
+    pack_image_kernel<<<blocks_for(npix, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d->img, mk(d->out));
+    POCO_LAUNCHED();
+    return 0;
+}
+
+extern "C" int poco_fuse_sum_run(const poco_fuse_sum* d, void* stream) {
+    if (check_act(d->out, "out")) return 1;
+    POCO_CHECK(d->n_in >= 1 && d->n_in <= POCO_MAX_FUSE_INPUTS, "n_in out of range");
+    FuseArgs a;
+    a.out = mk(d->out);
+    a.n_in = d->n_in;
+    a.relu = d->relu;
+    for (int k = 0; k < d->n_in; ++k) {
+        if (check_act(d->in[k], "in")) return 1;
+        POCO_CHECK(d->in[k].C == d->out.C && d->in[k].N == d->out.N, "fuse input channel/batch mismatch");
+        POCO_CHECK(d->shift[k] >= 0 && (d->in[k].H << d->shift[k]) == d->out.H && (d->in[k].W << d->shift[k]) == d->out.W,
+                   "fuse input resolution mismatch");
+        a.in[k] = mk(d->in[k]);
+        a.shift[k] = d->shift[k];
+    }
+    const long long npix = (long long)d->out.N * d->out.H * d->out.W;
+    dim3 grid(blocks_for(npix, 256), d->out.C / 8);
+    fuse_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    POCO_LAUNCHED();
+    return 0;
+}
+
+extern "C" int poco_upsample2x_run(const poco_upsample2x* d, void* stream) {
+    if (check_act(d->in, "in") || check_act(d->out, "out")) return 1;
+    POCO_CHECK(d->out.H == 2 * d->in.H && d->out.W == 2 * d->in.W && d->out.C == d->in.C && d->out.N == d->in.N,
+               "upsample geometry mismatch");
+    const float sy = d->out.H > 1 ? float(d->in.H - 1) / float(d->out.H - 1) : 0.f;
+    const float sx = d->out.W > 1 ? float(d->in.W - 1) / float(d->out.W - 1) : 0.f;
+    const long long npix = (long long)d->out.N * d->out.H * d->out.W;
+    dim3 grid(blocks_for(npix, 256), d->out.C / 8);
+    upsample2x_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(d->in), mk(d->out), sy, sx);
+    POCO_LAUNCHED();
+    return 0;
+}
+
+extern "C" int poco_maxpool_run(const poco_maxpool* d, void* stream) {
+    if (check_act(d->in, "in") || check_act(d->out, "out")) return 1;
+    POCO_CHECK(d->out.H == (d->in.H + 2 - 3) / 2 + 1 && d->out.W == (d->in.W + 2 - 3) / 2 + 1 && d->out.C == d->in.C,
+               "maxpool geometry mismatch");
+    const long long npix = (long long)d->out.N * d->out.H * d->out.W;
+    dim3 grid(blocks_for(npix, 256), d->out.C / 8);
+    maxpool_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(d->in), mk(d->out));
+    POCO_LAUNCHED();
+    return 0;
+}
+
+extern "C" int poco_avgpool_run(const poco_avgpool* d, void* stream) {
+    if (check_act(d->in, "in")) return 1;
+    POCO_CHECK(d->out != nullptr && d->ld >= d->in.C, "bad output");
+    const long long warps = (long long)d->in.N * (d->in.C / 8);
+    avgpool_kernel<<<blocks_for(warps * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(d->in), d->out, d->ld);
+    POCO_LAUNCHED();
+    return 0;
+}
+
+extern "C" int poco_unpack_run(const poco_unpack* d, void* stream) {
+    if (check_act(d->in, "in")) return 1;
+    POCO_CHECK(d->out != nullptr && d->c_valid > 0 && d->c_valid <= d->in.C, "bad output");
+    const long long npix = (long long)d->in.N * d->in.H * d->in.W;
+    dim3 grid(blocks_for(npix, 256), (d->c_valid + 7) / 8);
+    unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(d->in), d->out, d->c_valid);
+    POCO_LAUNCHED();
+    return 0;
+}

@@ -1,0 +1,298 @@
+"""Host-side plan builder: turns a POCO state dict + batch size into the static op schedule that
+libpoco_b200.so replays (include/poco_b200.h `poco_plan`).
+
+Tensor plumbing only (allowed to be torch): device buffers, BatchNorm folding, weight repacking
+into the kernel layout, and the list of op descriptors.  No arithmetic of the hot path runs here.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+BN_EPS = 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# planar-8 padded activation tensors
+# ------------------------------------------------------------------------------------------------
+class ActT:
+    """[C/8][N][H+2][W+2][8] fp16 view into a torch buffer (see include/poco_b200.h)."""
+
+    def __init__(self, buf, ptr, C_, N, H, W, plane_stride, cap_planes, root=None):
+        self.buf, self.ptr = buf, ptr
+        self.C, self.N, self.H, self.W = C_, N, H, W
+        self.plane_stride = plane_stride
+        self.cap_planes = cap_planes
+        self.root = root or self
+
+    def desc(self):
+        return L.Act(self.ptr, self.plane_stride, self.C, self.N, self.H, self.W)
+
+    def channels(self, c0, c1):
+        """channel-slice view (free torch.cat / torch.split: planes are contiguous)"""
+        assert c0 % 8 == 0 and c1 % 8 == 0 and 0 <= c0 < c1 <= self.C
+        return ActT(self.buf, self.ptr + (c0 // 8) * self.plane_stride * 16, c1 - c0, self.N, self.H, self.W,
+                    self.plane_stride, 0, self.root)
+
+    def retype(self, C_):
+        """same buffer, fewer channels (pool reuse)"""
+        assert C_ % 8 == 0 and C_ // 8 <= self.cap_planes
+        return ActT(self.buf, self.ptr, C_, self.N, self.H, self.W, self.plane_stride, self.cap_planes, None)
+
+
+def alloc_act(C_, N, H, W, device):
+    assert C_ % 8 == 0
+    plane = N * (H + 2) * (W + 2)
+    guard = L.ACT_GUARD_BYTES // 2
+    buf = torch.zeros(guard + (C_ // 8) * plane * 8 + guard, dtype=torch.float16, device=device)
+    return ActT(buf, buf.data_ptr() + L.ACT_GUARD_BYTES, C_, N, H, W, plane, C_ // 8)
+
+
+def to_planar(x, c_pad=None):
+    """torch reference of the layout (tests / debugging): NCHW float -> ActT on x.device"""
+    N, C_, H, W = x.shape
+    Cp = c_pad or ((C_ + 7) // 8 * 8)
+    a = alloc_act(Cp, N, H, W, x.device)
+    v = act_view(a)
+    xp = torch.zeros(N, Cp, H, W, dtype=torch.float16, device=x.device)
+    xp[:, :C_] = x.to(torch.float16)
+    v[:, :, 1:H + 1, 1:W + 1, :] = xp.view(N, Cp // 8, 8, H, W).permute(1, 0, 3, 4, 2)
+    return a
+
+
+def act_view(a):
+    """[C/8, N, H+2, W+2, 8] torch view of an (unsliced) ActT"""
+    guard = L.ACT_GUARD_BYTES // 2
+    off = (a.ptr - a.buf.data_ptr()) // 2
+    assert off >= guard
+    n = (a.C // 8) * a.plane_stride * 8
+    flat = a.buf[off:off + n]
+    return flat.view(a.C // 8, a.plane_stride, 8)[:, :a.N * (a.H + 2) * (a.W + 2)].reshape(
+        a.C // 8, a.N, a.H + 2, a.W + 2, 8)
+
+
+def from_planar(a):
+    """ActT -> NCHW float32 torch tensor (tests / debugging)"""
+    v = act_view(a)[:, :, 1:a.H + 1, 1:a.W + 1, :]
+    return v.permute(1, 0, 4, 2, 3).reshape(a.N, a.C, a.H, a.W).float()
+
+
+# ------------------------------------------------------------------------------------------------
+# weight preparation
+# ------------------------------------------------------------------------------------------------
+def fold_bn(w, conv_bias, bn):
+    """w' = w * g/sqrt(v+eps),  b' = beta + (conv_bias - mean) * g/sqrt(v+eps)   (fp32, before the fp16 cast)"""
+    w = w.float()
+    cout = w.shape[0]
+    b = conv_bias.float() if conv_bias is not None else torch.zeros(cout, device=w.device)
+    if bn is not None:
+        g, beta, mean, var = (t.float() for t in bn)
+        s = g / torch.sqrt(var + BN_EPS)
+        w = w * s.view(-1, 1, 1, 1)
+        b = beta + (b - mean) * s
+    return w, b
+
+
+def pack_conv_weight(w, cin_pad=None):
+    """[Cout, Cin, kh, kw] f32 -> fp16 [kh*kw][Cin/8][Cout][8] (UMMA no-swizzle K-major B slabs)"""
+    cout, cin, kh, kw = w.shape
+    cp = cin_pad or cin
+    if cp != cin:
+        w = torch.cat([w, w.new_zeros(cout, cp - cin, kh, kw)], 1)
+    assert cp % 16 == 0 and cout % 16 == 0, (cin, cout)
+    p = w.permute(2, 3, 1, 0).reshape(kh * kw, cp // 8, 8, cout).permute(0, 1, 3, 2)
+    return p.contiguous().to(torch.float16)
+
+
+def pack_realnvp(sd, prefix='flow_head.flow.'):
+    """flat fp32 parameter block of poco_realnvp (include/poco_b200.h)"""
+    mask = sd[prefix + 'mask']
+    parts = []
+    for i in range(mask.shape[0]):
+        parts.append(mask[i].reshape(-1))
+        for net in ('s', 't'):
+            for l in ('0', '2', '4'):
+                parts.append(sd[f'{prefix}{net}.{i}.{l}.weight'].reshape(-1))
+                parts.append(sd[f'{prefix}{net}.{i}.{l}.bias'].reshape(-1))
+    return torch.cat([p.float() for p in parts]).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# plan builder
+# ------------------------------------------------------------------------------------------------
+class PlanBuilder:
+    """Backend of poco_b200.arch: every arch function call appends one op descriptor."""
+
+    mode = 'plan'
+
+    def __init__(self, sd, N, device, conv_impl=0):
+        self.sd = sd
+        self.N = N
+        self.device = torch.device(device)
+        self.ops = []
+        self.keep = []          # torch tensors the descriptors point into
+        self.free_pool = {}     # (H, W) -> [root ActT]
+        self.conv_impl = conv_impl
+        self.conv_log = []
+
+    # -- buffers
+    def act(self, C_, H, W):
+        pool = self.free_pool.get((H, W), [])
+        best = None
+        for a in pool:
+            if a.cap_planes >= C_ // 8 and (best is None or a.cap_planes < best.cap_planes):
+                best = a
+        if best is not None:
+            pool.remove(best)
+            return best.retype(C_) if best.C != C_ else best
+        a = alloc_act(C_, self.N, H, W, self.device)
+        self.keep.append(a.buf)
+        return a
+
+    def free(self, a):
+        """return the buffer behind `a` to the pool (safe: ops run in program order on one stream)"""
+        root = a.root
+        if root is not a and a.ptr != root.ptr:
+            return
+        full = ActT(root.buf, root.ptr, root.cap_planes * 8, root.N, root.H, root.W, root.plane_stride, root.cap_planes)
+        lst = self.free_pool.setdefault((root.H, root.W), [])
+        if all(x.buf is not full.buf for x in lst):
+            lst.append(full)
+
+    def f32(self, *shape):
+        t = torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def dev(self, t, dtype=torch.float32):
+        t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    def add(self, desc):
+        self.ops.append(L.make_op(desc))
+
+    # -- ops
+    def pack_image(self, img, H, W):
+        out = self.act(16, H, W)
+        self.add(L.PackImage(img.data_ptr(), out.desc()))
+        return out
+
+    def conv_bn(self, x, conv, bn, cin, cout, k, stride=1, relu=True, residual=None, out=None, pad=None, bias=False):
+        """conv (+bias) + eval BatchNorm folded, + residual, ReLU.  `conv` / `bn` may be lists: several
+        convs reading the same input run as one launch with their output channels concatenated."""
+        sd = self.sd
+        convs = conv if isinstance(conv, (list, tuple)) else [conv]
+        bns = bn if isinstance(bn, (list, tuple)) else [bn] * len(convs)
+        ws, bs = [], []
+        for cv, b_ in zip(convs, bns):
+            w = sd[cv + '.weight'].to(self.device)
+            assert tuple(w.shape) == (cout // len(convs), cin, k, k), (cv, tuple(w.shape), (cout, cin, k, k))
+            cb = sd.get(cv + '.bias')
+            assert (cb is not None) == bool(bias), f'{cv}: conv bias presence mismatch'
+            bnp = None
+            if b_ is not None:
+                bnp = tuple(sd[b_ + s].to(self.device) for s in ('.weight', '.bias', '.running_mean', '.running_var'))
+            wf, bf = fold_bn(w, cb.to(self.device) if cb is not None else None, bnp)
+            ws.append(wf)
+            bs.append(bf)
+        wp = pack_conv_weight(torch.cat(ws, 0), cin_pad=x.C)
+        bf = torch.cat(bs, 0).contiguous()
+        self.keep += [wp, bf]
+        pad = k // 2 if pad is None else pad
+        Ho = (x.H + 2 * pad - k) // stride + 1
+        Wo = (x.W + 2 * pad - k) // stride + 1
+        if out is None:
+            out = self.act(cout, Ho, Wo)
+        assert (out.C, out.H, out.W) == (cout, Ho, Wo), (conv, (out.C, out.H, out.W), (cout, Ho, Wo))
+        if residual is not None:
+            assert (residual.C, residual.H, residual.W) == (cout, Ho, Wo), conv
+        d = L.Conv(x.desc(), out.desc(), wp.data_ptr(), bf.data_ptr(),
+                   residual.ptr if residual is not None else None,
+                   residual.plane_stride if residual is not None else 0,
+                   k, k, stride, pad, int(relu), self.conv_impl)
+        self.add(d)
+        self.conv_log.append((convs[0], x.C, cout, k, stride, x.H, Ho))
+        return out
+
+    def fuse_sum(self, terms, relu, out=None):
+        """terms: list of (ActT, shift)"""
+        a0 = terms[0][0]
+        H, W = a0.H << terms[0][1], a0.W << terms[0][1]
+        if out is None:
+            out = self.act(a0.C, H, W)
+        d = L.FuseSum()
+        d.out = out.desc()
+        for i, (a, s) in enumerate(terms):
+            d.in_[i] = a.desc()
+            d.shift[i] = s
+        d.n_in = len(terms)
+        d.relu = 1 if relu else 0
+        self.add(d)
+        return out
+
+    def upsample2x(self, x):
+        out = self.act(x.C, 2 * x.H, 2 * x.W)
+        self.add(L.Upsample2x(x.desc(), out.desc()))
+        return out
+
+    def maxpool(self, x):
+        out = self.act(x.C, (x.H - 1) // 2 + 1, (x.W - 1) // 2 + 1)
+        self.add(L.MaxPool(x.desc(), out.desc()))
+        return out
+
+    def avgpool(self, x, out, col=0):
+        """-> columns [col, col+C) of the f32 matrix `out` [N, ld]"""
+        self.add(L.AvgPool(x.desc(), out.data_ptr() + 4 * col, out.stride(0)))
+
+    def unpack(self, x, c_valid=None):
+        out = self.f32(self.N, c_valid or x.C, x.H, x.W)
+        self.add(L.Unpack(x.desc(), out.data_ptr(), c_valid or x.C))
+        return out
+
+    def linear(self, x, xcol, I, wkey, y, ycol, act=0, res=None, rescol=0):
+        """y[:, ycol:ycol+O] = act(x[:, xcol:xcol+I] W^T + b) (+ res[:, rescol:rescol+O])"""
+        w = self.dev(self.sd[wkey + '.weight'])
+        b = self.dev(self.sd[wkey + '.bias'])
+        O = w.shape[0]
+        assert w.shape[1] == I, (wkey, tuple(w.shape), I)
+        self.add(L.Linear(x.data_ptr() + 4 * xcol, x.stride(0), w.data_ptr(), b.data_ptr(),
+                          (res.data_ptr() + 4 * rescol) if res is not None else None,
+                          res.stride(0) if res is not None else 0,
+                          y.data_ptr() + 4 * ycol, y.stride(0), x.shape[0], I, O, act))
+
+    def copy2d(self, src, scol, dst, dcol, cols, bcast=False):
+        self.add(L.Copy2d(src.data_ptr() + 4 * scol, src.stride(0), dst.data_ptr() + 4 * dcol, dst.stride(0),
+                          dst.shape[0], cols, 1 if bcast else 0))
+
+    def rot6d(self, x, xcol, per_row, out):
+        self.add(L.Rot6d(x.data_ptr() + 4 * xcol, x.stride(0), per_row, x.shape[0] * per_row, out.data_ptr()))
+
+
+class Plan:
+    """Owns the C plan handle plus every device buffer its descriptors point into."""
+
+    def __init__(self, builder):
+        self.keep = builder.keep
+        self.ops = builder.ops
+        n = len(builder.ops)
+        arr = (L.Op * n)(*builder.ops)
+        h = C.c_void_p()
+        L.check(L.lib().poco_plan_create(arr, n, C.byref(h)))
+        self.handle = h
+        self.num_ops = n
+        self.flops = int(L.lib().poco_plan_flops(h))
+        self.conv_log = builder.conv_log
+
+    def run(self, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        L.check(L.lib().poco_plan_run(self.handle, C.c_void_p(s)))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.lib().poco_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

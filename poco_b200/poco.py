@@ -1,0 +1,466 @@
+"""poco_b200.POCO -- drop-in for pocolib.models.POCO (reference poco.py:12-154).
+
+Same constructor signature, same sub-module names (backbone / head / smpl / uncert_head / flow_head),
+same state-dict key names and the same `forward(batch) -> dict`, but forward() does not execute
+torch.nn modules: it replays a static op schedule (engine.Plan) of hand-written sm_100a kernels
+through the C ABI in include/poco_b200.h.  There is no CPU / eager fallback.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import arch
+from .engine import Plan, PlanBuilder, pack_realnvp
+from .smpl import make_smpl_stage
+
+SMPL_MEAN_PARAMS = 'data/smpl_mean_params.npz'      # reference: pocolib/core/config.py:37
+
+
+class ParamTree(nn.Module):
+    """Container that holds parameters / buffers under dotted reference names."""
+
+    def register(self, path, tensor, kind):
+        parts = path.split('.')
+        node = self
+        for p in parts[:-1]:
+            if p not in node._modules:
+                node.add_module(p, ParamTree())
+            node = node._modules[p]
+        if kind == 'param':
+            node.register_parameter(parts[-1], nn.Parameter(tensor))
+        else:
+            node.register_buffer(parts[-1], tensor)
+
+    def forward(self, *a, **k):
+        raise RuntimeError('poco_b200 sub-modules hold parameters only; call POCO.forward')
+
+
+def _load_mean_params(src):
+    if src is None:
+        src = os.environ.get('POCO_SMPL_MEAN_PARAMS', SMPL_MEAN_PARAMS)
+    if isinstance(src, (str, os.PathLike)):
+        src = np.load(src)
+    return {k: np.asarray(src[k], np.float32) for k in ('pose', 'shape', 'cam')}
+
+
+def _flow_masks(kind, num_rv, layers):
+    """nf_head.py:20-29"""
+    if kind == 'alter':
+        a = [i % 2 for i in range(num_rv)]
+        b = [(i + 1) % 2 for i in reversed(range(num_rv))]
+    elif kind == 'new':
+        sp = math.floor(num_rv / 2)
+        a = [min(i // sp, 1) for i in range(num_rv)]
+        b = [min(i // sp, 1) for i in reversed(range(num_rv))]
+    elif kind == 'old':
+        sp = math.ceil(num_rv / 2)
+        a = [i // sp for i in range(num_rv)]
+        b = [i // sp for i in reversed(range(num_rv))]
+    else:
+        raise NameError(f'get_{kind}_masks')
+    return torch.tensor([a, b] * layers, dtype=torch.float32)
+
+
+class POCO(nn.Module):
+    def __init__(
+            self,
+            backbone='resnet50',
+            img_res=224,
+            uncert_layer='diff_branch',
+            activation_type='sigmoid',
+            uncert_type=['pose'],
+            uncert_inp_type='feat',
+            loss_ver='gauss_sigma',
+            num_neurons='1024-512',
+            num_flow_layers=3,
+            sigma_dim=9,
+            num_nf_rv=9,
+            mask_params_id='',
+            nflow_mask_type='',
+            exclude_uncert_idx='',
+            use_dropout=False,
+            use_iter_feats=False,
+            cond_nflow=False,
+            context_dim=1024,
+            gt_pose_cond=False,
+            gt_pose_cond_ds='h36m',
+            gt_pose_cond_ratio=0.25,
+            pretrained=None,
+            inf_model='best',
+            is_test=True,
+            # extensions (keyword-only in practice; defaults reproduce the reference behaviour)
+            smpl_mean_params=None,
+            smpl=None,
+            use_cuda_graph=None,
+    ):
+        super().__init__()
+        self.backbone_name, self.head_name = backbone.split('-')
+        if self.backbone_name not in arch.BACKBONES:
+            raise NameError(f"backbone '{self.backbone_name}' is not built in poco_b200 "
+                            f"(available: {sorted(arch.BACKBONES)})")
+        if self.head_name not in ('pare', 'cliff'):
+            raise NameError(f"head '{self.head_name}' is not built in poco_b200 (available: pare, cliff)")
+        self.num_output_channels = arch.BACKBONES[self.backbone_name][1]
+        self.img_res = img_res
+        self.uncert_layer = uncert_layer
+        self.num_neurons = list(map(int, filter(None, num_neurons.split('-'))))
+        self.num_flow_layers = num_flow_layers
+        self.sigma_dim = sigma_dim
+        self.num_nf_rv = num_nf_rv
+        self.mask_params_id = mask_params_id
+        self.nflow_mask_type = nflow_mask_type
+        self.exclude_uncert_idx = list(filter(None, exclude_uncert_idx.split('-')))
+        self.activation_type = activation_type
+        self.use_dropout = use_dropout
+        self.use_iter_feats = False if self.backbone_name.startswith('hrnet') else use_iter_feats
+        self.uncert_type = uncert_type
+        self.uncert_inp_type = uncert_inp_type
+        self.cond_nflow = cond_nflow
+        self.context_dim = context_dim
+        self.gt_pose_cond = gt_pose_cond
+        self.gt_pose_cond_ds = gt_pose_cond_ds
+        self.gt_pose_cond_ratio = gt_pose_cond_ratio
+        self.loss_ver = loss_ver
+        self.inf_model = inf_model
+        self.is_test = is_test
+        if img_res != 224:
+            raise ValueError('poco_b200 is built for 224x224 crops (DATASET.IMG_RES, config.py:115)')
+        if uncert_layer != 'diff_branch':
+            raise NotImplementedError("only uncert_layer='diff_branch' (both demo configs) is built")
+        if self.exclude_uncert_idx:
+            raise NotImplementedError('exclude_uncert_idx is not built (empty in both demo configs)')
+        if 'norm_flow' in loss_ver and 'pose' not in uncert_type:
+            raise SystemExit(f'Normalizing flow for {uncert_type} is not defined')      # nf_head.py:66-68
+
+        # width of head_output['uncert_feat'] == head.get_output_channels().  The reference hard-codes
+        # 2048 for cliff_head (cliff_head.py:129-132), which crashes hrnet_w32-cliff; we use the true
+        # pooled width (documented deviation).
+        self.uncert_feat_dim = 24 * 128 if self.head_name == 'pare' else self.num_output_channels
+        # poco_head.get_num_uncertainty_outputs (poco_head.py:84-94)
+        sd_eff = sigma_dim if 'norm_flow' in loss_ver else 1
+        mult = 2 if loss_ver in ['genG', 'delta', 'mse_genG'] else (3 if loss_ver in 'gauss_genG' else 1)
+        self.var_sigma_dim = sd_eff
+        self.n_uncert_out = (24 * mult * sd_eff) if 'pose' in uncert_type else 0
+
+        mp = _load_mean_params(smpl_mean_params)
+        spec = arch.SpecBackend()
+        arch.BACKBONES[self.backbone_name][0](spec, None)
+        if self.head_name == 'pare':
+            arch.pare_head_convs(spec, arch.SymAct(self.num_output_channels, 1, 1), self.num_output_channels)
+            arch.pare_head_spec(spec)
+        else:
+            arch.cliff_head_spec(spec, self.num_output_channels)
+        arch.poco_head_spec(spec, self.uncert_feat_dim, self.num_neurons, uncert_inp_type)
+        self.has_flow = 'norm_flow' in loss_ver
+        if self.has_flow:
+            arch.flow_head_spec(spec, self.uncert_feat_dim, context_dim, cond_nflow, num_flow_layers, num_nf_rv)
+
+        self.backbone = ParamTree()
+        self.head = ParamTree()
+        self.uncert_head = ParamTree()
+        if self.has_flow:
+            self.flow_head = ParamTree()
+        g = torch.Generator().manual_seed(0)
+        for name, (shape, kind) in spec.spec.items():
+            top, _, rest = name.partition('.')
+            getattr(self, top).register(rest, self._init_tensor(name, shape, kind, mp, g), 'param' if kind == 'param' else 'buffer')
+        self.smpl = smpl if smpl is not None else make_smpl_stage(self.head_name, img_res)
+
+        self.use_cuda_graph = (os.environ.get('POCO_B200_GRAPH', '1') != '0') if use_cuda_graph is None else use_cuda_graph
+        self.conv_impl = int(os.environ.get('POCO_B200_CONV_IMPL', '0'))
+        self._engines = {}
+        self._version = 0
+        if pretrained is not None:
+            self.load_pretrained(pretrained)
+
+    # ------------------------------------------------------------------ parameters
+    def _init_tensor(self, name, shape, kind, mp, g):
+        leaf = name.rpartition('.')[2]
+        if kind == 'long':
+            return torch.zeros((), dtype=torch.long)
+        if leaf == 'temperature':
+            return torch.tensor(1.0)
+        if leaf == 'init_pose':
+            return torch.from_numpy(mp['pose'][:shape[1]].copy()).unsqueeze(0)
+        if leaf == 'init_shape':
+            return torch.from_numpy(mp['shape'].copy()).unsqueeze(0)
+        if leaf == 'init_cam':
+            return torch.from_numpy(mp['cam'].copy()).unsqueeze(0)
+        if leaf == 'mask':
+            return _flow_masks(self.nflow_mask_type, self.num_nf_rv, self.num_flow_layers)
+        if leaf == 'running_mean':
+            return torch.zeros(shape)
+        if leaf == 'running_var':
+            return torch.ones(shape)
+        if len(shape) == 1:
+            # BatchNorm gamma is the only 1-D '.weight'; every 1-D '.bias' starts at zero
+            return torch.ones(shape) if leaf == 'weight' else torch.zeros(shape)
+        fan_in = int(np.prod(shape[1:])) if len(shape) != 6 else shape[2]
+        gain = 2.0 if len(shape) == 4 else 1.0
+        return torch.randn(shape, generator=g) * math.sqrt(gain / fan_in)
+
+    def _invalidate(self):
+        self._version += 1
+        self._engines.clear()
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._invalidate()
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._invalidate()
+        return r
+
+    def load_pretrained(self, file):
+        """Same splitting rules as the reference (poco.py:131-154, train_utils.py:69-136)."""
+        path = _get_model_path(file, self.inf_model)
+        state_dict = torch.load(path, map_location='cpu')
+        state_dict = state_dict['model'] if 'model' in state_dict.keys() else state_dict
+        state_dict = state_dict['state_dict'] if 'state_dict' in state_dict.keys() else state_dict
+        parts = ['backbone', 'head']
+        if self.uncert_layer == 'diff_branch' and self.is_test and _part(state_dict, 'uncert_head'):
+            parts.append('uncert_head')
+        if self.has_flow and self.is_test and _part(state_dict, 'flow_head'):
+            parts.append('flow_head')
+        for part in parts:
+            sub = _part(state_dict, part)
+            mod = getattr(self, part)
+            try:
+                mod.load_state_dict(sub, strict=True)
+            except Exception:           # reference falls back to non-strict with a warning
+                mod.load_state_dict(sub, strict=False)
+        self._invalidate()
+
+    # ------------------------------------------------------------------ plan
+    def _build_engine(self, B, device):
+        if device.type == 'cuda':       # (a cpu device is accepted only to *build* schedules in host-logic tests)
+            L.check(L.lib().poco_device_check(device.index if device.index is not None else torch.cuda.current_device()))
+        sd ={k: v.detach() for k, v in self.state_dict().items()}
+        b = PlanBuilder(sd, B, device, conv_impl=self.conv_impl)
+        eng = _Engine()
+        eng.img = b.f32(B, 3, self.img_res, self.img_res)
+        feats = arch.BACKBONES[self.backbone_name][0](b, eng.img)
+        Cf = self.num_output_channels
+        out = {}
+        if self.head_name == 'pare':
+            part, smplf = arch.pare_head_convs(b, feats, Cf)
+            H, W = part.H, part.W
+            segm = b.f32(B, 25, H, W)
+            uf, p6 = b.f32(B, 24 * 128), b.f32(B, 24, 6)
+            rot, shape, cam = b.f32(B, 24, 3, 3), b.f32(B, 10), b.f32(B, 3)
+            scratch = b.f32(int(L.lib().poco_pare_scratch_floats(B, H, W)))
+            w = {k: b.dev(sd['head.' + k]) for k in (
+                'keypoint_final_layer.weight', 'keypoint_final_layer.bias', 'smpl_final_layer.weight',
+                'smpl_final_layer.bias', 'pose_mlp.weight', 'shape_mlp.weight', 'shape_mlp.bias',
+                'cam_mlp.weight', 'cam_mlp.bias')}
+            b.add(L.PareHead(part.desc(), smplf.desc(),
+                             w['keypoint_final_layer.weight'].data_ptr(), w['keypoint_final_layer.bias'].data_ptr(),
+                             w['smpl_final_layer.weight'].data_ptr(), w['smpl_final_layer.bias'].data_ptr(),
+                             w['pose_mlp.weight'].data_ptr(), w['shape_mlp.weight'].data_ptr(),
+                             w['shape_mlp.bias'].data_ptr(), w['cam_mlp.weight'].data_ptr(), w['cam_mlp.bias'].data_ptr(),
+                             segm.data_ptr(), uf.data_ptr(), p6.data_ptr(), rot.data_ptr(), shape.data_ptr(),
+                             cam.data_ptr(), scratch.data_ptr()))
+            out.update(pred_segm_mask=segm, pred_pose=rot, pred_pose6d=p6, pred_cam=cam, pred_shape=shape,
+                       uncert_feat=uf)
+            feat_mat = uf
+        else:
+            F_ = Cf
+            xc = b.f32(B, F_ + 3 + 157)
+            eng.bbox = b.f32(B, 3)
+            b.avgpool(feats, xc, 0)
+            b.copy2d(eng.bbox, 0, xc, F_, 3)
+            ip, ish, ic = b.dev(sd['head.init_pose']), b.dev(sd['head.init_shape']), b.dev(sd['head.init_cam'])
+            cp, cs, cc = F_ + 3, F_ + 3 + 144, F_ + 3 + 154
+            b.copy2d(ip, 0, xc, cp, 144, bcast=True)
+            b.copy2d(ish, 0, xc, cs, 10, bcast=True)
+            b.copy2d(ic, 0, xc, cc, 3, bcast=True)
+            h1, h2 = b.f32(B, 1024), b.f32(B, 1024)
+            for _ in range(3):          # cliff_head.forward n_iter=3 (cliff_head.py:103-113)
+                b.linear(xc, 0, F_ + 160, 'head.fc1', h1, 0)
+                b.linear(h1, 0, 1024, 'head.fc2', h2, 0)
+                b.linear(h2, 0, 1024, 'head.decpose', xc, cp, res=xc, rescol=cp)
+                b.linear(h2, 0, 1024, 'head.decshape', xc, cs, res=xc, rescol=cs)
+                b.linear(h2, 0, 1024, 'head.deccam', xc, cc, res=xc, rescol=cc)
+            rot = b.f32(B, 24, 3, 3)
+            b.rot6d(xc, cp, 24, rot)
+            out.update(pred_pose=rot, pred_cam=xc[:, cc:cc + 3], pred_shape=xc[:, cs:cs + 10],
+                       pred_pose_6d=xc[:, cp:cp + 144], uncert_feat=xc[:, :F_], body_feat2=h2)
+            feat_mat = xc           # columns [0, F) are the features
+        # ---- uncertainty head (poco_head.forward, inference branch)
+        nfeat = self.uncert_feat_dim
+        act = {'sigmoid': 1, 'softplus': 2}.get(self.activation_type, 0)
+        pre, layers = arch.poco_head_layers(nfeat, self.num_neurons, self.uncert_inp_type, self.n_uncert_out)
+        pose = rot.view(B, 216)
+        if pre:
+            n1 = pre[0][2]
+            x = b.f32(B, 2 * n1)
+            b.linear(feat_mat, 0, nfeat, 'uncert_head.uncert_fc_featNet', x, 0, act=1)
+            b.linear(pose, 0, 216, 'uncert_head.uncert_fc_poseNet', x, n1, act=1)
+        elif self.uncert_inp_type == 'feat-pose':
+            x = b.f32(B, nfeat + 216)
+            b.copy2d(feat_mat, 0, x, 0, nfeat)
+            b.copy2d(pose, 0, x, nfeat, 216)
+        else:
+            x = feat_mat
+        for name, i, o in layers:
+            y = b.f32(B, o)
+            b.linear(x, 0, i, 'uncert_head.' + name, y, 0, act=act)
+            x = y
+        out['var_pose'] = x
+        eng.out = out
+        eng.plan = Plan(b)
+        eng.builder_keep = b.keep
+        return eng
+
+    def _engine(self, B, device):
+        key = (B, str(device))
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = self._build_engine(B, device)
+            self._engines[key] = eng
+        return eng
+
+    # ------------------------------------------------------------------ forward
+    def hot_path(self, batch):
+        """backbone + regression head + uncertainty head on the GPU; returns a fresh dict."""
+        img = batch['img']
+        if not (torch.is_tensor(img) and img.is_cuda):
+            raise L.PocoError('poco_b200.POCO.forward needs CUDA tensors (sm_100a); there is no CPU path')
+        if self.training:
+            raise L.PocoError('poco_b200 implements the inference path only -- call model.eval()')
+        B = img.shape[0]
+        if tuple(img.shape[1:]) != (3, self.img_res, self.img_res):
+            raise ValueError(f"batch['img'] must be [B,3,{self.img_res},{self.img_res}], got {tuple(img.shape)}")
+        eng = self._engine(B, img.device)
+        eng.img.copy_(img)
+        if self.head_name == 'cliff':
+            eng.bbox.copy_(batch['bbox_info'])
+        eng.run(self.use_cuda_graph)
+        out = {}
+        for k, v in eng.out.items():
+            out[k] = v.clone() if v.is_contiguous() else v.contiguous()
+        if self.var_sigma_dim == 9:
+            out['var_pose'] = out['var_pose'].view(B, -1, 3, 3)
+        return out
+
+    def forward(self, batch):
+        head_output = self.hot_path(batch)
+        if self.head_name == 'cliff':
+            smpl_output = self.smpl(
+                rotmat=head_output['pred_pose'], shape=head_output['pred_shape'], cam=head_output['pred_cam'],
+                focal_length=batch['focal_length'], bbox_scale=batch['scale'], bbox_center=batch['center'],
+                img_h=batch['orig_shape'][:, 0], img_w=batch['orig_shape'][:, 1])
+        else:
+            smpl_output = self.smpl(
+                rotmat=head_output['pred_pose'], shape=head_output['pred_shape'], cam=head_output['pred_cam'],
+                normalize_joints2d=True)
+        var_pose = head_output.pop('var_pose')
+        smpl_output.update(head_output)
+        smpl_output['var_pose'] = var_pose
+        smpl_output['gt_pose_cond_idx'] = []
+        if self.has_flow:
+            # inference: the reference evaluates cond_layer and discards it, log_phi is None (nf_head.py:128-135)
+            smpl_output['log_phi'] = None
+        return smpl_output
+
+    # ------------------------------------------------------------------ RealNVP (separately callable)
+    def _flow_params(self, device):
+        key = ('flow', str(device))
+        if key not in self._engines:
+            sd = self.state_dict()
+            self._engines[key] = (pack_realnvp(sd).to(device), sd['flow_head.flow.mask'].shape[0])
+        return self._engines[key]
+
+    def _flow_run(self, x, ctx, direction):
+        if not x.is_cuda:
+            raise L.PocoError('RealNVP kernels need CUDA tensors')
+        params, nl = self._flow_params(x.device)
+        x = x.float().contiguous()
+        R, D = x.shape
+        ctxd = ctx.shape[1] if ctx is not None else 0
+        ctx = ctx.float().contiguous() if ctx is not None else None
+        out = torch.empty(R if direction == 0 else (R, D), dtype=torch.float32, device=x.device)
+        z = torch.empty(R, D, dtype=torch.float32, device=x.device) if direction == 0 else None
+        ld = torch.empty(R, dtype=torch.float32, device=x.device) if direction == 0 else None
+        d = L.RealNVP(x.data_ptr(), ctx.data_ptr() if ctx is not None else None, params.data_ptr(), out.data_ptr(),
+                      z.data_ptr() if z is not None else None, ld.data_ptr() if ld is not None else None,
+                      R, D, ctxd, 64, nl, direction)
+        L.run_op(d, torch.cuda.current_stream().cuda_stream)
+        return out, z, ld
+
+    def flow_context(self, uncert_feat):
+        """cond_layer(uncert_feat) (nf_head.py:82)"""
+        w, b_ = self.flow_head.cond_layer.weight, self.flow_head.cond_layer.bias
+        x = uncert_feat.float().contiguous()
+        y = torch.empty(x.shape[0], w.shape[0], dtype=torch.float32, device=x.device)
+        d = L.Linear(x.data_ptr(), x.stride(0), w.data_ptr(), b_.data_ptr(), None, 0, y.data_ptr(), y.stride(0),
+                     x.shape[0], x.shape[1], w.shape[0], 0)
+        L.run_op(d, torch.cuda.current_stream().cuda_stream)
+        return y
+
+    def flow_log_prob(self, x, ctx):
+        """RealNVP.log_prob (real_nvp.py:55-65)"""
+        return self._flow_run(x, ctx, 0)[0]
+
+    def flow_backward(self, x, ctx):
+        """RealNVP.backward_p (real_nvp.py:40-53) -> (z, log_det_J)"""
+        _, z, ld = self._flow_run(x, ctx, 0)
+        return z, ld
+
+    def flow_forward(self, z, ctx):
+        """RealNVP.forward_p (real_nvp.py:25-38)"""
+        return self._flow_run(z, ctx, 1)[0]
+
+
+class _Engine:
+    """One static plan (+ optional CUDA graph) for one batch size."""
+
+    def __init__(self):
+        self.img = self.bbox = self.plan = self.out = None
+        self.graph = None
+        self.warm = False
+
+    def run(self, use_graph):
+        if not use_graph:
+            self.plan.run()
+            return
+        if self.graph is None:
+            if not self.warm:           # first call runs eagerly (one-time attribute setup happens outside capture)
+                self.plan.run()
+                self.warm = True
+                return
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self.plan.run()
+            self.graph = g
+        self.graph.replay()
+
+
+def _part(full, part):
+    """train_utils.get_part_statedict + prepare_statedict (train_utils.py:69-90)"""
+    out = {}
+    for k, v in full.items():
+        for pre in (f'model.{part}.', f'{part}.'):
+            if k.startswith(pre):
+                out[k[len(pre):]] = v
+                break
+    return out
+
+
+def _get_model_path(path, inf_model='best'):
+    """train_utils.get_model_path (train_utils.py:126-136)"""
+    if path.endswith(('.pt', '.ckpt', '.pth')):
+        return path
+    if inf_model == 'best':
+        return path + '/best_model.pt'
+    if inf_model == 'best_mpjpe_var':
+        return path + '/best_mpjpe_var_model.pt'
+    import glob
+    return sorted(glob.glob(f'{path}/tb_logs_poco-smpl/*/checkpoints/*'))[-1]

@@ -1,0 +1,159 @@
+"""TEST INFRASTRUCTURE -- CPU interpreter of poco_op descriptors.
+
+Replays an engine.Plan's op list with plain torch on CPU buffers, honouring the same layouts, fp16
+storage roundings and in-place aliasing as the CUDA kernels.  It checks the *host logic* (graph
+wiring, buffer-pool reuse, BN folding, weight packing, descriptor fields) without a GPU, and
+predicts how far fp16 activation storage moves the outputs from the fp32 oracle.
+It is not a product path: poco_b200 never imports it.
+"""
+import bisect
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from poco_b200 import _lib as L
+
+
+class Emu:
+    def __init__(self, keep):
+        items = sorted(((t.data_ptr(), t) for t in keep if t.numel() > 0), key=lambda x: x[0])
+        self.starts = [p for p, _ in items]
+        self.tensors = [t for _, t in items]
+
+    def flat(self, ptr, dtype):
+        """1-D view (of `dtype`) starting at raw address ptr, to the end of its buffer"""
+        i = bisect.bisect_right(self.starts, ptr) - 1
+        t = self.tensors[i]
+        base = t.data_ptr()
+        nbytes = t.numel() * t.element_size()
+        assert base <= ptr < base + nbytes, 'pointer outside every kept buffer'
+        rem = t.view(-1).view(torch.uint8)[ptr - base:]
+        es = torch.empty(0, dtype=dtype).element_size()
+        return rem[:rem.numel() // es * es].view(dtype)
+
+    def act(self, a):
+        f = self.flat(a.data, torch.float16)
+        Hp, Wp = a.H + 2, a.W + 2
+        return torch.as_strided(f, (a.C // 8, a.N, Hp, Wp, 8), (a.plane_stride * 8, Hp * Wp * 8, Wp * 8, 8, 1))
+
+    def act_get(self, a):
+        v = self.act(a)[:, :, 1:a.H + 1, 1:a.W + 1, :]
+        return v.permute(1, 0, 4, 2, 3).reshape(a.N, a.C, a.H, a.W).float()
+
+    def act_set(self, a, x):
+        v = self.act(a)
+        v[:, :, 1:a.H + 1, 1:a.W + 1, :] = x.to(torch.float16).view(a.N, a.C // 8, 8, a.H, a.W).permute(1, 0, 3, 4, 2)
+
+    def mat(self, ptr, rows, cols, ld):
+        return torch.as_strided(self.flat(ptr, torch.float32), (rows, cols), (ld, 1))
+
+    # ------------------------------------------------------------------------------------------
+    def run(self, op):
+        k = op.kind
+        getattr(self, '_op%d' % k)(getattr(op.u, L._FIELD_OF_KIND[k]))
+
+    def _op1(self, d):      # pack image
+        o = d.out
+        img = self.flat(d.img, torch.float32)[:o.N * 3 * o.H * o.W].view(o.N, 3, o.H, o.W)
+        x = torch.zeros(o.N, o.C, o.H, o.W)
+        x[:, :3] = img
+        self.act_set(o, x)
+
+    def _op2(self, d):      # conv
+        i, o = d.in_, d.out
+        taps = d.kh * d.kw
+        wp = self.flat(d.weight, torch.float16)[:taps * i.C * o.C].view(taps, i.C // 8, o.C, 8).float()
+        w = wp.permute(2, 1, 3, 0).reshape(o.C, i.C, d.kh, d.kw)
+        b = self.flat(d.bias, torch.float32)[:o.C]
+        y = F.conv2d(self.act_get(i), w, b, stride=d.stride, padding=d.pad)
+        if d.relu == 2:
+            y = F.relu(y)
+        if d.residual:
+            r = L.Act(d.residual, d.res_plane_stride, o.C, o.N, o.H, o.W)
+            y = y + self.act_get(r)
+        if d.relu == 1:
+            y = F.relu(y)
+        self.act_set(o, y)
+
+    def _op3(self, d):      # fuse sum
+        y = None
+        for k in range(d.n_in):
+            t = self.act_get(d.in_[k])
+            if d.shift[k]:
+                t = F.interpolate(t, scale_factor=2 ** d.shift[k], mode='nearest')
+            y = t if y is None else y + t
+        self.act_set(d.out, F.relu(y) if d.relu else y)
+
+    def _op4(self, d):      # bilinear x2
+        self.act_set(d.out, F.interpolate(self.act_get(d.in_), scale_factor=2, mode='bilinear', align_corners=True))
+
+    def _op5(self, d):      # maxpool
+        self.act_set(d.out, F.max_pool2d(self.act_get(d.in_), 3, 2, 1))
+
+    def _op6(self, d):      # avgpool
+        x = self.act_get(d.in_)
+        self.mat(d.out, x.shape[0], x.shape[1], d.ld)[:] = x.mean(dim=(2, 3))
+
+    def _op7(self, d):      # unpack
+        x = self.act_get(d.in_)[:, :d.c_valid]
+        self.flat(d.out, torch.float32)[:x.numel()] = x.reshape(-1)
+
+    def _op8(self, d):      # linear
+        x = self.mat(d.x, d.M, d.I, d.ldx)
+        w = self.flat(d.w, torch.float32)[:d.O * d.I].view(d.O, d.I)
+        y = x @ w.t()
+        if d.b:
+            y = y + self.flat(d.b, torch.float32)[:d.O]
+        if d.act == 1:
+            y = torch.sigmoid(y)
+        elif d.act == 2:
+            y = F.softplus(y)
+        if d.res:
+            y = y + self.mat(d.res, d.M, d.O, d.ldres)
+        self.mat(d.y, d.M, d.O, d.ldy)[:] = y
+
+    def _op9(self, d):      # copy2d
+        src = self.mat(d.src, 1 if d.bcast else d.rows, d.cols, d.lds)
+        self.mat(d.dst, d.rows, d.cols, d.ldd)[:] = src
+
+    def _op10(self, d):     # rot6d
+        rows = d.n // d.per_row
+        x = self.mat(d.x, rows, d.per_row * 6, d.ldx).reshape(-1, 3, 2)
+        a1, a2 = x[:, :, 0], x[:, :, 1]
+        b1 = F.normalize(a1)
+        b2 = F.normalize(a2 - (b1 * a2).sum(1, keepdim=True) * b1)
+        b3 = torch.linalg.cross(b1, b2, dim=1)
+        self.flat(d.out, torch.float32)[:d.n * 9] = torch.stack((b1, b2, b3), -1).reshape(-1)
+
+    def _op11(self, d):     # PARE head
+        pf, sf = self.act_get(d.part_feats), self.act_get(d.smpl_feats)
+        N, _, H, W = pf.shape
+        f32 = lambda p, n: self.flat(p, torch.float32)[:n]
+        wkp, bkp = f32(d.w_kp, 25 * 128).view(25, 128), f32(d.b_kp, 25)
+        segm = torch.einsum('nchw,jc->njhw', pf, wkp) + bkp.view(1, 25, 1, 1)
+        f32(d.segm, segm.numel())[:] = segm.reshape(-1)
+        att = F.softmax(segm[:, 1:].reshape(N, 24, -1), -1)
+        pl = torch.einsum('njp,ncp->ncj', att, sf.reshape(N, 128, -1))           # [N,128,24]
+        f32(d.uncert_feat, N * 3072)[:] = pl.reshape(-1)
+        wsf, bsf = f32(d.w_sf, 64 * 128).view(64, 128), f32(d.b_sf, 64)
+        cs = torch.einsum('oc,ncj->noj', wsf, pl) + bsf.view(1, 64, 1)
+        wp = f32(d.w_pose, 6 * 128 * 24).view(6, 128, 24)
+        p6 = torch.einsum('ncj,ocj->njo', pl, wp)                               # [N,24,6]
+        f32(d.pose6d, N * 144)[:] = p6.reshape(-1)
+        flat = cs.reshape(N, -1)
+        f32(d.shape, N * 10)[:] = (flat @ f32(d.w_shape, 15360).view(10, 1536).t() + f32(d.b_shape, 10)).reshape(-1)
+        f32(d.cam, N * 3)[:] = (flat @ f32(d.w_cam, 4608).view(3, 1536).t() + f32(d.b_cam, 3)).reshape(-1)
+        x = p6.reshape(-1, 3, 2)
+        a1, a2 = x[:, :, 0], x[:, :, 1]
+        b1 = F.normalize(a1)
+        b2 = F.normalize(a2 - (b1 * a2).sum(1, keepdim=True) * b1)
+        b3 = torch.linalg.cross(b1, b2, dim=1)
+        f32(d.rotmat, N * 216)[:] = torch.stack((b1, b2, b3), -1).reshape(-1)
+
+
+def run_plan_ops(ops, keep):
+    emu = Emu(keep)
+    with torch.no_grad():
+        for op in ops:
+            emu.run(op)

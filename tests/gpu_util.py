@@ -1,0 +1,66 @@
+"""helpers for -m gpu tests: every call goes through the C ABI (poco_b200._lib)"""
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+from poco_b200 import _lib as L
+from poco_b200 import engine
+
+
+def sync_or_die(seconds=60.0):
+    """cudaStreamSynchronize with a deadline: a hung kernel must not take the GPU box down with it"""
+    ev = torch.cuda.Event()
+    ev.record()
+    t0 = time.time()
+    while not ev.query():
+        if time.time() - t0 > seconds:
+            sys.stderr.write(f'FATAL: GPU work did not finish within {seconds}s -- aborting the process\n')
+            sys.stderr.flush()
+            os._exit(3)
+        time.sleep(0.002)
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def run_conv(x, w, bias, stride=1, pad=None, relu=1, residual=None, impl=0):
+    """x [N,Cin,H,W], w [Cout,Cin,k,k], bias [Cout] (CPU float) -> [N,Cout,Ho,Wo] float (CPU).
+    Inputs are rounded to fp16 exactly as the engine does."""
+    dev = 'cuda'
+    N, Cin, H, W = x.shape
+    Cout, _, k, _ = w.shape
+    pad = k // 2 if pad is None else pad
+    cin_p = (Cin + 15) // 16 * 16
+    a = engine.to_planar(x.to(dev), c_pad=cin_p)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    o = engine.alloc_act(Cout, N, Ho, Wo, dev)
+    wp = engine.pack_conv_weight(w.to(dev).float(), cin_pad=cin_p)
+    b = bias.to(dev).float().contiguous()
+    r = engine.to_planar(residual.to(dev)) if residual is not None else None
+    d = L.Conv(a.desc(), o.desc(), wp.data_ptr(), b.data_ptr(), r.ptr if r is not None else None,
+               r.plane_stride if r is not None else 0, k, k, stride, pad, relu, impl)
+    L.run_op(d, stream())
+    sync_or_die()
+    out = engine.from_planar(o).cpu()
+    halo = engine.act_view(o)
+    assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
+                 halo[:, :, :, -1].abs().sum()) == 0.0, 'kernel wrote into the zero halo'
+    return out
+
+
+def conv_reference(x, w, bias, stride=1, pad=None, relu=1, residual=None):
+    """fp32 oracle arithmetic on the fp16-rounded operands (what the kernel is specified to compute)"""
+    k = w.shape[-1]
+    pad = k // 2 if pad is None else pad
+    y = F.conv2d(x.half().float(), w.half().float(), bias.float(), stride=stride, padding=pad)
+    if relu == 2:
+        y = F.relu(y)
+    if residual is not None:
+        y = y + residual.half().float()
+    if relu == 1:
+        y = F.relu(y)
+    return y

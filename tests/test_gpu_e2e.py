@@ -1,0 +1,116 @@
+"""-m gpu: POCO.forward through the C ABI on a B200 against the reference-generated goldens."""
+import numpy as np
+import pytest
+import torch
+
+import emu
+from common import GATED, PRESETS, build_model, load_preset, rel_err, synthetic_batch
+from gpu_util import sync_or_die
+
+pytestmark = pytest.mark.gpu
+
+# fp16 weights + fp16 activation storage through ~110 sequential conv layers against the fp32
+# reference, on the calibrated synthetic checkpoint (DESIGN.md "precision"): max-abs-err / max-abs-ref
+E2E_TOL = {'pred_pose': 6e-2, 'pred_shape': 6e-3, 'pred_cam': 1.5e-2, 'var_pose': 1e-3}
+
+
+@pytest.mark.parametrize('preset', PRESETS)
+def test_forward_matches_reference_goldens(preset):
+    meta, gold, _ = load_preset(preset)
+    m = build_model(preset, 'cuda')
+    batch = synthetic_batch(preset, 'cuda')
+    with torch.no_grad():
+        out = m(batch)
+    sync_or_die(120)
+    B = meta['test_b']
+    # dict contract
+    assert out['log_phi'] is None and out['gt_pose_cond_idx'] == []
+    assert out['pred_pose'].shape == (B, 24, 3, 3) and out['var_pose'].shape == (B, 24)
+    assert out['smpl_vertices'].shape == (B, 6890, 3) and out['pred_cam_t'].shape == (B, 3)
+    if 'cliff' in preset:
+        assert set(out) >= {'pred_pose_6d', 'uncert_feat', 'body_feat2', 'pred_fullimg_cam_t'}
+    else:
+        assert set(out) >= {'pred_pose6d', 'uncert_feat', 'pred_segm_mask'}
+        assert out['pred_segm_mask'].shape[:2] == (B, 25)
+    for k, v in out.items():
+        if torch.is_tensor(v):
+            assert v.dtype == torch.float32 and v.is_cuda, k
+            assert torch.isfinite(v).all(), k
+    errs = {k: rel_err(out[k].cpu().numpy(), gold[k]) for k in GATED}
+    print(preset, errs)
+    for k in GATED:
+        assert errs[k] < E2E_TOL[k], (k, errs)
+    # non-gated outputs are checked too (looser: features carry the raw fp16 noise)
+    for k in ('uncert_feat', 'body_feat2', 'pred_pose6d', 'pred_pose_6d'):
+        if k in gold:
+            assert rel_err(out[k].cpu().numpy(), gold[k]) < 3e-2, k
+    if 'pred_segm_mask_sub' in gold:
+        st = int(gold['segm_stride'])
+        assert rel_err(out['pred_segm_mask'][:, :, ::st, ::st].cpu().numpy(), gold['pred_segm_mask_sub']) < 5e-2
+
+
+@pytest.mark.parametrize('preset', ['pare_r50', 'cliff_w32'])
+def test_gpu_equals_cpu_replay_of_the_same_schedule(preset):
+    """the CUDA kernels and the CPU op interpreter implement the same arithmetic (fp16 storage, fp32
+    accumulate): they may differ only by accumulation order -> an order of magnitude tighter than the
+    distance to the fp32 reference"""
+    meta, gold, _ = load_preset(preset)
+    m = build_model(preset, 'cuda')
+    with torch.no_grad():
+        out = m.hot_path(synthetic_batch(preset, 'cuda'))
+    sync_or_die(120)
+    mc = build_model(preset)
+    batch = synthetic_batch(preset)
+    eng = mc._build_engine(meta['test_b'], torch.device('cpu'))
+    eng.img.copy_(batch['img'])
+    if eng.bbox is not None:
+        eng.bbox.copy_(batch['bbox_info'])
+    emu.run_plan_ops(eng.plan.ops, eng.plan.keep)
+    for k in GATED:
+        e = rel_err(out[k].cpu().numpy(), eng.out[k].reshape(out[k].shape).numpy())
+        print(preset, k, e)
+        assert e < max(E2E_TOL[k] / 3, 3e-4), (k, e)
+
+
+def test_cuda_graph_replay_is_bitwise_equal_to_eager():
+    batch = synthetic_batch('cliff_w32', 'cuda')
+    m = build_model('cliff_w32', 'cuda', use_cuda_graph=False)
+    g = build_model('cliff_w32', 'cuda', use_cuda_graph=True)
+    with torch.no_grad():
+        a = m.hot_path(batch)
+        for _ in range(3):          # eager warm-up, capture, replay
+            b = g.hot_path(batch)
+    sync_or_die(120)
+    for k in GATED:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_outputs_are_fresh_and_batch_invariant():
+    m = build_model('cliff_w32', 'cuda')
+    batch = synthetic_batch('cliff_w32', 'cuda')
+    with torch.no_grad():
+        a = m.hot_path(batch)
+        b = m.hot_path(batch)
+        assert a['pred_pose'].data_ptr() != b['pred_pose'].data_ptr()       # caller owns the outputs
+        assert torch.equal(a['pred_pose'], b['pred_pose'])                 # deterministic
+        # a crop's result does not depend on the batch it travels in (bitwise shard == single-GPU)
+        one = m.hot_path({k: v[1:2] for k, v in batch.items()})
+    sync_or_die(120)
+    for k in GATED:
+        assert torch.equal(one[k][0], a[k][1]), k
+
+
+def test_debug_conv_kernels_agree_with_tcgen05_path():
+    batch = synthetic_batch('pare_r50', 'cuda')
+    import os
+    os.environ['POCO_B200_CONV_IMPL'] = '1'
+    try:
+        ref = build_model('pare_r50', 'cuda')
+    finally:
+        os.environ.pop('POCO_B200_CONV_IMPL')
+    tc = build_model('pare_r50', 'cuda')
+    with torch.no_grad():
+        a, b = ref.hot_path(batch), tc.hot_path(batch)
+    sync_or_die(120)
+    for k in GATED:
+        assert rel_err(b[k].cpu().numpy(), a[k].cpu().numpy()) < max(E2E_TOL[k] / 3, 3e-4), k

@@ -1,0 +1,228 @@
+"""-m gpu: every CUDA op through the C ABI against the oracle arithmetic (torch fp32 on CPU).
+Tolerances: conv outputs are stored in fp16 -> 2^-10 relative to the tensor max (one rounding) plus
+fp32 accumulation-order noise; fp32 ops -> 1e-5."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import load_preset, rel_err
+from gpu_util import conv_reference, run_conv, stream, sync_or_die
+from oracle import poco_oracle as O
+from poco_b200 import _lib as L
+from poco_b200 import engine
+
+pytestmark = pytest.mark.gpu
+CONV_TOL = 1.5e-3
+
+# (Cin, Cout, k, stride, H, N, residual, relu)
+CONV_CASES = [
+    # linear-halo mode (3x3 s1 / 1x1 s1), weights resident
+    (32, 32, 3, 1, 56, 2, True, 1), (64, 64, 3, 1, 28, 2, True, 1), (16, 32, 3, 1, 8, 1, False, 0),
+    (48, 48, 3, 1, 56, 1, True, 1), (64, 256, 1, 1, 56, 1, True, 1), (256, 64, 1, 1, 56, 1, False, 1),
+    (256, 32, 1, 1, 7, 3, False, 0),
+    # linear-halo mode, weights streamed per K chunk
+    (128, 128, 3, 1, 14, 3, True, 1), (256, 256, 3, 1, 7, 5, True, 1), (480, 256, 3, 1, 28, 1, False, 1),
+    (256, 256, 3, 1, 56, 1, False, 1),
+    # several N blocks
+    (384, 384, 3, 1, 7, 2, True, 1), (1024, 2048, 1, 1, 7, 2, False, 1), (96, 480, 1, 1, 14, 1, False, 0),
+    # gather mode (stride 2, 7x7)
+    (3, 64, 3, 2, 224, 1, False, 1), (64, 64, 3, 2, 112, 1, False, 1), (32, 64, 3, 2, 56, 2, False, 1),
+    (256, 256, 3, 2, 14, 2, True, 2), (3, 64, 7, 2, 224, 1, False, 1), (256, 512, 1, 2, 56, 1, False, 0),
+    (128, 256, 3, 2, 14, 3, True, 1),
+]
+
+
+def _case_tensors(cin, cout, k, stride, H, N, res, seed=0):
+    g = torch.Generator().manual_seed(seed + cin * 7 + cout)
+    x = torch.randn(N, cin, H, H, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = 0.1 * torch.randn(cout, generator=g)
+    pad = k // 2
+    Ho = (H + 2 * pad - k) // stride + 1
+    r = torch.randn(N, cout, Ho, Ho, generator=g) if res else None
+    return x, w, b, r
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: 'c%d-%d_k%d_s%d_h%d_n%d' % c[:6])
+def test_conv_tcgen05(case):
+    cin, cout, k, stride, H, N, res, relu = case
+    x, w, b, r = _case_tensors(cin, cout, k, stride, H, N, res)
+    ref = conv_reference(x, w, b, stride, None, relu, r)
+    out = run_conv(x, w, b, stride, None, relu, r, impl=0)
+    assert rel_err(out.numpy(), ref.numpy()) < CONV_TOL
+
+
+@pytest.mark.parametrize('case', [CONV_CASES[0], CONV_CASES[7], CONV_CASES[14], CONV_CASES[17]],
+                         ids=lambda c: 'c%d-%d_k%d_s%d_h%d_n%d' % c[:6])
+def test_conv_debug_kernel(case):
+    cin, cout, k, stride, H, N, res, relu = case
+    x, w, b, r = _case_tensors(cin, cout, k, stride, H, N, res)
+    ref = conv_reference(x, w, b, stride, None, relu, r)
+    out = run_conv(x, w, b, stride, None, relu, r, impl=1)
+    assert rel_err(out.numpy(), ref.numpy()) < CONV_TOL
+
+
+def test_conv_identity_and_tap_shift():
+    """1x1 identity weights return the input; a single hot tap of a 3x3 returns the shifted input"""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 32, 12, 12, generator=g).half().float()
+    w1 = torch.eye(32).view(32, 32, 1, 1)
+    assert torch.equal(run_conv(x, w1, torch.zeros(32), relu=0), x)
+    for t in range(9):
+        w = torch.zeros(32, 32, 3, 3)
+        w[:, :, t // 3, t % 3] = torch.eye(32)
+        out = run_conv(x, w, torch.zeros(32), relu=0)
+        ref = F.conv2d(x, w, padding=1)
+        assert torch.equal(out, ref), f'tap {t}'
+
+
+def test_conv_batch_invariance():
+    """per-crop math does not depend on the batch it is in (needed for bitwise shard == single-GPU)"""
+    x, w, b, _ = _case_tensors(64, 64, 3, 1, 28, 4, False)
+    full = run_conv(x, w, b)
+    for i in range(4):
+        assert torch.equal(run_conv(x[i:i + 1], w, b)[0], full[i])
+
+
+def test_pack_unpack_fuse_upsample_pool():
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(2, 3, 224, 224, generator=g)
+    o = engine.alloc_act(16, 2, 224, 224, dev)
+    imgd = img.to(dev)
+    L.run_op(L.PackImage(imgd.data_ptr(), o.desc()), stream())
+    sync_or_die()
+    got = engine.from_planar(o).cpu()
+    assert torch.equal(got[:, :3], img.half().float()) and got[:, 3:].abs().sum() == 0
+    # unpack
+    outf = torch.zeros(2, 3, 224, 224, device=dev)
+    L.run_op(L.Unpack(o.desc(), outf.data_ptr(), 3), stream())
+    sync_or_die()
+    assert torch.equal(outf.cpu(), img.half().float())
+    # fuse: x0 + up2(x1) + up4(x2), relu
+    xs = [torch.randn(2, 32, 16 >> s, 16 >> s, generator=g).half().float() for s in range(3)]
+    acts = [engine.to_planar(x.to(dev)) for x in xs]
+    out = engine.alloc_act(32, 2, 16, 16, dev)
+    d = L.FuseSum()
+    d.out = out.desc()
+    for i, a in enumerate(acts):
+        d.in_[i] = a.desc()
+        d.shift[i] = i
+    d.n_in, d.relu = 3, 1
+    L.run_op(d, stream())
+    sync_or_die()
+    ref = F.relu(xs[0] + F.interpolate(xs[1], scale_factor=2, mode='nearest') + F.interpolate(xs[2], scale_factor=4, mode='nearest'))
+    assert rel_err(engine.from_planar(out).cpu().numpy(), ref.numpy()) < 1e-3
+    # bilinear x2 align_corners
+    x = xs[0]
+    up = engine.alloc_act(32, 2, 32, 32, dev)
+    L.run_op(L.Upsample2x(acts[0].desc(), up.desc()), stream())
+    sync_or_die()
+    ref = F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)
+    assert rel_err(engine.from_planar(up).cpu().numpy(), ref.numpy()) < 1e-3
+    # maxpool 3x3 s2 p1 (odd and even sizes)
+    for H in (16, 15):
+        xm = torch.randn(1, 16, H, H, generator=g).half().float()
+        am = engine.to_planar(xm.to(dev))
+        Ho = (H - 1) // 2 + 1
+        om = engine.alloc_act(16, 1, Ho, Ho, dev)
+        L.run_op(L.MaxPool(am.desc(), om.desc()), stream())
+        sync_or_die()
+        assert torch.equal(engine.from_planar(om).cpu(), F.max_pool2d(xm, 3, 2, 1))
+    # global average pool into a strided matrix
+    mat = torch.zeros(2, 40, device=dev)
+    L.run_op(L.AvgPool(acts[0].desc(), mat.data_ptr() + 4 * 5, 40), stream())
+    sync_or_die()
+    assert rel_err(mat[:, 5:37].cpu().numpy(), xs[0].mean(dim=(2, 3)).numpy()) < 1e-5
+    assert mat[:, :5].abs().sum() == 0 and mat[:, 37:].abs().sum() == 0
+
+
+@pytest.mark.parametrize('M,I,O,act', [(4, 2208, 1024, 0), (256, 1024, 144, 0), (7, 3288, 512, 1), (3, 432, 24, 2), (33, 65, 67, 1)])
+def test_linear(M, I, O, act):
+    g = torch.Generator().manual_seed(2)
+    x, w, b, r = torch.randn(M, I, generator=g), torch.randn(O, I, generator=g) / I ** 0.5, torch.randn(O, generator=g), torch.randn(M, O, generator=g)
+    xd, wd, bd, rd = (t.cuda() for t in (x, w, b, r))
+    y = torch.zeros(M, O + 3, device='cuda')
+    L.run_op(L.Linear(xd.data_ptr(), I, wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), O, y.data_ptr() + 4, O + 3, M, I, O, act), stream())
+    sync_or_die()
+    ref = x.double() @ w.double().t() + b.double()
+    ref = torch.sigmoid(ref) if act == 1 else (F.softplus(ref) if act == 2 else ref)
+    ref = ref + r.double()
+    assert rel_err(y[:, 1:O + 1].cpu().numpy(), ref.numpy()) < 1e-5
+    assert y[:, 0].abs().sum() == 0 and y[:, O + 1:].abs().sum() == 0
+
+
+def test_rot6d_and_copy2d():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 160, generator=g)
+    xd = x.cuda()
+    out = torch.zeros(5 * 24, 3, 3, device='cuda')
+    L.run_op(L.Rot6d(xd.data_ptr() + 4 * 10, 160, 24, 120, out.data_ptr()), stream())
+    sync_or_die()
+    ref = O.rot6d_to_rotmat(x[:, 10:154].reshape(-1, 6))
+    assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-5
+    dst = torch.zeros(5, 20, device='cuda')
+    src = torch.arange(7.0).view(1, 7).cuda()
+    L.run_op(L.Copy2d(src.data_ptr(), 7, dst.data_ptr() + 4 * 3, 20, 5, 7, 1), stream())
+    sync_or_die()
+    assert torch.equal(dst[:, 3:10].cpu(), torch.arange(7.0).expand(5, 7))
+
+
+@pytest.mark.parametrize('H', [56, 7])
+def test_pare_head(H):
+    """fused part-attention head vs the oracle restatement of pare_head.py:754-826, :896-906"""
+    meta, gold, sd = load_preset('pare_w32')
+    g = torch.Generator().manual_seed(4)
+    N = 3
+    part = F.relu(torch.randn(N, 128, H, H, generator=g)).half().float()
+    smpl = F.relu(torch.randn(N, 128, H, H, generator=g)).half().float()
+    dev = 'cuda'
+    pa, sa = engine.to_planar(part.to(dev)), engine.to_planar(smpl.to(dev))
+    f = lambda *s: torch.zeros(*s, device=dev)
+    segm, uf, p6, rot, shape, cam = f(N, 25, H, H), f(N, 3072), f(N, 24, 6), f(N, 24, 3, 3), f(N, 10), f(N, 3)
+    scratch = f(int(L.lib().poco_pare_scratch_floats(N, H, H)))
+    w = {k: sd['head.' + k].to(dev).contiguous() for k in (
+        'keypoint_final_layer.weight', 'keypoint_final_layer.bias', 'smpl_final_layer.weight', 'smpl_final_layer.bias',
+        'pose_mlp.weight', 'shape_mlp.weight', 'shape_mlp.bias', 'cam_mlp.weight', 'cam_mlp.bias')}
+    d = L.PareHead(pa.desc(), sa.desc(), *(w[k].data_ptr() for k in w), segm.data_ptr(), uf.data_ptr(), p6.data_ptr(),
+                   rot.data_ptr(), shape.data_ptr(), cam.data_ptr(), scratch.data_ptr())
+    L.run_op(d, stream())
+    sync_or_die()
+    # oracle: same math from the two branch outputs on
+    s = O._SD(sd, 'head.')
+    with torch.no_grad():
+        segm_ref = O.conv(part, s, 'keypoint_final_layer')
+        att = F.softmax(segm_ref[:, 1:].reshape(N, 24, -1), -1)
+        pl = torch.matmul(att, smpl.reshape(N, 128, -1).transpose(2, 1)).transpose(2, 1)
+        cs = torch.matmul(att, O.conv(smpl, s, 'smpl_final_layer').reshape(N, 64, -1).transpose(2, 1)).transpose(2, 1)
+        pose6 = torch.einsum('bcj,ocj->boj', pl, s['pose_mlp.weight'][0, :, :, :, 0, 0]).transpose(2, 1)
+        shape_ref = O.linear(cs.flatten(1), s, 'shape_mlp')
+        cam_ref = O.linear(cs.flatten(1), s, 'cam_mlp')
+        rot_ref = O.rot6d_to_rotmat(pose6).reshape(N, 24, 3, 3)
+    for got, ref, name in ((segm, segm_ref, 'segm'), (uf, pl.reshape(N, -1), 'uncert_feat'), (p6, pose6, 'pose6d'),
+                           (shape, shape_ref, 'shape'), (cam, cam_ref, 'cam'), (rot, rot_ref, 'rotmat')):
+        assert rel_err(got.cpu().numpy(), ref.numpy()) < 2e-5, name
+
+
+@pytest.mark.parametrize('preset', ['pare_w32', 'cliff_w32'])
+def test_realnvp_against_reference_goldens(preset):
+    from common import build_model
+    meta, gold, sd = load_preset(preset)
+    m = build_model(preset, 'cuda')
+    rows = gold['flow_x'].shape[0]
+    ctx = torch.repeat_interleave(torch.from_numpy(gold['flow_ctx']), rows // meta['test_b'], 0).cuda()
+    x, z = torch.from_numpy(gold['flow_x']).cuda(), torch.from_numpy(gold['flow_z']).cuda()
+    lp = m.flow_log_prob(x, ctx)
+    zb, ld = m.flow_backward(x, ctx)
+    fx = m.flow_forward(z, ctx)
+    sync_or_die()
+    assert rel_err(lp.cpu().numpy(), gold['flow_log_prob']) < 2e-5
+    assert rel_err(zb.cpu().numpy(), gold['flow_backward_z']) < 2e-5
+    assert rel_err(ld.cpu().numpy(), gold['flow_logdet']) < 2e-5
+    assert rel_err(fx.cpu().numpy(), gold['flow_forward_x']) < 2e-5
+    # round trip and ragged row count (R not a multiple of the CTA row block)
+    assert rel_err(m.flow_forward(zb[:13], ctx[:13]).cpu().numpy(), gold['flow_x'][:13]) < 1e-4
+    # cond_layer
+    uf = torch.from_numpy(gold['uncert_feat']).cuda()
+    assert rel_err(m.flow_context(uf).cpu().numpy(), gold['flow_ctx']) < 2e-5

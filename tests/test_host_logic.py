@@ -1,0 +1,125 @@
+"""CPU tests of the host side: checkpoint contract, C-ABI surface, weight preparation, and the op
+schedule replayed by the CPU op interpreter (tests/emu.py) against the reference-generated goldens."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import emu
+from common import GATED, PRESETS, build_model, load_preset, rel_err, synthetic_batch
+from poco_b200 import POCO, PocoError, _lib, engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'poco_b200.h')).read()
+    declared = set(re.findall(r'\b(poco_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.poco_version() >= 100
+
+
+def test_ctypes_structs_match_header_sizes():
+    # poco_act: ptr + i64 + 4*i32 = 32 bytes; poco_conv: 2*32 + 3 ptr + i64 + 6*i32 = 120
+    assert ctypes.sizeof(_lib.Act) == 32
+    assert ctypes.sizeof(_lib.Conv) == 120
+    assert ctypes.sizeof(_lib.Linear) == 80
+    assert _lib.Op.u.offset == 8
+
+
+@pytest.mark.parametrize('preset', PRESETS)
+def test_state_dict_contract(preset):
+    """same names / shapes as the reference (spec_<preset>.json was dumped from pocolib.models.POCO)"""
+    meta, _, sd = load_preset(preset)
+    m = build_model(preset)
+    got = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert got == meta['spec']
+    for part in ('backbone', 'head', 'uncert_head', 'flow_head'):
+        assert len(list(getattr(m, part).parameters())) > 0        # trainer.py:598-601 per-module groups
+
+
+def test_load_pretrained_variants(tmp_path):
+    meta, _, sd = load_preset('pare_r50')
+    from oracle import synth_ckpt as S
+    for wrap in (lambda d: d, lambda d: {'model': d}, lambda d: {'state_dict': {'model.' + k: v for k, v in d.items()}}):
+        f = tmp_path / 'ckpt.pt'
+        torch.save(wrap(dict(sd)), f)
+        m = POCO(**meta['kwargs'], smpl_mean_params=S.smpl_mean_params(0), pretrained=str(f))
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, sd[k]), k
+
+
+def test_constructor_errors_and_no_cpu_path():
+    from oracle import synth_ckpt as S
+    with pytest.raises(NameError):
+        POCO(backbone='vgg16-pare', smpl_mean_params=S.smpl_mean_params(0))
+    m = build_model('pare_r50')
+    with pytest.raises(PocoError):
+        m({'img': torch.zeros(1, 3, 224, 224)})            # CPU tensors: there is no fallback
+    with pytest.raises(KeyError):
+        m({})
+
+
+def test_fold_and_pack_weights():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(32, 16, 3, 3, generator=g)
+    bn = (torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g), torch.randn(32, generator=g),
+          torch.rand(32, generator=g) + 0.5)
+    x = torch.randn(2, 16, 9, 9, generator=g)
+    wf, bf = engine.fold_bn(w, None, bn)
+    ref = F.batch_norm(F.conv2d(x, w, padding=1), bn[2], bn[3], bn[0], bn[1], False, 0.0, 1e-5)
+    assert torch.allclose(F.conv2d(x, wf, bf, padding=1), ref, atol=1e-4)
+    p = engine.pack_conv_weight(wf)
+    assert p.shape == (9, 2, 32, 8) and p.dtype == torch.float16
+    t, ci, co = 5, 11, 7
+    assert p[t, ci // 8, co, ci % 8] == wf[co, ci, t // 3, t % 3].half()
+
+
+def test_planar_layout_round_trip():
+    x = torch.randn(3, 24, 5, 7).half().float()
+    a = engine.to_planar(x)
+    assert torch.equal(engine.from_planar(a), x)
+    v = engine.act_view(a)
+    assert v[:, :, 0].abs().sum() == 0 and v[:, :, :, 0].abs().sum() == 0      # zero halo
+    assert v[:, :, -1].abs().sum() == 0 and v[:, :, :, -1].abs().sum() == 0
+
+
+# fp16 storage of weights / activations through ~110 conv layers: what the schedule can deliver
+# against the fp32 reference on this synthetic checkpoint (see DESIGN.md "precision").
+EMU_TOL = {'pred_pose': 6e-2, 'pred_shape': 6e-3, 'pred_cam': 1.5e-2, 'var_pose': 1e-3}
+
+
+@pytest.mark.parametrize('preset', ['pare_r50', 'cliff_w32'])
+def test_schedule_replay_matches_reference(preset):
+    """build the op schedule on CPU buffers, replay it with the op interpreter, compare with the
+    reference goldens: validates graph wiring, buffer reuse, BN folding and weight packing."""
+    meta, gold, _ = load_preset(preset)
+    m = build_model(preset)
+    batch = synthetic_batch(preset)
+    eng = m._build_engine(meta['test_b'], torch.device('cpu'))
+    eng.img.copy_(batch['img'])
+    if eng.bbox is not None:
+        eng.bbox.copy_(batch['bbox_info'])
+    emu.run_plan_ops(eng.plan.ops, eng.plan.keep)
+    for k in GATED:
+        assert rel_err(eng.out[k].reshape(gold[k].shape).numpy(), gold[k]) < EMU_TOL[k], k
+    assert eng.plan.num_ops == len(eng.plan.ops) > 50
+    assert eng.plan.flops > 0
+
+
+def test_buffer_pool_keeps_zero_halo():
+    """pool reuse never hands a buffer to a tensor of different spatial geometry"""
+    b = engine.PlanBuilder({}, 2, 'cpu')
+    a = b.act(32, 8, 8)
+    b.free(a)
+    c = b.act(16, 8, 8)
+    assert c.buf is a.buf and c.C == 16
+    d = b.act(16, 4, 4)
+    assert d.buf is not a.buf
