@@ -162,7 +162,21 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def per_kernel_pass(eng, torch, reps=2):
+def op_label(op):
+    from poco_b200 import _lib as L
+    if op.kind == L.OP_CONV:
+        c = op.u.conv
+        return f'conv {c.in_.C}->{c.out.C} k{c.kh} s{c.stride} {c.in_.H}->{c.out.H}' + (' +res' if c.residual else '')
+    if op.kind == L.OP_LINEAR:
+        return f'linear {op.u.linear.M}x{op.u.linear.I}->{op.u.linear.O}'
+    if op.kind == L.OP_FUSE_SUM:
+        return f'fuse_sum x{op.u.fuse_sum.n_in} c{op.u.fuse_sum.out.C} h{op.u.fuse_sum.out.H}'
+    if op.kind == L.OP_UPSAMPLE2X:
+        return f'upsample2x c{op.u.upsample2x.in_.C} h{op.u.upsample2x.in_.H}'
+    return L._FIELD_OF_KIND[op.kind]
+
+
+def per_kernel_pass(eng, torch, reps=2, dump=None):
     """eager op-by-op replay with CUDA events: time share and algorithmic FLOPs per kernel class"""
     from poco_b200 import _lib as L
     s = torch.cuda.current_stream().cuda_stream
@@ -176,8 +190,10 @@ def per_kernel_pass(eng, torch, reps=2):
             evs[i + 1].record()
         torch.cuda.synchronize()
         classes = {}
+        rows = []
         for i, op in enumerate(ops):
             ms = evs[i].elapsed_time(evs[i + 1])
+            rows.append((i, op_label(op), ms))
             if op.kind == L.OP_CONV:
                 c = op.u.conv
                 lin = c.stride == 1 and c.in_.H == c.out.H and ((c.kh == 3 and c.pad == 1) or (c.kh == 1 and c.pad == 0))
@@ -189,6 +205,16 @@ def per_kernel_pass(eng, torch, reps=2):
             e['ms'] += ms
             e['flops'] += fl
             e['launches'] += 1
+    if dump:
+        agg = {}
+        for i, lab, ms in rows:
+            a = agg.setdefault(lab, [0, 0.0])
+            a[0] += 1
+            a[1] += ms
+        with open(dump, 'w') as f:
+            f.write('label,count,total_ms,avg_us\n')
+            for lab, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write(f'{lab},{n},{ms:.4f},{ms / n * 1e3:.2f}\n')
     return classes
 
 
@@ -283,7 +309,7 @@ def run_gpu_arm(args):
     shares = {}
     if rank == 0:
         with torch.no_grad():
-            classes = per_kernel_pass(eng, torch)
+            classes = per_kernel_pass(eng, torch, dump=args.dump_ops)
         tot = sum(c['ms'] for c in classes.values())
         dom = max(classes, key=lambda k: classes[k]['ms'])
         d = classes[dom]
@@ -330,6 +356,7 @@ def main():
     ap.add_argument('--batch', type=int, default=256, help='crops per GPU (weak scaling)')
     ap.add_argument('--cpu-sample', type=int, default=16, help='crops per CPU-arm forward (bounded sample)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dump-ops', default=None, help='write the per-op timing table (eager, CUDA events) to this CSV')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
