@@ -131,40 +131,59 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     const __half* wg = p.w + size_t(nb) * p.n_tile * 8;       // this N block's column offset inside a slab row
 
     // ---------------------------------------------------------------- weight loader (shared by both modes)
+    // All producer / MMA control flow below is warp-convergent with the single issuing lane chosen by
+    // elect.sync: every operand of the bulk copies and of tcgen05.mma is then provably warp-uniform
+    // and lives in uniform registers (a divergent `if (lane == 0)` loop made ptxas wrap each UBLKCP /
+    // UTCHMMA in a vote + branch "waterfall", ~60 issue slots per MMA -- see profiles/).
+    // When this CTA covers all of Cout (one N block), consecutive 8-channel slabs are contiguous in
+    // global and shared memory, so `group` slabs travel as one bulk copy.
+    const bool whole_n = p.n_tile == p.Cout;
     auto load_resident_weights = [&]() {
         mbar_arrive_expect_tx(smem_u32(&hdr->w_ready), uint32_t(p.w_res_bytes));
-        for (int s = 0; s < taps * cin8; ++s)
-            bulk_g2s(smem_u32(w_res) + uint32_t(s) * slab_bytes, wg + size_t(s) * p.Cout * 8, slab_bytes,
+        const int total = taps * cin8;
+        const int group = whole_n ? min(total, 64) : 1;          // <= 64 slabs (<= 256 KB) per copy
+        for (int s = 0; s < total; s += group) {
+            const int g = min(group, total - s);
+            bulk_g2s(smem_u32(w_res) + uint32_t(s) * slab_bytes, wg + size_t(s) * p.Cout * 8, uint32_t(g) * slab_bytes,
                      smem_u32(&hdr->w_ready));
+        }
+    };
+    auto load_stage_weights = [&](uint32_t ws, uint32_t bar, int t0, int t1, int c) {
+        // taps [t0, t1) of K chunk c -> ws, slabs ordered [tap][plane]
+        for (int t = t0; t < t1; ++t) {
+            const uint32_t dst = ws + uint32_t((t - t0) * planes_per_chunk) * slab_bytes;
+            const __half* src = wg + size_t(t * cin8 + c * planes_per_chunk) * p.Cout * 8;
+            if (whole_n) {
+                bulk_g2s(dst, src, uint32_t(planes_per_chunk) * slab_bytes, bar);
+            } else {
+                for (int j = 0; j < planes_per_chunk; ++j)
+                    bulk_g2s(dst + uint32_t(j) * slab_bytes, src + size_t(j) * p.Cout * 8, slab_bytes, bar);
+            }
+        }
     };
 
     if (MODE == MODE_LINEAR && warp == 0) {
         // ============================================================ producer (bulk copies)
-        if (lane == 0) {
-            if (p.w_resident) load_resident_weights();
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-                const long long q0 = (long long)tile * kTileM - p.halo;
-                for (int c = 0; c < p.n_chunks; ++c, ++it) {
-                    const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
-                    mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
+        if (p.w_resident && elect_one()) load_resident_weights();
+        __syncwarp();
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+            const long long q0 = (long long)tile * kTileM - p.halo;
+            for (int c = 0; c < p.n_chunks; ++c, ++it) {
+                const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+                mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
+                if (elect_one()) {
                     const uint32_t bar = smem_u32(&hdr->full[slot]);
                     const uint32_t tx = uint32_t(planes_per_chunk) * p.a_copy_bytes +
                                         (p.w_resident ? 0u : uint32_t(p.w_stage_bytes));
                     mbar_arrive_expect_tx(bar, tx);
-                    uint8_t* st = stage0 + size_t(slot) * stage_bytes;
-                    for (int j = 0; j < planes_per_chunk; ++j) {
-                        const __half* src = p.in + ((long long)(c * planes_per_chunk + j) * p.in_plane + q0) * 8;
-                        bulk_g2s(smem_u32(st) + uint32_t(j) * p.a_plane_bytes, src, uint32_t(p.a_copy_bytes), bar);
-                    }
-                    if (!p.w_resident) {
-                        const uint32_t ws = smem_u32(st) + p.a_stage_bytes;
-                        for (int t = 0; t < taps; ++t)
-                            for (int j = 0; j < planes_per_chunk; ++j)
-                                bulk_g2s(ws + uint32_t(t * planes_per_chunk + j) * slab_bytes,
-                                         wg + size_t(t * cin8 + c * planes_per_chunk + j) * p.Cout * 8, slab_bytes, bar);
-                    }
+                    const uint32_t st = smem_u32(stage0 + size_t(slot) * stage_bytes);
+                    const __half* src = p.in + ((long long)(c * planes_per_chunk) * p.in_plane + q0) * 8;
+                    for (int j = 0; j < planes_per_chunk; ++j, src += p.in_plane * 8)
+                        bulk_g2s(st + uint32_t(j) * p.a_plane_bytes, src, uint32_t(p.a_copy_bytes), bar);
+                    if (!p.w_resident) load_stage_weights(st + p.a_stage_bytes, bar, 0, taps, c);
                 }
+                __syncwarp();
             }
         }
     } else if (MODE == MODE_GATHER && warp < 4) {
@@ -207,75 +226,77 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             mbar_arrive(smem_u32(&hdr->full[d % p.stages]));
     } else if (MODE == MODE_GATHER && warp == R::kWWarp) {
         // ============================================================ W producer (bulk copies)
-        if (lane == 0) {
-            if (p.w_resident) {
-                load_resident_weights();
-            } else {
-                uint32_t it = 0;
-                for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x)
-                    for (int t = 0; t < taps; ++t)
-                        for (int c = 0; c < p.n_chunks; ++c, ++it) {
-                            const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
-                            mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
+        if (p.w_resident) {
+            if (elect_one()) load_resident_weights();
+            __syncwarp();
+        } else {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x)
+                for (int t = 0; t < taps; ++t)
+                    for (int c = 0; c < p.n_chunks; ++c, ++it) {
+                        const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+                        mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
+                        if (elect_one()) {
                             const uint32_t bar = smem_u32(&hdr->full[slot]);
                             mbar_arrive_expect_tx(bar, uint32_t(p.w_stage_bytes));
-                            const uint32_t ws = smem_u32(stage0 + size_t(slot) * stage_bytes) + p.a_stage_bytes;
-                            for (int j = 0; j < planes_per_chunk; ++j)
-                                bulk_g2s(ws + uint32_t(j) * slab_bytes,
-                                         wg + size_t(t * cin8 + c * planes_per_chunk + j) * p.Cout * 8, slab_bytes, bar);
+                            load_stage_weights(smem_u32(stage0 + size_t(slot) * stage_bytes) + p.a_stage_bytes, bar, t, t + 1, c);
                         }
-            }
+                        __syncwarp();
+                    }
         }
     } else if (warp == R::kMmaWarp) {
-        // ============================================================ MMA issuer (one thread)
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(kTileM, uint32_t(p.n_tile));
-            if (p.w_resident) mbar_wait(smem_u32(&hdr->w_ready), 0);
-            uint32_t it = 0, tl = 0;
-            const int Wp = p.Wout + 2;
-            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
-                const uint32_t buf = tl & 1u;
-                mbar_wait(smem_u32(&hdr->tmem_empty[buf]), ((tl >> 1) & 1u) ^ 1u);
+        // ============================================================ MMA issuer (warp-convergent, one elected lane issues)
+        const uint32_t idesc = umma_idesc_f16(kTileM, uint32_t(p.n_tile));
+        // descriptor = hi:lo, lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version<<14: only lo changes
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+        const uint32_t a_lbo = (uint32_t(p.a_plane_bytes) >> 4) << 16, b_lbo = (slab_bytes >> 4) << 16;
+        const uint32_t a_kstep = (2u * uint32_t(p.a_plane_bytes)) >> 4, b_kstep = (2u * slab_bytes) >> 4;
+        const int ksteps = planes_per_chunk >> 1;
+        const int Wp = p.Wout + 2;
+        if (p.w_resident) mbar_wait(smem_u32(&hdr->w_ready), 0);
+        uint32_t it = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
+            const uint32_t buf = tl & 1u;
+            mbar_wait(smem_u32(&hdr->tmem_empty[buf]), ((tl >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * buf_cols;
+            for (int ki = 0; ki < kiters; ++ki, ++it) {
+                const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+                mbar_wait(smem_u32(&hdr->full[slot]), ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * buf_cols;
-                uint32_t acc = 0;
-                for (int ki = 0; ki < kiters; ++ki, ++it) {
-                    const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
-                    mbar_wait(smem_u32(&hdr->full[slot]), ph);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint32_t a_base = smem_u32(stage0 + size_t(slot) * stage_bytes);
                     const uint32_t w_stage = a_base + p.a_stage_bytes;
+                    uint32_t acc = ki > 0 ? 1u : 0u;
                     if (MODE == MODE_LINEAR) {
                         const int c = ki;
+                        const uint32_t w0 = p.w_resident ? smem_u32(w_res) + uint32_t(c * planes_per_chunk) * slab_bytes : w_stage;
+                        const uint32_t w_tap_stride = (p.w_resident ? uint32_t(cin8) : uint32_t(planes_per_chunk)) * slab_bytes;
                         for (int t = 0; t < taps; ++t) {
                             // tap (r,s): shift of (r-1) rows and (s-1) pixels inside the landed run
                             const int shift = taps == 1 ? 0 : ((t / 3 - 1) * Wp + (t % 3 - 1));
-                            const uint32_t a_tap = a_base + uint32_t(p.halo + shift) * 16u;
-                            const uint32_t w_tap = p.w_resident
-                                ? smem_u32(w_res) + uint32_t(t * cin8 + c * planes_per_chunk) * slab_bytes
-                                : w_stage + uint32_t(t * planes_per_chunk) * slab_bytes;
-                            for (int k = 0; k < (planes_per_chunk >> 1); ++k) {
-                                const uint64_t da = umma_desc(a_tap + uint32_t(2 * k) * p.a_plane_bytes, p.a_plane_bytes, 128);
-                                const uint64_t db = umma_desc(w_tap + uint32_t(2 * k) * slab_bytes, slab_bytes, 128);
-                                umma_f16(d_tmem, da, db, idesc, acc);
+                            uint32_t a_lo = (((a_base + uint32_t(p.halo + shift) * 16u) & 0x3FFFFu) >> 4) | a_lbo;
+                            uint32_t b_lo = (((w0 + uint32_t(t) * w_tap_stride) & 0x3FFFFu) >> 4) | b_lbo;
+                            for (int k = 0; k < ksteps; ++k, a_lo += a_kstep, b_lo += b_kstep) {
+                                umma_f16(d_tmem, (uint64_t(desc_hi) << 32) | a_lo, (uint64_t(desc_hi) << 32) | b_lo, idesc, acc);
                                 acc = 1;
                             }
                         }
                     } else {
                         const int t = ki / p.n_chunks, c = ki % p.n_chunks;
-                        const uint32_t w_tap = p.w_resident
-                            ? smem_u32(w_res) + uint32_t(t * cin8 + c * planes_per_chunk) * slab_bytes
-                            : w_stage;
-                        for (int k = 0; k < (planes_per_chunk >> 1); ++k) {
-                            const uint64_t da = umma_desc(a_base + uint32_t(2 * k) * p.a_plane_bytes, p.a_plane_bytes, 128);
-                            const uint64_t db = umma_desc(w_tap + uint32_t(2 * k) * slab_bytes, slab_bytes, 128);
-                            umma_f16(d_tmem, da, db, idesc, acc);
+                        const uint32_t w0 = p.w_resident
+                            ? smem_u32(w_res) + uint32_t(t * cin8 + c * planes_per_chunk) * slab_bytes : w_stage;
+                        uint32_t a_lo = ((a_base & 0x3FFFFu) >> 4) | a_lbo;
+                        uint32_t b_lo = ((w0 & 0x3FFFFu) >> 4) | b_lbo;
+                        for (int k = 0; k < ksteps; ++k, a_lo += a_kstep, b_lo += b_kstep) {
+                            umma_f16(d_tmem, (uint64_t(desc_hi) << 32) | a_lo, (uint64_t(desc_hi) << 32) | b_lo, idesc, acc);
                             acc = 1;
                         }
                     }
                     umma_commit(smem_u32(&hdr->empty[slot]));      // smem slot free once these MMAs retire
+                    if (ki == kiters - 1) umma_commit(smem_u32(&hdr->tmem_full[buf]));   // accumulator complete
                 }
-                umma_commit(smem_u32(&hdr->tmem_full[buf]));       // accumulator complete
+                __syncwarp();
             }
         }
     } else if (warp >= R::kEpiWarp0) {
@@ -431,7 +452,7 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
             const int w_stage = resident ? 0 : (mode == MODE_LINEAR ? taps : 1) * kc * n_tile * 2;
             const int avail = budget - (resident ? round_up(w_total, 128) : 0);
             const int min_stages = mode == MODE_GATHER ? kGatherLag + 1 : 2;
-            int stages = std::min(mode == MODE_GATHER ? 6 : 4, avail / (a_stage + w_stage));
+            int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
             if (stages < min_stages) continue;
             p.kc = kc; p.n_chunks = in.C / kc;
             p.w_resident = resident;
