@@ -23,6 +23,7 @@
 //   * persistent grid: <= one CTA per SM, static round-robin over M tiles; mbarrier pipelines
 //     smem full/empty (producer <-> MMA) and tmem full/empty (MMA <-> epilogue).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -33,10 +34,15 @@ namespace poco {
 namespace {
 
 constexpr int kMaxStages = 8;
+constexpr int kMaxAccBufs = 8;                     // TMEM accumulator ring (512 columns / n_tile)
 constexpr int kTileM = 128;
 constexpr int kSmemBudget = 225 * 1024;   // of 227 KB usable per CTA
 constexpr int kHeaderBytes = 2048;        // barriers + bias
 constexpr int kGatherLag = 2;
+constexpr int kItemBytes = 2 * kTileM * 16;        // epilogue work item = 16 columns = 2 output planes x 128 rows
+constexpr int kOutRing = 3, kResRing = 4;
+constexpr int kHalfRingBytes = (kOutRing + kResRing) * kItemBytes;
+constexpr int kRingBytes = 2 * kHalfRingBytes;     // two epilogue halves
 
 enum { MODE_LINEAR = 0, MODE_GATHER = 1 };
 
@@ -57,20 +63,23 @@ struct ConvTcParams {
     int kc, n_chunks;
     int n_tile;
     int w_resident;
-    int stages;
+    int stages;           // per ring
+    int rings;            // 1, or 2 = one shared-memory stage ring per MMA issuer warp (tiles alternate)
     int num_m_tiles;
     long long P_out;
     int a_plane_bytes, a_copy_bytes, a_stage_bytes, w_stage_bytes, w_res_bytes;
     int halo;
-    int tmem_cols;
+    int tmem_cols, acc_bufs;
+    int debug;            // POCO_CONV_DEBUG bits (bring-up only): 1 skip epilogue work, 2 skip MMAs, 4 skip A loads
 };
 
 struct SmemHeader {
     unsigned long long full[kMaxStages];
     unsigned long long empty[kMaxStages];
-    unsigned long long tmem_full[2];
-    unsigned long long tmem_empty[2];
+    unsigned long long tmem_full[kMaxAccBufs];
+    unsigned long long tmem_empty[kMaxAccBufs];
     unsigned long long w_ready;
+    unsigned long long res_full[2 * kResRing];
     uint32_t tmem_base;
     uint32_t pad_[5];
     float bias[256];
@@ -79,20 +88,20 @@ static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
 
 template <int MODE>
 struct Roles {
-    // MODE_LINEAR: warp 0 producer, warp 1 MMA, warps 2-5 epilogue
-    // MODE_GATHER: warps 0-3 A producers, warp 4 MMA, warp 5 W producer, warps 6-9 epilogue
+    // MODE_LINEAR: warp 0 producer, warps 1-2 MMA issuers (alternate tiles), warps 3-10 epilogue
+    // MODE_GATHER: warps 0-3 A producers, warps 4-5 MMA issuers, warp 6 W producer, warps 7-14 epilogue
     static constexpr int kProducerWarps = MODE == MODE_LINEAR ? 1 : 4;
     static constexpr int kMmaWarp = MODE == MODE_LINEAR ? 1 : 4;
-    static constexpr int kWWarp = MODE == MODE_LINEAR ? 0 : 5;
-    static constexpr int kEpiWarp0 = MODE == MODE_LINEAR ? 2 : 6;
-    static constexpr int kThreads = (kEpiWarp0 + 4) * 32;
+    static constexpr int kWWarp = MODE == MODE_LINEAR ? 0 : 6;
+    static constexpr int kEpiWarp0 = MODE == MODE_LINEAR ? 3 : 7;
+    static constexpr int kThreads = (kEpiWarp0 + 8) * 32;
 };
 
 template <int MODE>
 __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
-    uint8_t* w_res = smem + kHeaderBytes;
+    uint8_t* w_res = smem + kHeaderBytes + kRingBytes;
     uint8_t* stage0 = w_res + p.w_res_bytes;
     const int stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
 
@@ -109,15 +118,16 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     // ---------------------------------------------------------------- setup
     if (threadIdx.x == 0) {
         const uint32_t full_count = MODE == MODE_LINEAR ? 1u : (128u + (p.w_resident ? 0u : 1u));
-        for (int i = 0; i < p.stages; ++i) {
+        for (int i = 0; i < p.stages * p.rings; ++i) {
             mbar_init(smem_u32(&hdr->full[i]), full_count);
             mbar_init(smem_u32(&hdr->empty[i]), 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < p.acc_bufs; ++i) {
             mbar_init(smem_u32(&hdr->tmem_full[i]), 1);
-            mbar_init(smem_u32(&hdr->tmem_empty[i]), 4);
+            mbar_init(smem_u32(&hdr->tmem_empty[i]), 8);
         }
         mbar_init(smem_u32(&hdr->w_ready), 1);
+        for (int i = 0; i < 2 * kResRing; ++i) mbar_init(smem_u32(&hdr->res_full[i]), 1);
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) hdr->bias[i] = p.bias[nb * p.n_tile + i];
@@ -126,7 +136,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
-    const uint32_t buf_cols = uint32_t(p.tmem_cols) >> 1;
+    const uint32_t buf_cols = uint32_t(p.tmem_cols) / uint32_t(p.acc_bufs);
+    const uint32_t nacc = uint32_t(p.acc_bufs);
 
     const __half* wg = p.w + size_t(nb) * p.n_tile * 8;       // this N block's column offset inside a slab row
 
@@ -166,20 +177,23 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         // ============================================================ producer (bulk copies)
         if (p.w_resident && elect_one()) load_resident_weights();
         __syncwarp();
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+        uint32_t its[2] = {0u, 0u}, tl = 0;
+        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
             const long long q0 = (long long)tile * kTileM - p.halo;
-            for (int c = 0; c < p.n_chunks; ++c, ++it) {
-                const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+            const uint32_t ring = p.rings == 2 ? (tl & 1u) : 0u;
+            for (int c = 0; c < p.n_chunks; ++c) {
+                const uint32_t it = its[ring]++;
+                const uint32_t slot = ring * p.stages + it % p.stages, ph = (it / p.stages) & 1u;
                 mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
                 if (elect_one()) {
                     const uint32_t bar = smem_u32(&hdr->full[slot]);
-                    const uint32_t tx = uint32_t(planes_per_chunk) * p.a_copy_bytes +
+                    const bool skip_a = (p.debug & 4) != 0;
+                    const uint32_t tx = (skip_a ? 0u : uint32_t(planes_per_chunk) * p.a_copy_bytes) +
                                         (p.w_resident ? 0u : uint32_t(p.w_stage_bytes));
                     mbar_arrive_expect_tx(bar, tx);
                     const uint32_t st = smem_u32(stage0 + size_t(slot) * stage_bytes);
                     const __half* src = p.in + ((long long)(c * planes_per_chunk) * p.in_plane + q0) * 8;
-                    for (int j = 0; j < planes_per_chunk; ++j, src += p.in_plane * 8)
+                    for (int j = 0; j < planes_per_chunk && !skip_a; ++j, src += p.in_plane * 8)
                         bulk_g2s(st + uint32_t(j) * p.a_plane_bytes, src, uint32_t(p.a_copy_bytes), bar);
                     if (!p.w_resident) load_stage_weights(st + p.a_stage_bytes, bar, 0, taps, c);
                 }
@@ -244,8 +258,12 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                         __syncwarp();
                     }
         }
-    } else if (warp == R::kMmaWarp) {
-        // ============================================================ MMA issuer (warp-convergent, one elected lane issues)
+    } else if (warp == R::kMmaWarp || warp == R::kMmaWarp + 1) {
+        // ============================================================ MMA issuers (warp-convergent, one elected lane issues)
+        // tcgen05.mma blocks its issuing thread for about the instruction's execution time (shallow
+        // queue) and the per-tile barrier traffic costs ~1k cycles; two warps taking alternate tiles
+        // keep the tensor pipe fed while the other one synchronises (profiles/r01_conv_role_bench.csv).
+        const uint32_t mw = uint32_t(warp - R::kMmaWarp);
         const uint32_t idesc = umma_idesc_f16(kTileM, uint32_t(p.n_tile));
         // descriptor = hi:lo, lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version<<14: only lo changes
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);
@@ -256,12 +274,13 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         if (p.w_resident) mbar_wait(smem_u32(&hdr->w_ready), 0);
         uint32_t it = 0, tl = 0;
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
-            const uint32_t buf = tl & 1u;
-            mbar_wait(smem_u32(&hdr->tmem_empty[buf]), ((tl >> 1) & 1u) ^ 1u);
+            if (p.rings == 2 ? (tl & 1u) != mw : mw != 0u) continue;   // one ring per issuer; a single ring is served by warp 0
+            const uint32_t buf = tl % nacc;
+            mbar_wait(smem_u32(&hdr->tmem_empty[buf]), ((tl / nacc) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * buf_cols;
             for (int ki = 0; ki < kiters; ++ki, ++it) {
-                const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+                const uint32_t slot = (p.rings == 2 ? mw * p.stages : 0u) + it % p.stages, ph = (it / p.stages) & 1u;
                 mbar_wait(smem_u32(&hdr->full[slot]), ph);
                 tc_fence_after();
                 if (elect_one()) {
@@ -272,7 +291,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                         const int c = ki;
                         const uint32_t w0 = p.w_resident ? smem_u32(w_res) + uint32_t(c * planes_per_chunk) * slab_bytes : w_stage;
                         const uint32_t w_tap_stride = (p.w_resident ? uint32_t(cin8) : uint32_t(planes_per_chunk)) * slab_bytes;
-                        for (int t = 0; t < taps; ++t) {
+                        for (int t = 0; t < ((p.debug & 2) ? 0 : taps); ++t) {
                             // tap (r,s): shift of (r-1) rows and (s-1) pixels inside the landed run
                             const int shift = taps == 1 ? 0 : ((t / 3 - 1) * Wp + (t % 3 - 1));
                             uint32_t a_lo = (((a_base + uint32_t(p.halo + shift) * 16u) & 0x3FFFFu) >> 4) | a_lbo;
@@ -300,41 +319,100 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             }
         }
     } else if (warp >= R::kEpiWarp0) {
-        // ============================================================ epilogue (4 warps = 128 TMEM lanes)
+        // ============================================================ epilogue (2 halves x 4 warps)
+        // Work item = 16 accumulator columns (2 output planes) of one tile; the two halves take
+        // alternate items, so 8 warps hide each other's TMEM / shared-memory / ALU latencies.
+        // Per half: residual tiles arrive by bulk copy into a 4-deep shared-memory ring (prefetched
+        // 4 items ahead by an elected lane), results are staged in a 3-deep ring and leave with one
+        // 2 KB bulk store per plane -- in the planar layout a (tile, plane) is one contiguous run.
+        // Halo rows are stored as zeros (keeps the zero-halo invariant); rows past the end of the
+        // plane are clipped.
+        const int ew = warp - R::kEpiWarp0;
+        const int half = ew >> 2;
         const int lg = warp & 3;                        // TMEM lane group this warp may access
         const int row = lg * 32 + lane;
+        const bool lead_warp = (ew & 3) == 0;
         const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
         const int plane0 = (nb * p.n_tile) >> 3;
-        uint32_t tl = 0;
+        const int items = p.n_tile >> 4;                // 16-column items per tile
+        const int my_items = (items - half + 1) >> 1;   // items half, half+2, ...
+        const bool has_res = p.res != nullptr;
+        uint8_t* out_ring = smem + kHeaderBytes + half * kHalfRingBytes;
+        uint8_t* res_ring = out_ring + kOutRing * kItemBytes;
+        unsigned long long* res_full = hdr->res_full + half * kResRing;
+        auto prefetch_residual = [&](uint32_t g) {      // elected lane: residual of this half's g-th item
+            const int tl_ = int(g / uint32_t(my_items)), item = half + 2 * int(g % uint32_t(my_items));
+            const long long tile_ = (long long)blockIdx.x + (long long)tl_ * gridDim.x;
+            if (tile_ >= p.num_m_tiles) return;
+            const long long q0 = tile_ * kTileM;
+            const uint32_t rows = uint32_t(min((long long)kTileM, p.P_out - q0));
+            const uint32_t slot = g % kResRing;
+            const uint32_t bar = smem_u32(&res_full[slot]);
+            mbar_arrive_expect_tx(bar, 2u * rows * 16u);
+            const __half* src = p.res + ((long long)(plane0 + item * 2) * p.res_plane + q0) * 8;
+            const uint32_t dst = smem_u32(res_ring) + slot * kItemBytes;
+            bulk_g2s(dst, src, rows * 16u, bar);
+            bulk_g2s(dst + 2048u, src + p.res_plane * 8, rows * 16u, bar);
+        };
+        if (has_res && lead_warp && my_items > 0) {
+            if (elect_one())
+                for (uint32_t g0 = 0; g0 < uint32_t(kResRing); ++g0) prefetch_residual(g0);
+            __syncwarp();
+        }
+        // position of this thread's row inside its crop, advanced incrementally from tile to tile
+        const uint32_t step = uint32_t(((long long)gridDim.x * kTileM) % HpWp_o);
+        uint32_t rem = uint32_t(((long long)blockIdx.x * kTileM + row) % HpWp_o);
+        const uint32_t magic_w = 0xFFFFFFFFu / uint32_t(Wp_o) + 1u;      // exact floor(n / Wp) for n < 2^16
+        uint32_t tl = 0, g = 0;
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
-            const uint32_t buf = tl & 1u;
-            const long long q = (long long)tile * kTileM + row;
-            const int rem = int(q % HpWp_o);
-            const int yy = rem / Wp_o, xx = rem % Wp_o;
-            const bool interior = q < p.P_out && yy >= 1 && yy <= p.Hout && xx >= 1 && xx <= p.Wout;
-            mbar_wait(smem_u32(&hdr->tmem_full[buf]), (tl >> 1) & 1u);
+            const uint32_t buf = tl % nacc;
+            const long long q0 = (long long)tile * kTileM;
+            const uint32_t yy = __umulhi(rem, magic_w), xx = rem - yy * uint32_t(Wp_o);
+            const bool interior = q0 + row < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout);
+            rem += step;
+            if (rem >= uint32_t(HpWp_o)) rem -= uint32_t(HpWp_o);
+            const uint32_t rows_valid = uint32_t(min((long long)kTileM, p.P_out - q0));
+            mbar_wait(smem_u32(&hdr->tmem_full[buf]), (tl / nacc) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + buf * buf_cols + (uint32_t(lg * 32) << 16);
-            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+            if (p.debug & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
+                continue;
+            }
+            for (int k = 0; k < my_items; ++k, ++g) {
+                const int item = half + 2 * k;
+                const int c0 = item * 16;
                 uint32_t v[16];
                 tmem_ld16(taddr + uint32_t(c0), v);
                 tmem_ld_wait();
-                if (interior) {
-                    float f[16];
+                if (k == my_items - 1) {                // this warp is done with the accumulator buffer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
+                }
+                const uint32_t rslot = g % kResRing, oslot = g % kOutRing;
+                if (has_res) mbar_wait(smem_u32(&res_full[rslot]), (g / kResRing) & 1u);
+                uint8_t* ob = out_ring + oslot * kItemBytes + row * 16;
+                const uint8_t* rb = res_ring + rslot * kItemBytes + row * 16;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + hdr->bias[c0 + i];
-                    const long long o0 = ((long long)(plane0 + (c0 >> 3)) * p.out_plane + q) * 8;
-                    if (p.relu == 2) {          // ReLU before the residual add (hrnet_cls.py:473-474)
+                for (int pl = 0; pl < 2; ++pl) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(&hdr->bias[c0 + pl * 8]);
+                    const float4 b1 = *reinterpret_cast<const float4*>(&hdr->bias[c0 + pl * 8 + 4]);
+                    float f[8] = {__uint_as_float(v[pl * 8 + 0]) + b0.x, __uint_as_float(v[pl * 8 + 1]) + b0.y,
+                                  __uint_as_float(v[pl * 8 + 2]) + b0.z, __uint_as_float(v[pl * 8 + 3]) + b0.w,
+                                  __uint_as_float(v[pl * 8 + 4]) + b1.x, __uint_as_float(v[pl * 8 + 5]) + b1.y,
+                                  __uint_as_float(v[pl * 8 + 6]) + b1.z, __uint_as_float(v[pl * 8 + 7]) + b1.w};
+                    if (p.relu == 2) {                  // ReLU before the residual add (hrnet_cls.py:473-474)
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
                     }
-                    if (p.res != nullptr) {
-                        const long long r0 = ((long long)(plane0 + (c0 >> 3)) * p.res_plane + q) * 8;
-                        const uint4 ra = *reinterpret_cast<const uint4*>(p.res + r0);
-                        const uint4 rb = *reinterpret_cast<const uint4*>(p.res + r0 + p.res_plane * 8);
-                        const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                    if (has_res) {
+                        const uint4 r4 = *reinterpret_cast<const uint4*>(rb + pl * 2048);
+                        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
+                        for (int i = 0; i < 4; ++i) {
                             const float2 t2 = unpack_half2(rr[i]);
                             f[2 * i] += t2.x;
                             f[2 * i + 1] += t2.y;
@@ -342,20 +420,42 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     }
                     if (p.relu == 1) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
                     }
-                    uint4 oa, ob;
-                    oa.x = pack_half2(f[0], f[1]);   oa.y = pack_half2(f[2], f[3]);
-                    oa.z = pack_half2(f[4], f[5]);   oa.w = pack_half2(f[6], f[7]);
-                    ob.x = pack_half2(f[8], f[9]);   ob.y = pack_half2(f[10], f[11]);
-                    ob.z = pack_half2(f[12], f[13]); ob.w = pack_half2(f[14], f[15]);
-                    *reinterpret_cast<uint4*>(p.out + o0) = oa;
-                    *reinterpret_cast<uint4*>(p.out + o0 + p.out_plane * 8) = ob;
+                    uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
+                    if (interior) {
+                        o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
+                        o4.z = pack_half2(f[4], f[5]); o4.w = pack_half2(f[6], f[7]);
+                    }
+                    *reinterpret_cast<uint4*>(ob + pl * 2048) = o4;
+                }
+                fence_proxy_async_smem();               // staged results -> visible to the bulk-store engine
+                if (lead_warp) {                        // out slot of item g+1 is free once store g-2 has read its smem
+                    if (elect_one()) bulk_store_wait_read<kOutRing - 2>();
+                    __syncwarp();
+                }
+                named_barrier_sync(1 + half, 128);
+                if (lead_warp) {
+                    if (elect_one()) {
+                        __half* dst = p.out + ((long long)(plane0 + item * 2) * p.out_plane + q0) * 8;
+                        const uint32_t src = smem_u32(out_ring) + oslot * kItemBytes;
+                        bulk_s2g(dst, src, rows_valid * 16u);
+                        bulk_s2g(dst + p.out_plane * 8, src + 2048u, rows_valid * 16u);
+                        bulk_store_commit();
+                        if (has_res) prefetch_residual(g + kResRing);       // its ring slot was consumed above
+                    }
+                    __syncwarp();
                 }
             }
-            tc_fence_before();
+            if (my_items == 0) {                        // (n_tile == 16: the second half has no columns)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
+            }
+        }
+        if (lead_warp) {
+            if (elect_one()) bulk_store_wait_all();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
         }
     }
 
@@ -410,6 +510,10 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
     p.Cin = in.C; p.Cout = out.C;
     p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad;
     p.relu = d->relu;
+    {
+        const char* dbg = getenv("POCO_CONV_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+    }
     p.P_out = int64_t(out.N) * (out.H + 2) * (out.W + 2);
     p.num_m_tiles = int((p.P_out + kTileM - 1) / kTileM);
 
@@ -420,15 +524,16 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
     POCO_CHECK(n_tile > 0, "no valid N tile");
     p.n_tile = n_tile;
     const int n_blocks = out.C / n_tile;
-    int cols = 32;
-    while (cols < 2 * n_tile) cols <<= 1;
-    p.tmem_cols = cols;
+    int cols = 32;                      // accumulator buffer pitch: power of two >= n_tile
+    while (cols < n_tile) cols <<= 1;
+    p.acc_bufs = std::min(kMaxAccBufs, 512 / cols);      // the MMA warp may run this many tiles ahead of the epilogue
+    p.tmem_cols = cols * p.acc_bufs;
 
     const int taps = d->kh * d->kw;
     const bool linear = d->stride == 1 && in.H == out.H && in.W == out.W &&
                         ((d->kh == 3 && d->kw == 3 && d->pad == 1) || (d->kh == 1 && d->kw == 1 && d->pad == 0));
     const int mode = linear ? MODE_LINEAR : MODE_GATHER;
-    const int budget = kSmemBudget - kHeaderBytes;
+    const int budget = kSmemBudget - kHeaderBytes - kRingBytes;
     const int w_total = taps * in.C * n_tile * 2;
 
     if (mode == MODE_LINEAR) {
@@ -458,7 +563,8 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
             p.w_resident = resident;
             p.w_res_bytes = resident ? round_up(w_total, 128) : 0;
             p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
-            p.stages = stages;
+            p.rings = (mode == MODE_LINEAR && stages >= 4) ? 2 : 1;
+            p.stages = stages / p.rings;
             found = true;
         }
     }
@@ -466,7 +572,7 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
     // slabs are n_tile*16 bytes (a multiple of 256), so the resident region needs no padding and
     // w_res_bytes is both the region size and the mbarrier transaction count
     POCO_CHECK(!p.w_resident || p.w_res_bytes == w_total, "weight slab total must be 128-byte aligned");
-    const size_t smem = size_t(kHeaderBytes) + p.w_res_bytes + size_t(p.stages) * (p.a_stage_bytes + p.w_stage_bytes);
+    const size_t smem = size_t(kHeaderBytes) + kRingBytes + p.w_res_bytes + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
     dim3 grid(std::max(1, std::min(p.num_m_tiles, num_sms() / n_blocks)), n_blocks);
     const ConvTcParams& pk = p;
     static std::once_flag once[2];
