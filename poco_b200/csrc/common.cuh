@@ -91,10 +91,11 @@ __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.b
 __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
-// 16-byte cp.async (LDGSTS) with zero-fill when !valid
+// 16-byte cp.async (LDGSTS) with zero-fill when !valid; .ca: neighbouring filter taps of a stride-2
+// gather hit the same 32-byte sectors, let L1 absorb the re-reads
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
     const uint32_t sz = valid ? 16u : 0u;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

@@ -40,9 +40,8 @@ constexpr int kSmemBudget = 225 * 1024;   // of 227 KB usable per CTA
 constexpr int kHeaderBytes = 2048;        // barriers + bias
 constexpr int kGatherLag = 2;
 constexpr int kItemBytes = 2 * kTileM * 16;        // epilogue work item = 16 columns = 2 output planes x 128 rows
-constexpr int kOutRing = 3, kResRing = 4;
-constexpr int kHalfRingBytes = (kOutRing + kResRing) * kItemBytes;
-constexpr int kRingBytes = 2 * kHalfRingBytes;     // two epilogue halves
+constexpr int kOutRing = 3, kResRing = 4, kMaxResRing = 16;     // residual prefetch depth grows into spare smem
+constexpr int kRingBytes = 2 * (kOutRing + kResRing) * kItemBytes;   // two epilogue halves, minimum depth
 
 enum { MODE_LINEAR = 0, MODE_GATHER = 1 };
 
@@ -70,6 +69,8 @@ struct ConvTcParams {
     int a_plane_bytes, a_copy_bytes, a_stage_bytes, w_stage_bytes, w_res_bytes;
     int halo;
     int tmem_cols, acc_bufs;
+    int res_ring;         // residual prefetch ring depth per epilogue half
+    int tap_group;        // gather mode: filter taps per stage
     int debug;            // POCO_CONV_DEBUG bits (bring-up only): 1 skip epilogue work, 2 skip MMAs, 4 skip A loads
 };
 
@@ -79,7 +80,7 @@ struct SmemHeader {
     unsigned long long tmem_full[kMaxAccBufs];
     unsigned long long tmem_empty[kMaxAccBufs];
     unsigned long long w_ready;
-    unsigned long long res_full[2 * kResRing];
+    unsigned long long res_full[2 * kMaxResRing];
     uint32_t tmem_base;
     uint32_t pad_[5];
     float bias[256];
@@ -101,7 +102,9 @@ template <int MODE>
 __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
-    uint8_t* w_res = smem + kHeaderBytes + kRingBytes;
+    const int res_ring_n = p.res_ring;
+    const int half_ring_bytes = (kOutRing + res_ring_n) * kItemBytes;
+    uint8_t* w_res = smem + kHeaderBytes + 2 * half_ring_bytes;
     uint8_t* stage0 = w_res + p.w_res_bytes;
     const int stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
 
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     const int taps = p.kh * p.kw;
     const int planes_per_chunk = p.kc >> 3;
     const int cin8 = p.Cin >> 3;
-    const int kiters = MODE == MODE_LINEAR ? p.n_chunks : p.n_chunks * taps;
+    const int kiters = MODE == MODE_LINEAR ? p.n_chunks : p.n_chunks * (taps / p.tap_group);
     const uint32_t slab_bytes = uint32_t(p.n_tile) * 16u;     // one (tap, 8-channel) weight slab
     using R = Roles<MODE>;
 
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             mbar_init(smem_u32(&hdr->tmem_empty[i]), 8);
         }
         mbar_init(smem_u32(&hdr->w_ready), 1);
-        for (int i = 0; i < 2 * kResRing; ++i) mbar_init(smem_u32(&hdr->res_full[i]), 1);
+        for (int i = 0; i < 2 * kMaxResRing; ++i) mbar_init(smem_u32(&hdr->res_full[i]), 1);
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) hdr->bias[i] = p.bias[nb * p.n_tile + i];
@@ -202,9 +205,13 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         }
     } else if (MODE == MODE_GATHER && warp < 4) {
         // ============================================================ A producers (cp.async gather)
+        // One stage = `tap_group` filter taps x 16 input channels (2 planes) x 128 rows: each of the
+        // 128 producer threads owns one tile row and issues 2 x tap_group 16-byte cp.async per stage
+        // (zero-fill outside the image), so up to (kGatherLag+1) x 18 loads are in flight per thread.
         const int r = threadIdx.x;                 // row of the tile
         const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
         const int Wp_i = p.Win + 2, HpWp_i = (p.Hin + 2) * Wp_i;
+        const int TG = p.tap_group, n_groups = taps / TG;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
             const long long q = (long long)tile * kTileM + r;
@@ -212,18 +219,33 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             const int rem = int(q - (long long)n * HpWp_o);
             const int yo = rem / Wp_o - 1, xo = rem % Wp_o - 1;
             const bool interior = q < p.P_out && yo >= 0 && yo < p.Hout && xo >= 0 && xo < p.Wout;
-            for (int t = 0; t < taps; ++t) {
-                const int yi = yo * p.stride + t / p.kw - p.pad;
-                const int xi = xo * p.stride + t % p.kw - p.pad;
-                const bool ok = interior && yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win;
-                const long long pix = ok ? ((long long)n * HpWp_i + (yi + 1) * Wp_i + (xi + 1)) : 0;
+            const long long crop0 = (long long)n * HpWp_i;
+            for (int tg = 0; tg < n_groups; ++tg) {
+                // source pixel of every tap of this group, computed once and reused by all K chunks
+                long long pix[9];
+                uint32_t okmask = 0;
+#pragma unroll
+                for (int tt = 0; tt < 9; ++tt) {
+                    const int t = tg * TG + tt;
+                    const int yi = yo * p.stride + t / p.kw - p.pad;
+                    const int xi = xo * p.stride + t % p.kw - p.pad;
+                    const bool ok = tt < TG && interior && yi >= 0 && yi < p.Hin && xi >= 0 && xi < p.Win;
+                    pix[tt] = ok ? (crop0 + (yi + 1) * Wp_i + (xi + 1)) * 8 : 0;
+                    okmask |= ok ? (1u << tt) : 0u;
+                }
                 for (int c = 0; c < p.n_chunks; ++c, ++it) {
                     const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
                     mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
-                    uint8_t* st = stage0 + size_t(slot) * stage_bytes;
-                    for (int j = 0; j < planes_per_chunk; ++j) {
-                        const __half* src = p.in + ((long long)(c * planes_per_chunk + j) * p.in_plane + pix) * 8;
-                        cp_async16(smem_u32(st) + uint32_t(j) * p.a_plane_bytes + uint32_t(r) * 16u, src, ok);
+                    const uint32_t st = smem_u32(stage0 + size_t(slot) * stage_bytes) + uint32_t(r) * 16u;
+                    const __half* src0 = p.in + (long long)(c * 2) * p.in_plane * 8;
+#pragma unroll
+                    for (int tt = 0; tt < 9; ++tt) {
+                        if (tt < TG) {
+                            const bool ok = (okmask >> tt) & 1u;
+                            const __half* src = src0 + pix[tt];
+                            cp_async16(st + uint32_t(tt) * 4096u, src, ok);
+                            cp_async16(st + uint32_t(tt) * 4096u + 2048u, src + p.in_plane * 8, ok);
+                        }
                     }
                     cp_async_commit();
                     if (it >= uint32_t(kGatherLag)) {
@@ -245,15 +267,17 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             __syncwarp();
         } else {
             uint32_t it = 0;
+            const int TG = p.tap_group, n_groups = taps / TG;
             for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x)
-                for (int t = 0; t < taps; ++t)
+                for (int tg = 0; tg < n_groups; ++tg)
                     for (int c = 0; c < p.n_chunks; ++c, ++it) {
                         const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
                         mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
                         if (elect_one()) {
                             const uint32_t bar = smem_u32(&hdr->full[slot]);
                             mbar_arrive_expect_tx(bar, uint32_t(p.w_stage_bytes));
-                            load_stage_weights(smem_u32(stage0 + size_t(slot) * stage_bytes) + p.a_stage_bytes, bar, t, t + 1, c);
+                            load_stage_weights(smem_u32(stage0 + size_t(slot) * stage_bytes) + p.a_stage_bytes, bar,
+                                               tg * TG, tg * TG + TG, c);
                         }
                         __syncwarp();
                     }
@@ -302,12 +326,13 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                             }
                         }
                     } else {
-                        const int t = ki / p.n_chunks, c = ki % p.n_chunks;
-                        const uint32_t w0 = p.w_resident
-                            ? smem_u32(w_res) + uint32_t(t * cin8 + c * planes_per_chunk) * slab_bytes : w_stage;
-                        uint32_t a_lo = ((a_base & 0x3FFFFu) >> 4) | a_lbo;
-                        uint32_t b_lo = ((w0 & 0x3FFFFu) >> 4) | b_lbo;
-                        for (int k = 0; k < ksteps; ++k, a_lo += a_kstep, b_lo += b_kstep) {
+                        const int tg = ki / p.n_chunks, c = ki % p.n_chunks, TG = p.tap_group;
+                        for (int tt = 0; tt < TG; ++tt) {          // one K=16 MMA per tap of the group
+                            const uint32_t w0 = p.w_resident
+                                ? smem_u32(w_res) + uint32_t((tg * TG + tt) * cin8 + c * 2) * slab_bytes
+                                : w_stage + uint32_t(tt * 2) * slab_bytes;
+                            const uint32_t a_lo = (((a_base + uint32_t(tt) * 4096u) & 0x3FFFFu) >> 4) | a_lbo;
+                            const uint32_t b_lo = ((w0 & 0x3FFFFu) >> 4) | b_lbo;
                             umma_f16(d_tmem, (uint64_t(desc_hi) << 32) | a_lo, (uint64_t(desc_hi) << 32) | b_lo, idesc, acc);
                             acc = 1;
                         }
@@ -337,16 +362,17 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         const int items = p.n_tile >> 4;                // 16-column items per tile
         const int my_items = (items - half + 1) >> 1;   // items half, half+2, ...
         const bool has_res = p.res != nullptr;
-        uint8_t* out_ring = smem + kHeaderBytes + half * kHalfRingBytes;
+        uint8_t* out_ring = smem + kHeaderBytes + half * half_ring_bytes;
         uint8_t* res_ring = out_ring + kOutRing * kItemBytes;
-        unsigned long long* res_full = hdr->res_full + half * kResRing;
+        unsigned long long* res_full = hdr->res_full + half * kMaxResRing;
+        const uint32_t rr_n = uint32_t(res_ring_n);
         auto prefetch_residual = [&](uint32_t g) {      // elected lane: residual of this half's g-th item
             const int tl_ = int(g / uint32_t(my_items)), item = half + 2 * int(g % uint32_t(my_items));
             const long long tile_ = (long long)blockIdx.x + (long long)tl_ * gridDim.x;
             if (tile_ >= p.num_m_tiles) return;
             const long long q0 = tile_ * kTileM;
             const uint32_t rows = uint32_t(min((long long)kTileM, p.P_out - q0));
-            const uint32_t slot = g % kResRing;
+            const uint32_t slot = g % rr_n;
             const uint32_t bar = smem_u32(&res_full[slot]);
             mbar_arrive_expect_tx(bar, 2u * rows * 16u);
             const __half* src = p.res + ((long long)(plane0 + item * 2) * p.res_plane + q0) * 8;
@@ -356,7 +382,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         };
         if (has_res && lead_warp && my_items > 0) {
             if (elect_one())
-                for (uint32_t g0 = 0; g0 < uint32_t(kResRing); ++g0) prefetch_residual(g0);
+                for (uint32_t g0 = 0; g0 < rr_n; ++g0) prefetch_residual(g0);
             __syncwarp();
         }
         // position of this thread's row inside its crop, advanced incrementally from tile to tile
@@ -392,8 +418,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
                 }
-                const uint32_t rslot = g % kResRing, oslot = g % kOutRing;
-                if (has_res) mbar_wait(smem_u32(&res_full[rslot]), (g / kResRing) & 1u);
+                const uint32_t rslot = g % rr_n, oslot = g % kOutRing;
+                if (has_res) mbar_wait(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
                 uint8_t* ob = out_ring + oslot * kItemBytes + row * 16;
                 const uint8_t* rb = res_ring + rslot * kItemBytes + row * 16;
 #pragma unroll
@@ -442,7 +468,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                         bulk_s2g(dst, src, rows_valid * 16u);
                         bulk_s2g(dst + p.out_plane * 8, src + 2048u, rows_valid * 16u);
                         bulk_store_commit();
-                        if (has_res) prefetch_residual(g + kResRing);       // its ring slot was consumed above
+                        if (has_res) prefetch_residual(g + rr_n);       // its ring slot was consumed above
                     }
                     __syncwarp();
                 }
@@ -547,32 +573,62 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
     }
     // choose K chunk, residency and stage count
     bool found = false;
-    const int kcs[4] = {64, 48, 32, 16};
-    for (int resident = 1; resident >= 0 && !found; --resident) {
-        if (resident && w_total > 112 * 1024) continue;
-        for (int ki = 0; ki < 4 && !found; ++ki) {
-            const int kc = kcs[ki];
-            if (in.C % kc != 0) continue;
-            const int a_stage = (kc / 8) * p.a_plane_bytes;
-            const int w_stage = resident ? 0 : (mode == MODE_LINEAR ? taps : 1) * kc * n_tile * 2;
-            const int avail = budget - (resident ? round_up(w_total, 128) : 0);
-            const int min_stages = mode == MODE_GATHER ? kGatherLag + 1 : 2;
-            int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
-            if (stages < min_stages) continue;
-            p.kc = kc; p.n_chunks = in.C / kc;
-            p.w_resident = resident;
-            p.w_res_bytes = resident ? round_up(w_total, 128) : 0;
-            p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
-            p.rings = (mode == MODE_LINEAR && stages >= 4) ? 2 : 1;
-            p.stages = stages / p.rings;
-            found = true;
+    p.tap_group = 1;
+    if (mode == MODE_LINEAR) {
+        const int kcs[4] = {64, 48, 32, 16};
+        for (int resident = 1; resident >= 0 && !found; --resident) {
+            if (resident && w_total > 112 * 1024) continue;
+            for (int ki = 0; ki < 4 && !found; ++ki) {
+                const int kc = kcs[ki];
+                if (in.C % kc != 0) continue;
+                const int a_stage = (kc / 8) * p.a_plane_bytes;
+                const int w_stage = resident ? 0 : taps * kc * n_tile * 2;
+                const int avail = budget - (resident ? w_total : 0);
+                const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
+                if (stages < 2) continue;
+                p.kc = kc; p.n_chunks = in.C / kc;
+                p.w_resident = resident;
+                p.w_res_bytes = resident ? w_total : 0;
+                p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
+                p.rings = stages >= 4 ? 2 : 1;
+                p.stages = stages / p.rings;
+                found = true;
+            }
+        }
+    } else {
+        // gather: K chunk = 16 channels (2 planes); a stage holds `tap_group` taps (all / one row / one)
+        const int groups[3] = {taps <= 9 ? taps : d->kw, d->kw, 1};
+        for (int resident = 1; resident >= 0 && !found; --resident) {
+            if (resident && w_total > 112 * 1024) continue;
+            for (int gi = 0; gi < 3 && !found; ++gi) {
+                const int tg = groups[gi];
+                if (taps % tg != 0) continue;
+                const int a_stage = tg * 4096;
+                const int w_stage = resident ? 0 : tg * 16 * n_tile * 2;
+                const int avail = budget - (resident ? w_total : 0);
+                const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
+                if (stages < kGatherLag + 1) continue;
+                p.kc = 16; p.n_chunks = in.C / 16;
+                p.tap_group = tg;
+                p.w_resident = resident;
+                p.w_res_bytes = resident ? w_total : 0;
+                p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
+                p.rings = 1;
+                p.stages = stages;
+                found = true;
+            }
         }
     }
     POCO_CHECK(found, "no shared-memory configuration fits this convolution");
-    // slabs are n_tile*16 bytes (a multiple of 256), so the resident region needs no padding and
+    // slabs are n_tile*16 bytes (a multiple of 256): the resident region needs no padding and
     // w_res_bytes is both the region size and the mbarrier transaction count
-    POCO_CHECK(!p.w_resident || p.w_res_bytes == w_total, "weight slab total must be 128-byte aligned");
-    const size_t smem = size_t(kHeaderBytes) + kRingBytes + p.w_res_bytes + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
+    size_t smem = size_t(kHeaderBytes) + kRingBytes + p.w_res_bytes + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
+    p.res_ring = kResRing;
+    if (d->residual != nullptr) {       // spend spare shared memory on a deeper residual prefetch ring
+        const int extra = int((size_t(kSmemBudget) - smem) / (2 * kItemBytes));
+        p.res_ring = std::min(kMaxResRing, kResRing + std::max(0, extra));
+        smem += size_t(p.res_ring - kResRing) * 2 * kItemBytes;
+    }
     dim3 grid(std::max(1, std::min(p.num_m_tiles, num_sms() / n_blocks)), n_blocks);
     const ConvTcParams& pk = p;
     static std::once_flag once[2];

@@ -12,42 +12,52 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------
 // y = act(x W^T + b) + res      x [M,I] (ldx), W [O,I] row-major, y [M,O] (ldy)
-// block tile 32(M) x 64(O), K step 32, 256 threads, 2x4 outputs per thread
 // ------------------------------------------------------------------------------------------------
-constexpr int LBM = 32, LBN = 64, LBK = 32;
+constexpr int LBM = 32, LBN = 32, LBK = 32;
 
+// 32x32 output tile, K step 32, 256 threads (2x2 outputs each); the next K tile is prefetched into
+// registers while the current one is multiplied, so a CTA has two tiles of loads in flight.
 __global__ void __launch_bounds__(256) linear_kernel(poco_linear d) {
     __shared__ float xs[LBK][LBM + 1];
     __shared__ float ws[LBK][LBN + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // tx -> O, ty -> M
     const int m0 = blockIdx.y * LBM, o0 = blockIdx.x * LBN;
-    float acc[2][4] = {};
-    for (int k0 = 0; k0 < d.I; k0 += LBK) {
-        for (int e = threadIdx.x; e < LBM * LBK; e += 256) {
-            const int m = e / LBK, k = e % LBK;
-            xs[k][m] = (m0 + m < d.M && k0 + k < d.I) ? d.x[(long long)(m0 + m) * d.ldx + k0 + k] : 0.f;
+    // each thread stages 4 x elements and 4 w elements per K tile: element e = threadIdx.x + 256*i
+    const int lk = threadIdx.x & 31, lr = threadIdx.x >> 5;     // k within tile, row group (8 groups x 4 rows)
+    float px[4], pw[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = lr + 8 * i, k = k0 + lk;
+            px[i] = (m0 + r < d.M && k < d.I) ? d.x[(long long)(m0 + r) * d.ldx + k] : 0.f;
+            pw[i] = (o0 + r < d.O && k < d.I) ? d.w[(long long)(o0 + r) * d.I + k] : 0.f;
         }
-        for (int e = threadIdx.x; e < LBN * LBK; e += 256) {
-            const int o = e / LBK, k = e % LBK;
-            ws[k][o] = (o0 + o < d.O && k0 + k < d.I) ? d.w[(long long)(o0 + o) * d.I + k0 + k] : 0.f;
+    };
+    float acc[2][2] = {};
+    fetch(0);
+    for (int k0 = 0; k0 < d.I; k0 += LBK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xs[lk][lr + 8 * i] = px[i];
+            ws[lk][lr + 8 * i] = pw[i];
         }
         __syncthreads();
-#pragma unroll 8
+        if (k0 + LBK < d.I) fetch(k0 + LBK);
+#pragma unroll
         for (int k = 0; k < LBK; ++k) {
             const float a0 = xs[k][ty], a1 = xs[k][ty + 16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float b = ws[k][tx + 16 * j];
-                acc[0][j] = fmaf(a0, b, acc[0][j]);
-                acc[1][j] = fmaf(a1, b, acc[1][j]);
-            }
+            const float b0 = ws[k][tx], b1 = ws[k][tx + 16];
+            acc[0][0] = fmaf(a0, b0, acc[0][0]);
+            acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]);
+            acc[1][1] = fmaf(a1, b1, acc[1][1]);
         }
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
             const int m = m0 + ty + 16 * i, o = o0 + tx + 16 * j;
             if (m < d.M && o < d.O) {
                 float v = acc[i][j] + (d.b ? d.b[o] : 0.f);

@@ -253,10 +253,12 @@ class PlanBuilder:
 
     def linear(self, x, xcol, I, wkey, y, ycol, act=0, res=None, rescol=0):
         """y[:, ycol:ycol+O] = act(x[:, xcol:xcol+I] W^T + b) (+ res[:, rescol:rescol+O])"""
-        w = self.dev(self.sd[wkey + '.weight'])
-        b = self.dev(self.sd[wkey + '.bias'])
+        self.linear_w(x, xcol, I, self.sd[wkey + '.weight'], self.sd[wkey + '.bias'], y, ycol, act, res, rescol)
+
+    def linear_w(self, x, xcol, I, w, b, y, ycol, act=0, res=None, rescol=0):
+        w, b = self.dev(w), self.dev(b)
         O = w.shape[0]
-        assert w.shape[1] == I, (wkey, tuple(w.shape), I)
+        assert w.shape[1] == I, (tuple(w.shape), I)
         self.add(L.Linear(x.data_ptr() + 4 * xcol, x.stride(0), w.data_ptr(), b.data_ptr(),
                           (res.data_ptr() + 4 * rescol) if res is not None else None,
                           res.stride(0) if res is not None else 0,

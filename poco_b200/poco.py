@@ -280,13 +280,18 @@ class POCO(nn.Module):
             b.copy2d(ip, 0, xc, cp, 144, bcast=True)
             b.copy2d(ish, 0, xc, cs, 10, bcast=True)
             b.copy2d(ic, 0, xc, cc, 3, bcast=True)
-            h1, h2 = b.f32(B, 1024), b.f32(B, 1024)
+            h2 = b.f32(B, 1024)
+            # fc1 -> Dropout(identity) -> fc2 has no non-linearity (cliff_head.py:103-109): the two layers
+            # are folded once, in float64, into W21 = W2 W1, b21 = W2 b1 + b2.  The three decoders write
+            # adjacent columns (pose | shape | cam), so they run as one [157 x 1024] layer.
+            w1, b1 = sd['head.fc1.weight'].double(), sd['head.fc1.bias'].double()
+            w2, b2 = sd['head.fc2.weight'].double(), sd['head.fc2.bias'].double()
+            w21, b21 = (w2 @ w1).float(), (w2 @ b1 + b2).float()
+            wd = torch.cat([sd['head.decpose.weight'], sd['head.decshape.weight'], sd['head.deccam.weight']], 0)
+            bd = torch.cat([sd['head.decpose.bias'], sd['head.decshape.bias'], sd['head.deccam.bias']], 0)
             for _ in range(3):          # cliff_head.forward n_iter=3 (cliff_head.py:103-113)
-                b.linear(xc, 0, F_ + 160, 'head.fc1', h1, 0)
-                b.linear(h1, 0, 1024, 'head.fc2', h2, 0)
-                b.linear(h2, 0, 1024, 'head.decpose', xc, cp, res=xc, rescol=cp)
-                b.linear(h2, 0, 1024, 'head.decshape', xc, cs, res=xc, rescol=cs)
-                b.linear(h2, 0, 1024, 'head.deccam', xc, cc, res=xc, rescol=cc)
+                b.linear_w(xc, 0, F_ + 160, w21, b21, h2, 0)
+                b.linear_w(h2, 0, 1024, wd, bd, xc, cp, res=xc, rescol=cp)
             rot = b.f32(B, 24, 3, 3)
             b.rot6d(xc, cp, 24, rot)
             out.update(pred_pose=rot, pred_cam=xc[:, cc:cc + 3], pred_shape=xc[:, cs:cs + 10],
