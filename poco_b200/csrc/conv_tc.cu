@@ -37,11 +37,11 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxAccBufs = 8;                     // TMEM accumulator ring (512 columns / n_tile)
 constexpr int kTileM = 128;
 constexpr int kSmemBudget = 225 * 1024;   // of 227 KB usable per CTA
-constexpr int kHeaderBytes = 2048;        // barriers + bias
+constexpr int kHeaderBytes = 4096;        // barriers + bias
 constexpr int kGatherLag = 2;
-constexpr int kItemBytes = 2 * kTileM * 16;        // epilogue work item = 16 columns = 2 output planes x 128 rows
-constexpr int kOutRing = 3, kResRing = 4, kMaxResRing = 16;     // residual prefetch depth grows into spare smem
-constexpr int kRingBytes = 2 * (kOutRing + kResRing) * kItemBytes;   // two epilogue halves, minimum depth
+constexpr int kPlaneTile = kTileM * 16;            // one output plane of one tile: 2 KB, contiguous in HBM
+constexpr int kOutRing = 0, kResRing = 4, kMaxResRing = 16;     // residual prefetch depth grows into spare smem
+constexpr int ring_bytes_for(int item_planes) { return 2 * (kOutRing + kResRing) * item_planes * kPlaneTile; }   // 8 warps x (out + res ring) x item slice
 
 enum { MODE_LINEAR = 0, MODE_GATHER = 1 };
 
@@ -70,8 +70,10 @@ struct ConvTcParams {
     int halo;
     int tmem_cols, acc_bufs;
     int res_ring;         // residual prefetch ring depth per epilogue half
+    int item_planes;      // epilogue work item = item_planes x 8 accumulator columns (2 or 4)
     int tap_group;        // gather mode: filter taps per stage
-    int debug;            // POCO_CONV_DEBUG bits (bring-up only): 1 skip epilogue work, 2 skip MMAs, 4 skip A loads
+    int debug;            // POCO_CONV_DEBUG bits (bring-up only): 1 skip epilogue work, 2 skip MMAs, 4 skip A loads,
+                          // 8 skip output stores, 16 ignore the residual
 };
 
 struct SmemHeader {
@@ -80,7 +82,7 @@ struct SmemHeader {
     unsigned long long tmem_full[kMaxAccBufs];
     unsigned long long tmem_empty[kMaxAccBufs];
     unsigned long long w_ready;
-    unsigned long long res_full[2 * kMaxResRing];
+    unsigned long long res_full[8 * kMaxResRing];      // [epilogue warp][slot]
     uint32_t tmem_base;
     uint32_t pad_[5];
     float bias[256];
@@ -98,13 +100,14 @@ struct Roles {
     static constexpr int kThreads = (kEpiWarp0 + 8) * 32;
 };
 
-template <int MODE>
+template <int MODE, int IPL>
 __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
     const int res_ring_n = p.res_ring;
-    const int half_ring_bytes = (kOutRing + res_ring_n) * kItemBytes;
-    uint8_t* w_res = smem + kHeaderBytes + 2 * half_ring_bytes;
+    constexpr int ipl = IPL;                            // output planes (8 columns each) per epilogue work item
+    const int warp_ring_bytes = (kOutRing + res_ring_n) * ipl * 512;      // per epilogue warp: out ring + residual ring
+    uint8_t* w_res = smem + kHeaderBytes + 8 * warp_ring_bytes;
     uint8_t* stage0 = w_res + p.w_res_bytes;
     const int stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
 
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             mbar_init(smem_u32(&hdr->tmem_empty[i]), 8);
         }
         mbar_init(smem_u32(&hdr->w_ready), 1);
-        for (int i = 0; i < 2 * kMaxResRing; ++i) mbar_init(smem_u32(&hdr->res_full[i]), 1);
+        for (int i = 0; i < 8 * kMaxResRing; ++i) mbar_init(smem_u32(&hdr->res_full[i]), 1);
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) hdr->bias[i] = p.bias[nb * p.n_tile + i];
@@ -139,6 +142,9 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
+    // Programmatic dependent launch: let the next kernel of the stream start its prologue on every SM
+    // this CTA leaves; roles that touch activations call pdl_wait() before their first access.
+    pdl_launch_dependents();
     const uint32_t buf_cols = uint32_t(p.tmem_cols) / uint32_t(p.acc_bufs);
     const uint32_t nacc = uint32_t(p.acc_bufs);
 
@@ -178,8 +184,9 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
 
     if (MODE == MODE_LINEAR && warp == 0) {
         // ============================================================ producer (bulk copies)
-        if (p.w_resident && elect_one()) load_resident_weights();
+        if (p.w_resident && elect_one()) load_resident_weights();      // weights are constants: no dependency
         __syncwarp();
+        pdl_wait();
         uint32_t its[2] = {0u, 0u}, tl = 0;
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
             const long long q0 = (long long)tile * kTileM - p.halo;
@@ -208,6 +215,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         // One stage = `tap_group` filter taps x 16 input channels (2 planes) x 128 rows: each of the
         // 128 producer threads owns one tile row and issues 2 x tap_group 16-byte cp.async per stage
         // (zero-fill outside the image), so up to (kGatherLag+1) x 18 loads are in flight per thread.
+        pdl_wait();
         const int r = threadIdx.x;                 // row of the tile
         const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
         const int Wp_i = p.Win + 2, HpWp_i = (p.Hin + 2) * Wp_i;
@@ -344,43 +352,55 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             }
         }
     } else if (warp >= R::kEpiWarp0) {
-        // ============================================================ epilogue (2 halves x 4 warps)
-        // Work item = 16 accumulator columns (2 output planes) of one tile; the two halves take
-        // alternate items, so 8 warps hide each other's TMEM / shared-memory / ALU latencies.
-        // Per half: residual tiles arrive by bulk copy into a 4-deep shared-memory ring (prefetched
-        // 4 items ahead by an elected lane), results are staged in a 3-deep ring and leave with one
-        // 2 KB bulk store per plane -- in the planar layout a (tile, plane) is one contiguous run.
-        // Halo rows are stored as zeros (keeps the zero-halo invariant); rows past the end of the
-        // plane are clipped.
+        // ============================================================ epilogue (8 autonomous warps)
+        // Work item = IPL output planes (8 accumulator columns each) of one tile; the two halves of
+        // the epilogue take alternate items.  Inside a half each of the 4 warps owns the 32 tile rows
+        // of its TMEM lane group and runs on its own: no CTA-level barrier.  Per warp: the residual
+        // slice (32 rows x 16 B per plane = one contiguous 512-byte run of the planar layout) arrives
+        // by bulk copy into a private ring, prefetched `res_ring` items ahead; results are written
+        // straight from registers, one 16-byte store per lane and plane = 512 contiguous bytes per
+        // warp instruction (a shared-memory staged bulk-store variant measured slower: its
+        // fence.proxy.async + store-queue waits sat on the per-item critical path).  Halo rows are
+        // never written (zero-halo invariant).
+        pdl_wait();
         const int ew = warp - R::kEpiWarp0;
         const int half = ew >> 2;
         const int lg = warp & 3;                        // TMEM lane group this warp may access
         const int row = lg * 32 + lane;
-        const bool lead_warp = (ew & 3) == 0;
         const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
         const int plane0 = (nb * p.n_tile) >> 3;
-        const int items = p.n_tile >> 4;                // 16-column items per tile
+        const int items = (p.n_tile + ipl * 8 - 1) / (ipl * 8);      // work items per tile
         const int my_items = (items - half + 1) >> 1;   // items half, half+2, ...
-        const bool has_res = p.res != nullptr;
-        uint8_t* out_ring = smem + kHeaderBytes + half * half_ring_bytes;
-        uint8_t* res_ring = out_ring + kOutRing * kItemBytes;
-        unsigned long long* res_full = hdr->res_full + half * kMaxResRing;
+        const bool has_res = p.res != nullptr && !(p.debug & 16);
+        const bool skip_store = (p.debug & 8) != 0;
+        constexpr uint32_t kSlot = IPL * 512;           // one item slice of this warp: IPL planes x 32 rows x 16 B
+        uint8_t* res_ring = smem + kHeaderBytes + ew * warp_ring_bytes;
+        unsigned long long* res_full = hdr->res_full + ew * kMaxResRing;
         const uint32_t rr_n = uint32_t(res_ring_n);
-        auto prefetch_residual = [&](uint32_t g) {      // elected lane: residual of this half's g-th item
-            const int tl_ = int(g / uint32_t(my_items)), item = half + 2 * int(g % uint32_t(my_items));
-            const long long tile_ = (long long)blockIdx.x + (long long)tl_ * gridDim.x;
+        long long pf_tile = blockIdx.x;                 // prefetch cursor (elected lane): next (tile, item) to fetch
+        int pf_k = 0;
+        auto prefetch_residual = [&](uint32_t g) {      // elected lane: residual slice of this warp's g-th item
+            const long long tile_ = pf_tile;
+            const int item = half + 2 * pf_k;
+            if (++pf_k == my_items) {
+                pf_k = 0;
+                pf_tile += gridDim.x;
+            }
             if (tile_ >= p.num_m_tiles) return;
-            const long long q0 = tile_ * kTileM;
-            const uint32_t rows = uint32_t(min((long long)kTileM, p.P_out - q0));
+            const long long qw = tile_ * kTileM + lg * 32;
+            const long long left = p.P_out - qw;
+            if (left <= 0) return;
+            const uint32_t rows = uint32_t(left < 32 ? left : 32);
             const uint32_t slot = g % rr_n;
             const uint32_t bar = smem_u32(&res_full[slot]);
-            mbar_arrive_expect_tx(bar, 2u * rows * 16u);
-            const __half* src = p.res + ((long long)(plane0 + item * 2) * p.res_plane + q0) * 8;
-            const uint32_t dst = smem_u32(res_ring) + slot * kItemBytes;
-            bulk_g2s(dst, src, rows * 16u, bar);
-            bulk_g2s(dst + 2048u, src + p.res_plane * 8, rows * 16u, bar);
+            const int planes = min(ipl, (p.n_tile >> 3) - item * ipl);
+            mbar_arrive_expect_tx(bar, uint32_t(planes) * rows * 16u);
+            const __half* src = p.res + ((long long)(plane0 + item * ipl) * p.res_plane + qw) * 8;
+            const uint32_t dst = smem_u32(res_ring) + slot * kSlot;
+            for (int pl = 0; pl < planes; ++pl, src += p.res_plane * 8)
+                bulk_g2s(dst + uint32_t(pl) * 512u, src, rows * 16u, bar);
         };
-        if (has_res && lead_warp && my_items > 0) {
+        if (has_res && my_items > 0) {
             if (elect_one())
                 for (uint32_t g0 = 0; g0 < rr_n; ++g0) prefetch_residual(g0);
             __syncwarp();
@@ -392,38 +412,42 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         uint32_t tl = 0, g = 0;
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
             const uint32_t buf = tl % nacc;
-            const long long q0 = (long long)tile * kTileM;
+            const long long qw = (long long)tile * kTileM + lg * 32;     // first row of this warp's slice
             const uint32_t yy = __umulhi(rem, magic_w), xx = rem - yy * uint32_t(Wp_o);
-            const bool interior = q0 + row < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout);
+            const bool interior = qw + lane < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout);
             rem += step;
             if (rem >= uint32_t(HpWp_o)) rem -= uint32_t(HpWp_o);
-            const uint32_t rows_valid = uint32_t(min((long long)kTileM, p.P_out - q0));
+            const long long left = p.P_out - qw;
+            const uint32_t rows_w = left <= 0 ? 0u : uint32_t(left < 32 ? left : 32);
             mbar_wait(smem_u32(&hdr->tmem_full[buf]), (tl / nacc) & 1u);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + buf * buf_cols + (uint32_t(lg * 32) << 16);
             if (p.debug & 1) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
                 continue;
             }
+            const uint32_t taddr = tmem_base + buf * buf_cols + (uint32_t(lg * 32) << 16);
             for (int k = 0; k < my_items; ++k, ++g) {
                 const int item = half + 2 * k;
-                const int c0 = item * 16;
-                uint32_t v[16];
+                const int c0 = item * ipl * 8;
+                const int planes = min(ipl, (p.n_tile - c0) >> 3);       // 2 or 4
+                uint32_t v[IPL * 8];
                 tmem_ld16(taddr + uint32_t(c0), v);
+                if (IPL == 4 && planes == 4) tmem_ld16(taddr + uint32_t(c0 + 16), v + (IPL == 4 ? 16 : 0));
                 tmem_ld_wait();
                 if (k == my_items - 1) {                // this warp is done with the accumulator buffer
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
                 }
-                const uint32_t rslot = g % rr_n, oslot = g % kOutRing;
-                if (has_res) mbar_wait(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
-                uint8_t* ob = out_ring + oslot * kItemBytes + row * 16;
-                const uint8_t* rb = res_ring + rslot * kItemBytes + row * 16;
+                const uint32_t rslot = g % rr_n;
+                if (has_res && rows_w > 0) mbar_wait(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
+                __half* outp = p.out + ((long long)(plane0 + item * ipl) * p.out_plane + qw + lane) * 8;
+                const uint8_t* rb = res_ring + rslot * kSlot + lane * 16;
 #pragma unroll
-                for (int pl = 0; pl < 2; ++pl) {
+                for (int pl = 0; pl < IPL; ++pl) {
+                    if (IPL == 4 && pl >= planes) break;
                     const float4 b0 = *reinterpret_cast<const float4*>(&hdr->bias[c0 + pl * 8]);
                     const float4 b1 = *reinterpret_cast<const float4*>(&hdr->bias[c0 + pl * 8 + 4]);
                     float f[8] = {__uint_as_float(v[pl * 8 + 0]) + b0.x, __uint_as_float(v[pl * 8 + 1]) + b0.y,
@@ -435,7 +459,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                         for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
                     }
                     if (has_res) {
-                        const uint4 r4 = *reinterpret_cast<const uint4*>(rb + pl * 2048);
+                        const uint4 r4 = *reinterpret_cast<const uint4*>(rb + pl * 512);
                         const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -448,28 +472,16 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
 #pragma unroll
                         for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
                     }
-                    uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
-                    if (interior) {
+                    if (interior && !skip_store) {      // 32 lanes x 16 B = one contiguous 512-byte run of the plane
+                        uint4 o4;
                         o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
                         o4.z = pack_half2(f[4], f[5]); o4.w = pack_half2(f[6], f[7]);
+                        *reinterpret_cast<uint4*>(outp + (long long)pl * p.out_plane * 8) = o4;
                     }
-                    *reinterpret_cast<uint4*>(ob + pl * 2048) = o4;
                 }
-                fence_proxy_async_smem();               // staged results -> visible to the bulk-store engine
-                if (lead_warp) {                        // out slot of item g+1 is free once store g-2 has read its smem
-                    if (elect_one()) bulk_store_wait_read<kOutRing - 2>();
-                    __syncwarp();
-                }
-                named_barrier_sync(1 + half, 128);
-                if (lead_warp) {
-                    if (elect_one()) {
-                        __half* dst = p.out + ((long long)(plane0 + item * 2) * p.out_plane + q0) * 8;
-                        const uint32_t src = smem_u32(out_ring) + oslot * kItemBytes;
-                        bulk_s2g(dst, src, rows_valid * 16u);
-                        bulk_s2g(dst + p.out_plane * 8, src + 2048u, rows_valid * 16u);
-                        bulk_store_commit();
-                        if (has_res) prefetch_residual(g + rr_n);       // its ring slot was consumed above
-                    }
+                if (has_res) {
+                    __syncwarp();                       // every lane is done with the residual slot
+                    if (elect_one()) prefetch_residual(g + rr_n);
                     __syncwarp();
                 }
             }
@@ -478,10 +490,6 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
             }
-        }
-        if (lead_warp) {
-            if (elect_one()) bulk_store_wait_all();
-            __syncwarp();
         }
     }
 
@@ -559,7 +567,7 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
     const bool linear = d->stride == 1 && in.H == out.H && in.W == out.W &&
                         ((d->kh == 3 && d->kw == 3 && d->pad == 1) || (d->kh == 1 && d->kw == 1 && d->pad == 0));
     const int mode = linear ? MODE_LINEAR : MODE_GATHER;
-    const int budget = kSmemBudget - kHeaderBytes - kRingBytes;
+    int budget = 0;         // set per attempt below
     const int w_total = taps * in.C * n_tile * 2;
 
     if (mode == MODE_LINEAR) {
@@ -571,78 +579,98 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
         p.a_copy_bytes = kTileM * 16;
         p.a_plane_bytes = kTileM * 16;
     }
-    // choose K chunk, residency and stage count
+    // choose epilogue item width, K chunk, residency and stage count.  Wide items (32 columns) halve the
+    // per-item synchronisation of the epilogue; they are used when N >= 64 and the rings still leave
+    // room for >= 4 operand stages; only the 1x1 convs (small K, epilogue bound) take them -- for every
+    // other shape the operand stages are the better use of shared memory (measured, profiles/).
     bool found = false;
     p.tap_group = 1;
-    if (mode == MODE_LINEAR) {
-        const int kcs[4] = {64, 48, 32, 16};
-        for (int resident = 1; resident >= 0 && !found; --resident) {
-            if (resident && w_total > 112 * 1024) continue;
-            for (int ki = 0; ki < 4 && !found; ++ki) {
-                const int kc = kcs[ki];
-                if (in.C % kc != 0) continue;
-                const int a_stage = (kc / 8) * p.a_plane_bytes;
-                const int w_stage = resident ? 0 : taps * kc * n_tile * 2;
-                const int avail = budget - (resident ? w_total : 0);
-                const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
-                if (stages < 2) continue;
-                p.kc = kc; p.n_chunks = in.C / kc;
-                p.w_resident = resident;
-                p.w_res_bytes = resident ? w_total : 0;
-                p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
-                p.rings = stages >= 4 ? 2 : 1;
-                p.stages = stages / p.rings;
-                found = true;
+    for (int want4 = (n_tile >= 64 && mode == MODE_LINEAR && taps == 1 ? 1 : 0); want4 >= 0 && !found; --want4) {
+        p.item_planes = want4 ? 4 : 2;
+        budget = kSmemBudget - kHeaderBytes - ring_bytes_for(p.item_planes);
+        if (mode == MODE_LINEAR) {
+            const int kcs[4] = {64, 48, 32, 16};
+            for (int resident = 1; resident >= 0 && !found; --resident) {
+                if (resident && w_total > 112 * 1024) continue;
+                for (int ki = 0; ki < 4 && !found; ++ki) {
+                    const int kc = kcs[ki];
+                    if (in.C % kc != 0) continue;
+                    const int a_stage = (kc / 8) * p.a_plane_bytes;
+                    const int w_stage = resident ? 0 : taps * kc * n_tile * 2;
+                    const int avail = budget - (resident ? w_total : 0);
+                    const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
+                    if (stages < (want4 ? 4 : 2)) continue;
+                    p.kc = kc; p.n_chunks = in.C / kc;
+                    p.w_resident = resident;
+                    p.w_res_bytes = resident ? w_total : 0;
+                    p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
+                    p.rings = stages >= 4 ? 2 : 1;
+                    p.stages = stages / p.rings;
+                    found = true;
+                }
             }
-        }
-    } else {
-        // gather: K chunk = 16 channels (2 planes); a stage holds `tap_group` taps (all / one row / one)
-        const int groups[3] = {taps <= 9 ? taps : d->kw, d->kw, 1};
-        for (int resident = 1; resident >= 0 && !found; --resident) {
-            if (resident && w_total > 112 * 1024) continue;
-            for (int gi = 0; gi < 3 && !found; ++gi) {
-                const int tg = groups[gi];
-                if (taps % tg != 0) continue;
-                const int a_stage = tg * 4096;
-                const int w_stage = resident ? 0 : tg * 16 * n_tile * 2;
-                const int avail = budget - (resident ? w_total : 0);
-                const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
-                if (stages < kGatherLag + 1) continue;
-                p.kc = 16; p.n_chunks = in.C / 16;
-                p.tap_group = tg;
-                p.w_resident = resident;
-                p.w_res_bytes = resident ? w_total : 0;
-                p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
-                p.rings = 1;
-                p.stages = stages;
-                found = true;
+        } else {
+            // gather: K chunk = 16 channels (2 planes); a stage holds `tap_group` taps (all / one row / one)
+            const int groups[3] = {taps <= 9 ? taps : d->kw, d->kw, 1};
+            for (int resident = 1; resident >= 0 && !found; --resident) {
+                if (resident && w_total > 112 * 1024) continue;
+                for (int gi = 0; gi < 3 && !found; ++gi) {
+                    const int tg = groups[gi];
+                    if (taps % tg != 0) continue;
+                    const int a_stage = tg * 4096;
+                    const int w_stage = resident ? 0 : tg * 16 * n_tile * 2;
+                    const int avail = budget - (resident ? w_total : 0);
+                    const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
+                    if (stages < (want4 ? 4 : kGatherLag + 1)) continue;
+                    p.kc = 16; p.n_chunks = in.C / 16;
+                    p.tap_group = tg;
+                    p.w_resident = resident;
+                    p.w_res_bytes = resident ? w_total : 0;
+                    p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
+                    p.rings = 1;
+                    p.stages = stages;
+                    found = true;
+                }
             }
         }
     }
     POCO_CHECK(found, "no shared-memory configuration fits this convolution");
     // slabs are n_tile*16 bytes (a multiple of 256): the resident region needs no padding and
     // w_res_bytes is both the region size and the mbarrier transaction count
-    size_t smem = size_t(kHeaderBytes) + kRingBytes + p.w_res_bytes + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
+    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes) + p.w_res_bytes + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
     p.res_ring = kResRing;
     if (d->residual != nullptr) {       // spend spare shared memory on a deeper residual prefetch ring
-        const int extra = int((size_t(kSmemBudget) - smem) / (2 * kItemBytes));
+        const int item_bytes = p.item_planes * kPlaneTile;
+        const int extra = int((size_t(kSmemBudget) - smem) / (2 * item_bytes));
         p.res_ring = std::min(kMaxResRing, kResRing + std::max(0, extra));
-        smem += size_t(p.res_ring - kResRing) * 2 * kItemBytes;
+        smem += size_t(p.res_ring - kResRing) * 2 * item_bytes;
     }
     dim3 grid(std::max(1, std::min(p.num_m_tiles, num_sms() / n_blocks)), n_blocks);
     const ConvTcParams& pk = p;
-    static std::once_flag once[2];
-    if (mode == MODE_LINEAR) {
-        std::call_once(once[0], [] {
-            cudaFuncSetAttribute(conv_tc_kernel<MODE_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-        });
-        conv_tc_kernel<MODE_LINEAR><<<grid, Roles<MODE_LINEAR>::kThreads, smem, s>>>(pk);
-    } else {
-        std::call_once(once[1], [] {
-            cudaFuncSetAttribute(conv_tc_kernel<MODE_GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-        });
-        conv_tc_kernel<MODE_GATHER><<<grid, Roles<MODE_GATHER>::kThreads, smem, s>>>(pk);
-    }
+    static const bool use_pdl = [] { const char* e = getenv("POCO_B200_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    auto launch = [&](auto kernel, std::once_flag& flag, int threads) -> cudaError_t {
+        std::call_once(flag, [&] { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget); });
+        cfg.blockDim = dim3(threads);
+        return cudaLaunchKernelEx(&cfg, kernel, pk);
+    };
+    static std::once_flag once4[4];
+    if (mode == MODE_LINEAR && p.item_planes == 2)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2>, once4[0], Roles<MODE_LINEAR>::kThreads));
+    else if (mode == MODE_LINEAR)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4>, once4[1], Roles<MODE_LINEAR>::kThreads));
+    else if (p.item_planes == 2)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 2>, once4[2], Roles<MODE_GATHER>::kThreads));
+    else
+        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 4>, once4[3], Roles<MODE_GATHER>::kThreads));
     POCO_LAUNCHED();
     return 0;
 }
