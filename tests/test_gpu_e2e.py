@@ -114,3 +114,15 @@ def test_debug_conv_kernels_agree_with_tcgen05_path():
     sync_or_die(120)
     for k in GATED:
         assert rel_err(b[k].cpu().numpy(), a[k].cpu().numpy()) < E2E_TOL[k], k
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_gpu_shards_plus_one_all_gather_equal_single_gpu():
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.join(root, 'tools', 'dist_check.py')],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
