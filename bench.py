@@ -186,12 +186,15 @@ def per_kernel_pass(eng, torch, reps=2, dump=None):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)]
         evs[0].record()
         for i, op in enumerate(ops):
-            L.run_op(op, s)
+            if op.kind not in (L.OP_FORK, L.OP_JOIN):       # (op-by-op pass is sequential)
+                L.run_op(op, s)
             evs[i + 1].record()
         torch.cuda.synchronize()
         classes = {}
         rows = []
         for i, op in enumerate(ops):
+            if op.kind in (L.OP_FORK, L.OP_JOIN):
+                continue
             ms = evs[i].elapsed_time(evs[i + 1])
             rows.append((i, op_label(op), ms))
             if op.kind == L.OP_CONV:

@@ -45,6 +45,8 @@ typedef struct poco_conv {
     int32_t kh, kw, stride, pad;
     int32_t relu; /* 0 none; 1 ReLU after the residual add; 2 ReLU before the residual add */
     int32_t impl; /* 0 = tcgen05 implicit GEMM (product path); 1 = CUDA-core debug kernel */
+    int32_t max_ctas; /* 0 = one CTA per SM; else cap on the persistent grid (concurrent plan lanes share the SMs) */
+    int32_t pad_;
 } poco_conv;
 
 /* batch['img'] f32 NCHW [N,3,H,W] -> planar-8 fp16 with channels padded to 16 (poco.py:100 input) */
@@ -167,6 +169,13 @@ typedef struct poco_realnvp {
     int32_t direction;
 } poco_realnvp;
 
+/* fork / join of plan lanes.  HRNet's branches (and the per-output fuse chains) are independent, and the
+ * low-resolution ones cannot fill 148 SMs on their own: a plan runs them concurrently on internal
+ * streams (lane k of `poco_op.lane`), each conv capped to its share of the SMs (poco_conv.max_ctas). */
+typedef struct poco_sync {
+    int32_t n_lanes;
+} poco_sync;
+
 typedef enum poco_op_kind {
     POCO_OP_PACK_IMAGE = 1,
     POCO_OP_CONV = 2,
@@ -179,7 +188,9 @@ typedef enum poco_op_kind {
     POCO_OP_COPY2D = 9,
     POCO_OP_ROT6D = 10,
     POCO_OP_PARE_HEAD = 11,
-    POCO_OP_REALNVP = 12
+    POCO_OP_REALNVP = 12,
+    POCO_OP_FORK = 13, /* lanes 1..n-1 start after everything enqueued so far on lane 0 */
+    POCO_OP_JOIN = 14  /* lane 0 continues after lanes 1..n-1 have drained */
 } poco_op_kind;
 
 typedef struct poco_op {
@@ -198,6 +209,7 @@ typedef struct poco_op {
         poco_rot6d rot6d;
         poco_pare_head pare_head;
         poco_realnvp realnvp;
+        poco_sync sync;
     } u;
 } poco_op;
 

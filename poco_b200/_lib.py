@@ -13,7 +13,7 @@ MAX_FUSE_INPUTS = 4
 ACT_GUARD_BYTES = 8192
 
 OP_PACK_IMAGE, OP_CONV, OP_FUSE_SUM, OP_UPSAMPLE2X, OP_MAXPOOL, OP_AVGPOOL, OP_UNPACK, OP_LINEAR, \
-    OP_COPY2D, OP_ROT6D, OP_PARE_HEAD, OP_REALNVP = range(1, 13)
+    OP_COPY2D, OP_ROT6D, OP_PARE_HEAD, OP_REALNVP, OP_FORK, OP_JOIN = range(1, 15)
 
 
 class Act(C.Structure):
@@ -25,7 +25,7 @@ class Conv(C.Structure):
     _fields_ = [('in_', Act), ('out', Act), ('weight', C.c_void_p), ('bias', C.c_void_p),
                 ('residual', C.c_void_p), ('res_plane_stride', C.c_int64),
                 ('kh', C.c_int32), ('kw', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
-                ('relu', C.c_int32), ('impl', C.c_int32)]
+                ('relu', C.c_int32), ('impl', C.c_int32), ('max_ctas', C.c_int32), ('pad_', C.c_int32)]
 
 
 class PackImage(C.Structure):
@@ -85,10 +85,14 @@ class RealNVP(C.Structure):
                 ('direction', C.c_int32)]
 
 
+class Sync(C.Structure):
+    _fields_ = [('n_lanes', C.c_int32)]
+
+
 class _OpU(C.Union):
     _fields_ = [('pack_image', PackImage), ('conv', Conv), ('fuse_sum', FuseSum), ('upsample2x', Upsample2x),
                 ('maxpool', MaxPool), ('avgpool', AvgPool), ('unpack', Unpack), ('linear', Linear),
-                ('copy2d', Copy2d), ('rot6d', Rot6d), ('pare_head', PareHead), ('realnvp', RealNVP)]
+                ('copy2d', Copy2d), ('rot6d', Rot6d), ('pare_head', PareHead), ('realnvp', RealNVP), ('sync', Sync)]
 
 
 class Op(C.Structure):
@@ -98,7 +102,7 @@ class Op(C.Structure):
 _FIELD_OF_KIND = {OP_PACK_IMAGE: 'pack_image', OP_CONV: 'conv', OP_FUSE_SUM: 'fuse_sum',
                   OP_UPSAMPLE2X: 'upsample2x', OP_MAXPOOL: 'maxpool', OP_AVGPOOL: 'avgpool',
                   OP_UNPACK: 'unpack', OP_LINEAR: 'linear', OP_COPY2D: 'copy2d', OP_ROT6D: 'rot6d',
-                  OP_PARE_HEAD: 'pare_head', OP_REALNVP: 'realnvp'}
+                  OP_PARE_HEAD: 'pare_head', OP_REALNVP: 'realnvp', OP_FORK: 'sync', OP_JOIN: 'sync'}
 _KIND_OF_TYPE = {PackImage: OP_PACK_IMAGE, Conv: OP_CONV, FuseSum: OP_FUSE_SUM, Upsample2x: OP_UPSAMPLE2X,
                  MaxPool: OP_MAXPOOL, AvgPool: OP_AVGPOOL, Unpack: OP_UNPACK, Linear: OP_LINEAR,
                  Copy2d: OP_COPY2D, Rot6d: OP_ROT6D, PareHead: OP_PARE_HEAD, RealNVP: OP_REALNVP}
@@ -148,9 +152,9 @@ def check(rc):
         raise PocoError(lib().poco_last_error().decode())
 
 
-def make_op(desc, lane=0):
+def make_op(desc, lane=0, kind=None):
     op = Op()
-    op.kind = _KIND_OF_TYPE[type(desc)]
+    op.kind = kind if kind is not None else _KIND_OF_TYPE[type(desc)]
     op.lane = lane
     setattr(op.u, _FIELD_OF_KIND[op.kind], desc)
     return op

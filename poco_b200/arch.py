@@ -88,6 +88,29 @@ class SpecBackend:
     def free(self, a):
         pass
 
+    N = 1
+
+    def fork(self, costs):
+        pass
+
+    def set_lane(self, k):
+        pass
+
+    def join(self):
+        pass
+
+
+def conv_cost(N, cin, cout, k, Hout, Wout):
+    """relative SM-cycles of one conv launch, used only to split the SMs between concurrent lanes.
+    tiles x MMAs x effective cycles per MMA, calibrated on measured per-tile times at batch 256
+    (profiles/r01_ops_b256_v7*.csv): ~105 clk for N <= 64 (issue floor 77 + epilogue exposure), ~170 at
+    N = 128 and ~260 at N = 256 when the weights are re-streamed from L2 for every tile."""
+    tiles = -(-N * (Hout + 2) * (Wout + 2) // 128)
+    n_tile = min(cout, 256)
+    streamed = k * k * cin * n_tile * 2 > 112 * 1024
+    cyc = 105 if n_tile <= 64 else ((170 if streamed else 110) if n_tile <= 128 else (260 if streamed else 160))
+    return tiles * (k * k * -(-cin // 16)) * -(-cout // n_tile) * cyc + 1500000
+
 
 # ------------------------------------------------------------------------------------------------
 # residual blocks
@@ -125,17 +148,36 @@ def bottleneck(b, x, name, cin, planes, stride=1, downsample=False, free_input=T
 # ------------------------------------------------------------------------------------------------
 def hr_module(b, xs, name, chans):
     """HighResolutionModule: 4 BasicBlocks per branch, then the multi-resolution fuse
-    (hrnet.py:188-266).  Inputs are consumed (freed)."""
+    (hrnet.py:188-266).  Inputs are consumed (freed).  The branches, and afterwards the per-output
+    fuse chains, are independent: they are emitted as concurrent plan lanes, each with a share of the
+    SMs proportional to its work (the 14x14 / 7x7 branches cannot fill 148 SMs on their own)."""
     nb = len(xs)
+    N = b.N
+    b.fork([8 * conv_cost(N, chans[i], chans[i], 3, xs[i].H, xs[i].W) for i in range(nb)])
     for i in range(nb):
+        b.set_lane(i)
         x = xs[i]
         for k in range(4):
             x = basic_block(b, x, f'{name}.branches.{i}.{k}', chans[i], chans[i])
         xs[i] = x
+    b.join()
     if nb == 1:
         return xs
+    dims = [(x.H, x.W) for x in xs]
+
+    def fuse_cost(i):
+        c = 0
+        for j in range(i + 1, nb):
+            c += conv_cost(N, chans[j], chans[i], 1, *dims[j])
+        for j in range(i):
+            for k in range(i - j):
+                co = chans[i] if k == i - j - 1 else chans[j]
+                c += conv_cost(N, chans[j], co, 3, dims[j][0] >> (k + 1), dims[j][1] >> (k + 1)) * 2   # gather mode
+        return c + N * dims[i][0] * dims[i][1] * chans[i] // 4          # + the element-wise sum
+    b.fork([fuse_cost(i) for i in range(nb)])
     outs = []
     for i in range(nb):
+        b.set_lane(i)
         ups = []
         for j in range(i + 1, nb):      # 1x1 conv + BN at low resolution; nearest upsample folded into the sum
             z = b.conv_bn(xs[j], f'{name}.fuse_layers.{i}.{j}.0', f'{name}.fuse_layers.{i}.{j}.1',
@@ -163,6 +205,7 @@ def hr_module(b, xs, name, chans):
         for z, _ in ups:
             b.free(z)
         outs.append(o)
+    b.join()
     for x in xs:
         b.free(x)
     return outs

@@ -1,5 +1,6 @@
 // poco_b200 -- C-ABI entry points that are not tied to one kernel file: error reporting, device
 // check, op dispatch and the plan (static layer schedule) executor.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -15,9 +16,18 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 using namespace poco;
 
+constexpr int kMaxLanes = 8;
+
 struct poco_plan {
     std::vector<poco_op> ops;
     int64_t flops = 0;
+    cudaStream_t side[kMaxLanes] = {};         // lanes 1..7 (lane 0 is the caller's stream)
+    std::vector<cudaEvent_t> events;           // one per fork, one per (join, lane)
+    ~poco_plan() {
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        for (cudaStream_t s : side)
+            if (s) cudaStreamDestroy(s);
+    }
 };
 
 extern "C" int poco_version(void) { return 100; }
@@ -71,22 +81,69 @@ extern "C" int poco_plan_create(const poco_op* ops, int32_t n_ops, poco_plan** o
     for (const poco_op& op : p->ops) {
         if (op.kind == POCO_OP_CONV) p->flops += conv_flops(&op.u.conv);
         if (op.kind == POCO_OP_LINEAR) p->flops += 2ll * op.u.linear.M * op.u.linear.I * op.u.linear.O;
-        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_REALNVP) {
+        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_JOIN || op.lane < 0 || op.lane >= kMaxLanes) {
             delete p;
             set_error("poco_plan_create: unknown op kind " + std::to_string(op.kind));
             return 1;
         }
     }
+    int max_lane = 0, n_events = 0;
+    for (const poco_op& op : p->ops) {
+        max_lane = std::max(max_lane, int(op.lane));
+        if (op.kind == POCO_OP_FORK) { max_lane = std::max(max_lane, op.u.sync.n_lanes - 1); n_events += 1; }
+        if (op.kind == POCO_OP_JOIN) n_events += op.u.sync.n_lanes;
+    }
+    if (max_lane >= kMaxLanes) {
+        delete p;
+        set_error("poco_plan_create: too many lanes");
+        return 1;
+    }
+    for (int k = 1; k <= max_lane; ++k)
+        if (cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking) != cudaSuccess) {
+            // (no device in host-logic tests: lanes then run on the caller's stream)
+            p->side[k] = nullptr;
+            cudaGetLastError();
+        }
+    p->events.resize(n_events, nullptr);
+    for (cudaEvent_t& e : p->events)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+            e = nullptr;
+            cudaGetLastError();
+        }
     *out = p;
     return 0;
 }
 
 extern "C" int poco_plan_run(poco_plan* plan, void* stream) {
     POCO_CHECK(plan != nullptr, "null plan");
+    cudaStream_t main_s = static_cast<cudaStream_t>(stream);
+    size_t ev = 0;
     for (size_t i = 0; i < plan->ops.size(); ++i) {
-        const int rc = poco_run_op(&plan->ops[i], stream);
+        const poco_op& op = plan->ops[i];
+        if (op.kind == POCO_OP_FORK) {
+            cudaEvent_t e = plan->events[ev++];
+            if (e) {
+                POCO_CUDA(cudaEventRecord(e, main_s));
+                for (int k = 1; k < op.u.sync.n_lanes; ++k)
+                    if (plan->side[k]) POCO_CUDA(cudaStreamWaitEvent(plan->side[k], e, 0));
+            }
+            continue;
+        }
+        if (op.kind == POCO_OP_JOIN) {
+            for (int k = 1; k < op.u.sync.n_lanes; ++k) {
+                cudaEvent_t e = plan->events[ev++];
+                if (e && plan->side[k]) {
+                    POCO_CUDA(cudaEventRecord(e, plan->side[k]));
+                    POCO_CUDA(cudaStreamWaitEvent(main_s, e, 0));
+                }
+            }
+            ++ev;       // (a join reserves n_lanes events; slot 0 is unused)
+            continue;
+        }
+        cudaStream_t s = (op.lane > 0 && plan->side[op.lane]) ? plan->side[op.lane] : main_s;
+        const int rc = poco_run_op(&op, s);
         if (rc != 0) {
-            set_error("op " + std::to_string(i) + " (kind " + std::to_string(plan->ops[i].kind) + "): " + g_error);
+            set_error("op " + std::to_string(i) + " (kind " + std::to_string(op.kind) + "): " + g_error);
             return rc;
         }
     }

@@ -645,7 +645,8 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
         p.res_ring = std::min(kMaxResRing, kResRing + std::max(0, extra));
         smem += size_t(p.res_ring - kResRing) * 2 * item_bytes;
     }
-    dim3 grid(std::max(1, std::min(p.num_m_tiles, num_sms() / n_blocks)), n_blocks);
+    const int sm_budget = d->max_ctas > 0 ? std::min(d->max_ctas, num_sms()) : num_sms();
+    dim3 grid(std::max(1, std::min(p.num_m_tiles, sm_budget / n_blocks)), n_blocks);
     const ConvTcParams& pk = p;
     static const bool use_pdl = [] { const char* e = getenv("POCO_B200_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg{};

@@ -5,6 +5,7 @@ Tensor plumbing only (allowed to be torch): device buffers, BatchNorm folding, w
 into the kernel layout, and the list of op descriptors.  No arithmetic of the hot path runs here.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -132,20 +133,26 @@ class PlanBuilder:
         self.device = torch.device(device)
         self.ops = []
         self.keep = []          # torch tensors the descriptors point into
-        self.free_pool = {}     # (H, W) -> [root ActT]
+        self.free_pool = {}     # (lane, H, W) -> [root ActT]; lane 'fork' = free before the current fork
         self.conv_impl = conv_impl
         self.conv_log = []
+        self.lane = 0
+        self.shares = None      # SM budget per lane inside a fork
+        self.num_sms = 148
+        self.use_lanes = os.environ.get('POCO_B200_LANES', '1') != '0'
 
     # -- buffers
     def act(self, C_, H, W):
-        pool = self.free_pool.get((H, W), [])
-        best = None
-        for a in pool:
-            if a.cap_planes >= C_ // 8 and (best is None or a.cap_planes < best.cap_planes):
-                best = a
-        if best is not None:
-            pool.remove(best)
-            return best.retype(C_) if best.C != C_ else best
+        # a lane may reuse what it freed itself, or what was already free when the lanes forked
+        for key in ((self.lane, H, W), ('fork', H, W)):
+            pool = self.free_pool.get(key, [])
+            best = None
+            for a in pool:
+                if a.cap_planes >= C_ // 8 and (best is None or a.cap_planes < best.cap_planes):
+                    best = a
+            if best is not None:
+                pool.remove(best)
+                return best.retype(C_) if best.C != C_ else best
         a = alloc_act(C_, self.N, H, W, self.device)
         self.keep.append(a.buf)
         return a
@@ -156,7 +163,7 @@ class PlanBuilder:
         if root is not a and a.ptr != root.ptr:
             return
         full = ActT(root.buf, root.ptr, root.cap_planes * 8, root.N, root.H, root.W, root.plane_stride, root.cap_planes)
-        lst = self.free_pool.setdefault((root.H, root.W), [])
+        lst = self.free_pool.setdefault((self.lane, root.H, root.W), [])
         if all(x.buf is not full.buf for x in lst):
             lst.append(full)
 
@@ -171,7 +178,43 @@ class PlanBuilder:
         return t
 
     def add(self, desc):
-        self.ops.append(L.make_op(desc))
+        self.ops.append(L.make_op(desc, lane=self.lane))
+
+    # -- lanes: independent op chains that the plan runs concurrently on internal streams
+    def fork(self, costs):
+        """start len(costs) concurrent lanes; `costs` (relative work) decide each lane's share of the SMs"""
+        assert self.shares is None and self.lane == 0
+        if not self.use_lanes:
+            return
+        n = len(costs)
+        tot = float(sum(costs)) or 1.0
+        shares = [max(4, int(round(self.num_sms * c / tot))) for c in costs]
+        while sum(shares) > self.num_sms:
+            shares[shares.index(max(shares))] -= 1
+        self.shares = shares
+        self.ops.append(L.make_op(L.Sync(n), lane=0, kind=L.OP_FORK))
+        for (lane, H, W), lst in list(self.free_pool.items()):     # everything free now is safe for any lane
+            if lane == 0 and lst:
+                self.free_pool.setdefault(('fork', H, W), []).extend(lst)
+                lst.clear()
+
+    def set_lane(self, k):
+        if not self.use_lanes:
+            return
+        assert self.shares is not None and 0 <= k < len(self.shares)
+        self.lane = k
+
+    def join(self):
+        if not self.use_lanes:
+            return
+        n = len(self.shares)
+        self.lane = 0
+        self.ops.append(L.make_op(L.Sync(n), lane=0, kind=L.OP_JOIN))
+        for (lane, H, W), lst in list(self.free_pool.items()):
+            if lane != 0 and lst:
+                self.free_pool.setdefault((0, H, W), []).extend(lst)
+                lst.clear()
+        self.shares = None
 
     # -- ops
     def pack_image(self, img, H, W):
@@ -211,7 +254,8 @@ class PlanBuilder:
         d = L.Conv(x.desc(), out.desc(), wp.data_ptr(), bf.data_ptr(),
                    residual.ptr if residual is not None else None,
                    residual.plane_stride if residual is not None else 0,
-                   k, k, stride, pad, int(relu), self.conv_impl)
+                   k, k, stride, pad, int(relu), self.conv_impl,
+                   self.shares[self.lane] if self.shares is not None else 0)
         self.add(d)
         self.conv_log.append((convs[0], x.C, cout, k, stride, x.H, Ho))
         return out

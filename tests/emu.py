@@ -152,6 +152,10 @@ class Emu:
         f32(d.rotmat, N * 216)[:] = torch.stack((b1, b2, b3), -1).reshape(-1)
 
 
+Emu._op13 = lambda self, d: None      # fork / join of plan lanes: the interpreter is sequential
+Emu._op14 = lambda self, d: None
+
+
 def run_plan_ops(ops, keep):
     emu = Emu(keep)
     with torch.no_grad():

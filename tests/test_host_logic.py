@@ -27,9 +27,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_ctypes_structs_match_header_sizes():
-    # poco_act: ptr + i64 + 4*i32 = 32 bytes; poco_conv: 2*32 + 3 ptr + i64 + 6*i32 = 120
+    # poco_act: ptr + i64 + 4*i32 = 32 bytes; poco_conv: 2*32 + 3 ptr + i64 + 8*i32 = 128
     assert ctypes.sizeof(_lib.Act) == 32
-    assert ctypes.sizeof(_lib.Conv) == 120
+    assert ctypes.sizeof(_lib.Conv) == 128
     assert ctypes.sizeof(_lib.Linear) == 80
     assert _lib.Op.u.offset == 8
 
@@ -123,3 +123,17 @@ def test_buffer_pool_keeps_zero_halo():
     assert c.buf is a.buf and c.C == 16
     d = b.act(16, 4, 4)
     assert d.buf is not a.buf
+    # concurrent lanes: a buffer freed inside lane 1 is not handed to lane 2 before the join
+    b.free(c)
+    b.fork([1, 1, 1])
+    b.set_lane(1)
+    e = b.act(16, 8, 8)
+    assert e.buf is a.buf                   # free before the fork: any lane may take it
+    b.free(e)
+    b.set_lane(2)
+    f = b.act(16, 8, 8)
+    assert f.buf is not a.buf
+    b.join()
+    g = b.act(16, 8, 8)
+    assert g.buf is a.buf                   # after the join everything is reusable again
+    assert sum(b.ops[i].kind in (13, 14) for i in range(len(b.ops))) == 2
