@@ -312,7 +312,17 @@ def run_gpu_arm(args):
     shares = {}
     if rank == 0:
         with torch.no_grad():
-            classes = per_kernel_pass(eng, torch, dump=args.dump_ops)
+            # per-kernel timing wants every launch alone on the full GPU: rebuild the schedule without
+            # concurrent lanes (whose convs are capped to a share of the SMs) for this pass only
+            os.environ['POCO_B200_LANES'] = '0'
+            eng_seq = model._build_engine(B, dev)
+            os.environ.pop('POCO_B200_LANES')
+            eng_seq.img.copy_(batch['img'])
+            if eng_seq.bbox is not None:
+                eng_seq.bbox.copy_(batch['bbox_info'])
+            eng_seq.plan.run()
+            classes = per_kernel_pass(eng_seq, torch, dump=args.dump_ops)
+            del eng_seq
         tot = sum(c['ms'] for c in classes.values())
         dom = max(classes, key=lambda k: classes[k]['ms'])
         d = classes[dom]
