@@ -122,18 +122,19 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     using R = Roles<MODE>;
 
     // ---------------------------------------------------------------- setup
-    if (threadIdx.x == 0) {
+    {   // barrier init spread over the CTA (one thread initialising ~170 mbarriers cost ~2.5 us per launch)
+        const int t = threadIdx.x;
         const uint32_t full_count = MODE == MODE_LINEAR ? 1u : (128u + (p.w_resident ? 0u : 1u));
-        for (int i = 0; i < p.stages * p.rings; ++i) {
-            mbar_init(smem_u32(&hdr->full[i]), full_count);
-            mbar_init(smem_u32(&hdr->empty[i]), 1);
+        if (t < p.stages * p.rings) {
+            mbar_init(smem_u32(&hdr->full[t]), full_count);
+            mbar_init(smem_u32(&hdr->empty[t]), 1);
         }
-        for (int i = 0; i < p.acc_bufs; ++i) {
-            mbar_init(smem_u32(&hdr->tmem_full[i]), 1);
-            mbar_init(smem_u32(&hdr->tmem_empty[i]), 8);
+        if (t >= 32 && t < 32 + p.acc_bufs) {
+            mbar_init(smem_u32(&hdr->tmem_full[t - 32]), 1);
+            mbar_init(smem_u32(&hdr->tmem_empty[t - 32]), (p.n_tile + ipl * 8 - 1) / (ipl * 8) >= 2 ? 8 : 4);   // epilogue warps draining one tile
         }
-        mbar_init(smem_u32(&hdr->w_ready), 1);
-        for (int i = 0; i < 8 * kMaxResRing; ++i) mbar_init(smem_u32(&hdr->res_full[i]), 1);
+        if (t == 63) mbar_init(smem_u32(&hdr->w_ready), 1);
+        if (t >= 64 && t < 64 + 8 * kMaxResRing) mbar_init(smem_u32(&hdr->res_full[t - 64]), 1);
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) hdr->bias[i] = p.bias[nb * p.n_tile + i];
@@ -370,7 +371,10 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
         const int plane0 = (nb * p.n_tile) >> 3;
         const int items = (p.n_tile + ipl * 8 - 1) / (ipl * 8);      // work items per tile
-        const int my_items = (items - half + 1) >> 1;   // items half, half+2, ...
+        // (tile, item) pairs are dealt alternately to the two halves: with one item per tile (N <= 32) the
+        // halves take alternate TILES, so each warp has two tile-times for its waits and index math
+        const int odd = items & 1;
+        auto k_first = [&](uint32_t tl_) { return (half + (odd ? int(tl_ & 1u) : 0)) & 1; };
         const bool has_res = p.res != nullptr && !(p.debug & 16);
         const bool skip_store = (p.debug & 8) != 0;
         constexpr uint32_t kSlot = IPL * 512;           // one item slice of this warp: IPL planes x 32 rows x 16 B
@@ -378,14 +382,17 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         unsigned long long* res_full = hdr->res_full + ew * kMaxResRing;
         const uint32_t rr_n = uint32_t(res_ring_n);
         long long pf_tile = blockIdx.x;                 // prefetch cursor (elected lane): next (tile, item) to fetch
-        int pf_k = 0;
+        uint32_t pf_tl = 0;
+        int pf_k = k_first(0);
         auto prefetch_residual = [&](uint32_t g) {      // elected lane: residual slice of this warp's g-th item
-            const long long tile_ = pf_tile;
-            const int item = half + 2 * pf_k;
-            if (++pf_k == my_items) {
-                pf_k = 0;
+            while (pf_k >= items) {                     // (this half has no item in that tile)
+                ++pf_tl;
                 pf_tile += gridDim.x;
+                pf_k = k_first(pf_tl);
             }
+            const long long tile_ = pf_tile;
+            const int item = pf_k;
+            pf_k += 2;
             if (tile_ >= p.num_m_tiles) return;
             const long long qw = tile_ * kTileM + lg * 32;
             const long long left = p.P_out - qw;
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             for (int pl = 0; pl < planes; ++pl, src += p.res_plane * 8)
                 bulk_g2s(dst + uint32_t(pl) * 512u, src, rows * 16u, bar);
         };
-        if (has_res && my_items > 0) {
+        if (has_res) {
             if (elect_one())
                 for (uint32_t g0 = 0; g0 < rr_n; ++g0) prefetch_residual(g0);
             __syncwarp();
@@ -419,6 +426,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             if (rem >= uint32_t(HpWp_o)) rem -= uint32_t(HpWp_o);
             const long long left = p.P_out - qw;
             const uint32_t rows_w = left <= 0 ? 0u : uint32_t(left < 32 ? left : 32);
+            const int k0 = k_first(tl);
+            if (k0 >= items) continue;                  // the other half drains this tile
             mbar_wait(smem_u32(&hdr->tmem_full[buf]), (tl / nacc) & 1u);
             tc_fence_after();
             if (p.debug & 1) {
@@ -428,15 +437,14 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 continue;
             }
             const uint32_t taddr = tmem_base + buf * buf_cols + (uint32_t(lg * 32) << 16);
-            for (int k = 0; k < my_items; ++k, ++g) {
-                const int item = half + 2 * k;
+            for (int item = k0; item < items; item += 2, ++g) {
                 const int c0 = item * ipl * 8;
                 const int planes = min(ipl, (p.n_tile - c0) >> 3);       // 2 or 4
                 uint32_t v[IPL * 8];
                 tmem_ld16(taddr + uint32_t(c0), v);
                 if (IPL == 4 && planes == 4) tmem_ld16(taddr + uint32_t(c0 + 16), v + (IPL == 4 ? 16 : 0));
                 tmem_ld_wait();
-                if (k == my_items - 1) {                // this warp is done with the accumulator buffer
+                if (item + 2 >= items) {                // this warp is done with the accumulator buffer
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
@@ -484,11 +492,6 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     if (elect_one()) prefetch_residual(g + rr_n);
                     __syncwarp();
                 }
-            }
-            if (my_items == 0) {                        // (n_tile == 16: the second half has no columns)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
             }
         }
     }
@@ -585,7 +588,7 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
     // other shape the operand stages are the better use of shared memory (measured, profiles/).
     bool found = false;
     p.tap_group = 1;
-    for (int want4 = (n_tile >= 64 && mode == MODE_LINEAR && taps == 1 ? 1 : 0); want4 >= 0 && !found; --want4) {
+    for (int want4 = (mode == MODE_LINEAR && ((n_tile >= 64 && taps == 1) || n_tile == 32) ? 1 : 0); want4 >= 0 && !found; --want4) {
         p.item_planes = want4 ? 4 : 2;
         budget = kSmemBudget - kHeaderBytes - ring_bytes_for(p.item_planes);
         if (mode == MODE_LINEAR) {

@@ -126,3 +126,36 @@ def test_two_gpu_shards_plus_one_all_gather_equal_single_gpu():
                         '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.join(root, 'tools', 'dist_check.py')],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_ragged_batch_sizes_and_reload():
+    """B = 1, an odd batch, a second batch size on the same model, and a weight reload (plans are rebuilt)"""
+    meta, gold, sd = load_preset('cliff_w32')
+    m = build_model('cliff_w32', 'cuda')
+    full = synthetic_batch('cliff_w32', 'cuda', B=7)
+    with torch.no_grad():
+        o7 = m.hot_path(full)
+        o1 = m.hot_path({k: v[:1] for k, v in full.items()})
+        o3 = m.hot_path({k: v[2:5].contiguous() for k, v in full.items()})
+    sync_or_die(120)
+    for k in GATED:
+        assert torch.equal(o1[k][0], o7[k][0]) and torch.equal(o3[k], o7[k][2:5]), k
+    # reloading weights invalidates the prepared plans: doubling a bias must change the output
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2['head.deccam.bias'] = sd2['head.deccam.bias'] + 1.0
+    m.load_state_dict(sd2)
+    with torch.no_grad():
+        o7b = m.hot_path(full)
+    sync_or_die(120)
+    assert (o7b['pred_cam'] - o7['pred_cam']).abs().min() > 0.5
+
+
+def test_empty_batch_and_bad_inputs_raise():
+    m = build_model('pare_r50', 'cuda')
+    with pytest.raises(ValueError):
+        m({'img': torch.zeros(2, 3, 128, 128, device='cuda')})
+    with pytest.raises(KeyError):
+        build_model('cliff_w32', 'cuda')({'img': torch.zeros(1, 3, 224, 224, device='cuda')})     # bbox_info missing
+    m.train()
+    with pytest.raises(Exception):
+        m({'img': torch.zeros(1, 3, 224, 224, device='cuda')})
