@@ -100,6 +100,40 @@ struct Roles {
     static constexpr int kThreads = (kEpiWarp0 + 8) * 32;
 };
 
+
+// Issue every MMA of one shared-memory stage as straight-line code.  The issuing thread is the
+// bottleneck for small N: measured (profiles/r01_mma_issue_rate.csv) the tensor pipe accepts an SS-mode
+// M=128 K=16 MMA every max(N/2, 32 + N/4) cycles (operand fetch at 128 B/clk), but a descriptor that is
+// built in vector registers and moved with R2UR costs the thread ~77 cycles per MMA.  Here every
+// descriptor is `base + compile-time multiple of a uniform stride`, so ptxas keeps the chain in uniform
+// registers: ~3 uniform ALU ops per UTCHMMA.
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; }
+
+template <int TAPS, int KS>
+__device__ __forceinline__ void issue_linear(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, int Wp, uint32_t a_kstep,
+                                             uint32_t b_kstep, uint32_t b_tap, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t acc0) {
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+        // tap (r,s): shift of (r-1) rows and (s-1) pixels inside the landed run (16 B per pixel = 1 descriptor unit)
+        const uint32_t at = a_lo + (TAPS == 1 ? 0u : uint32_t((t / 3 - 1) * Wp + (t % 3 - 1)));
+        const uint32_t bt = b_lo + uint32_t(t) * b_tap;
+#pragma unroll
+        for (int k = 0; k < KS; ++k)
+            umma_f16(d_tmem, desc64(desc_hi, at + uint32_t(k) * a_kstep), desc64(desc_hi, bt + uint32_t(k) * b_kstep), idesc,
+                     (t | k) ? 1u : acc0);
+    }
+}
+
+template <int TG>
+__device__ __forceinline__ void issue_gather(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t b_tap,
+                                             uint32_t desc_hi, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+    for (int tt = 0; tt < TG; ++tt)      // one K=16 MMA per tap of the group; A taps are 4 KB (256 units) apart
+        umma_f16(d_tmem, desc64(desc_hi, a_lo + uint32_t(tt) * 256u), desc64(desc_hi, b_lo + uint32_t(tt) * b_tap), idesc,
+                 tt ? 1u : acc0);
+}
+
 template <int MODE, int IPL>
 __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -111,7 +145,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     uint8_t* stage0 = w_res + p.w_res_bytes;
     const int stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // provably warp-uniform for ptxas
     const int lane = threadIdx.x & 31;
     const int nb = blockIdx.y;                      // N block
     const int taps = p.kh * p.kw;
@@ -304,6 +338,11 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         const uint32_t a_kstep = (2u * uint32_t(p.a_plane_bytes)) >> 4, b_kstep = (2u * slab_bytes) >> 4;
         const int ksteps = planes_per_chunk >> 1;
         const int Wp = p.Wout + 2;
+        const uint32_t w_res_u32 = smem_u32(w_res);
+        // descriptor-unit (16 B) pitch between the weight slabs of consecutive taps
+        const uint32_t w_tap_stride = MODE == MODE_LINEAR
+            ? ((p.w_resident ? uint32_t(cin8) : uint32_t(planes_per_chunk)) * slab_bytes) >> 4
+            : ((p.w_resident ? uint32_t(cin8) : 2u) * slab_bytes) >> 4;
         if (p.w_resident) mbar_wait(smem_u32(&hdr->w_ready), 0);
         uint32_t it = 0, tl = 0;
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
@@ -317,33 +356,42 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 mbar_wait(smem_u32(&hdr->full[slot]), ph);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t a_base = smem_u32(stage0 + size_t(slot) * stage_bytes);
+                    const uint32_t a_base = smem_u32(stage0) + slot * uint32_t(stage_bytes);
                     const uint32_t w_stage = a_base + p.a_stage_bytes;
-                    uint32_t acc = ki > 0 ? 1u : 0u;
+                    const uint32_t acc = ki > 0 ? 1u : 0u;
                     if (MODE == MODE_LINEAR) {
-                        const int c = ki;
-                        const uint32_t w0 = p.w_resident ? smem_u32(w_res) + uint32_t(c * planes_per_chunk) * slab_bytes : w_stage;
-                        const uint32_t w_tap_stride = (p.w_resident ? uint32_t(cin8) : uint32_t(planes_per_chunk)) * slab_bytes;
-                        for (int t = 0; t < ((p.debug & 2) ? 0 : taps); ++t) {
-                            // tap (r,s): shift of (r-1) rows and (s-1) pixels inside the landed run
-                            const int shift = taps == 1 ? 0 : ((t / 3 - 1) * Wp + (t % 3 - 1));
-                            uint32_t a_lo = (((a_base + uint32_t(p.halo + shift) * 16u) & 0x3FFFFu) >> 4) | a_lbo;
-                            uint32_t b_lo = (((w0 + uint32_t(t) * w_tap_stride) & 0x3FFFFu) >> 4) | b_lbo;
-                            for (int k = 0; k < ksteps; ++k, a_lo += a_kstep, b_lo += b_kstep) {
-                                umma_f16(d_tmem, (uint64_t(desc_hi) << 32) | a_lo, (uint64_t(desc_hi) << 32) | b_lo, idesc, acc);
-                                acc = 1;
+                        const uint32_t w0 = p.w_resident ? w_res_u32 + uint32_t(ki * planes_per_chunk) * slab_bytes : w_stage;
+                        const uint32_t a_lo = ((a_base + uint32_t(p.halo) * 16u) >> 4) | a_lbo;
+                        const uint32_t b_lo = (w0 >> 4) | b_lbo;
+                        if (!(p.debug & 2)) {
+#define POCO_ISSUE(T, K) issue_linear<T, K>(d_tmem, a_lo, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, acc)
+                            if (taps == 9) {
+                                switch (ksteps) {
+                                    case 1: POCO_ISSUE(9, 1); break;
+                                    case 2: POCO_ISSUE(9, 2); break;
+                                    case 3: POCO_ISSUE(9, 3); break;
+                                    default: POCO_ISSUE(9, 4); break;
+                                }
+                            } else {
+                                switch (ksteps) {
+                                    case 1: POCO_ISSUE(1, 1); break;
+                                    case 2: POCO_ISSUE(1, 2); break;
+                                    case 3: POCO_ISSUE(1, 3); break;
+                                    default: POCO_ISSUE(1, 4); break;
+                                }
                             }
+#undef POCO_ISSUE
                         }
                     } else {
-                        const int tg = ki / p.n_chunks, c = ki % p.n_chunks, TG = p.tap_group;
-                        for (int tt = 0; tt < TG; ++tt) {          // one K=16 MMA per tap of the group
-                            const uint32_t w0 = p.w_resident
-                                ? smem_u32(w_res) + uint32_t((tg * TG + tt) * cin8 + c * 2) * slab_bytes
-                                : w_stage + uint32_t(tt * 2) * slab_bytes;
-                            const uint32_t a_lo = (((a_base + uint32_t(tt) * 4096u) & 0x3FFFFu) >> 4) | a_lbo;
-                            const uint32_t b_lo = ((w0 & 0x3FFFFu) >> 4) | b_lbo;
-                            umma_f16(d_tmem, (uint64_t(desc_hi) << 32) | a_lo, (uint64_t(desc_hi) << 32) | b_lo, idesc, acc);
-                            acc = 1;
+                        const int tg = ki / p.n_chunks, c = ki - tg * p.n_chunks, TG = p.tap_group;
+                        const uint32_t w0 = p.w_resident ? w_res_u32 + uint32_t(tg * TG * cin8 + c * 2) * slab_bytes : w_stage;
+                        const uint32_t a_lo = (a_base >> 4) | a_lbo;
+                        const uint32_t b_lo = (w0 >> 4) | b_lbo;
+                        switch (TG) {
+                            case 9: issue_gather<9>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
+                            case 7: issue_gather<7>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
+                            case 3: issue_gather<3>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
+                            default: issue_gather<1>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
                         }
                     }
                     umma_commit(smem_u32(&hdr->empty[slot]));      // smem slot free once these MMAs retire
