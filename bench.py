@@ -167,6 +167,9 @@ def op_label(op):
     if op.kind == L.OP_CONV:
         c = op.u.conv
         return f'conv {c.in_.C}->{c.out.C} k{c.kh} s{c.stride} {c.in_.H}->{c.out.H}' + (' +res' if c.residual else '')
+    if op.kind == L.OP_CONV_CHAIN:
+        c = op.u.conv_chain.seg[0]
+        return f'chain x{op.u.conv_chain.n_seg} conv {c.in_.C}->{c.out.C} k{c.kh} {c.in_.H}'
     if op.kind == L.OP_LINEAR:
         return f'linear {op.u.linear.M}x{op.u.linear.I}->{op.u.linear.O}'
     if op.kind == L.OP_FUSE_SUM:
@@ -198,12 +201,15 @@ def per_kernel_pass(eng, torch, reps=2, dump=None):
             ms = evs[i].elapsed_time(evs[i + 1])
             rows.append((i, op_label(op), ms))
             by = 0.0
-            if op.kind == L.OP_CONV:
-                c = op.u.conv
-                by = 2.0 * c.out.N * (c.in_.H * c.in_.W * c.in_.C + c.out.H * c.out.W * c.out.C * (2 if c.residual else 1))
+            if op.kind in (L.OP_CONV, L.OP_CONV_CHAIN):
+                segs = [op.u.conv] if op.kind == L.OP_CONV else [op.u.conv_chain.seg[k] for k in range(op.u.conv_chain.n_seg)]
+                c = segs[0]
                 lin = c.stride == 1 and c.in_.H == c.out.H and ((c.kh == 3 and c.pad == 1) or (c.kh == 1 and c.pad == 0))
                 name = 'conv_tc_linear' if lin else 'conv_tc_gather'
-                fl = 2.0 * c.out.N * c.out.H * c.out.W * c.out.C * c.in_.C * c.kh * c.kw
+                fl = 0.0
+                for c in segs:      # a chain launch does the work of all its segments
+                    by += 2.0 * c.out.N * (c.in_.H * c.in_.W * c.in_.C + c.out.H * c.out.W * c.out.C * (2 if c.residual else 1))
+                    fl += 2.0 * c.out.N * c.out.H * c.out.W * c.out.C * c.in_.C * c.kh * c.kw
             else:
                 name, fl = L._FIELD_OF_KIND[op.kind], 0.0
             e = classes.setdefault(name, {'ms': 0.0, 'flops': 0.0, 'launches': 0, 'bytes': 0.0})

@@ -49,6 +49,22 @@ typedef struct poco_conv {
     int32_t pad_;
 } poco_conv;
 
+/* A chain of convolutions of ONE geometry (3x3/s1/p1 or 1x1/s1, Cin == Cout) executed by one persistent
+ * launch: segment i reads what segment i-1 wrote (seg[i].in.data == seg[i-1].out.data).  Used for the
+ * four BasicBlocks of an HRNet branch (hrnet.py:42-58 x4 inside HighResolutionModule._make_one_branch,
+ * hrnet.py:140-186): eight convs, one launch.  Tiles of segment i+1 start as soon as the three tiles of
+ * segment i they read are complete (per-tile counters in `flags`), so there is no grid-wide barrier and
+ * no per-conv launch / pipeline fill.  A residual must come from outside the chain or from a segment
+ * at least two before its use.  flags: (n_seg - 1) * ceil(N*(H+2)*(W+2) / 128) int32, owned by the
+ * caller, zeroed by the call itself (cudaMemsetAsync on `stream`) before the kernel. */
+#define POCO_MAX_CHAIN 8
+typedef struct poco_conv_chain {
+    poco_conv seg[POCO_MAX_CHAIN];
+    int32_t n_seg;
+    int32_t pad_;
+    int32_t* flags;
+} poco_conv_chain;
+
 /* batch['img'] f32 NCHW [N,3,H,W] -> planar-8 fp16 with channels padded to 16 (poco.py:100 input) */
 typedef struct poco_pack_image {
     const float* img;
@@ -190,7 +206,8 @@ typedef enum poco_op_kind {
     POCO_OP_PARE_HEAD = 11,
     POCO_OP_REALNVP = 12,
     POCO_OP_FORK = 13, /* lanes 1..n-1 start after everything enqueued so far on lane 0 */
-    POCO_OP_JOIN = 14  /* lane 0 continues after lanes 1..n-1 have drained */
+    POCO_OP_JOIN = 14, /* lane 0 continues after lanes 1..n-1 have drained */
+    POCO_OP_CONV_CHAIN = 15
 } poco_op_kind;
 
 typedef struct poco_op {
@@ -199,6 +216,7 @@ typedef struct poco_op {
     union {
         poco_pack_image pack_image;
         poco_conv conv;
+        poco_conv_chain conv_chain;
         poco_fuse_sum fuse_sum;
         poco_upsample2x upsample2x;
         poco_maxpool maxpool;
@@ -224,6 +242,8 @@ int64_t poco_kernel_launches(void); /* kernels launched by this library since lo
 /* single ops (each equals poco_run_op on the matching poco_op) */
 int poco_run_op(const poco_op* op, void* stream);
 int poco_conv_run(const poco_conv* d, void* stream);
+int poco_conv_chain_run(const poco_conv_chain* d, void* stream);
+int64_t poco_conv_chain_flag_count(const poco_conv_chain* d); /* int32 entries `flags` must hold */
 int poco_pack_image_run(const poco_pack_image* d, void* stream);
 int poco_fuse_sum_run(const poco_fuse_sum* d, void* stream);
 int poco_upsample2x_run(const poco_upsample2x* d, void* stream);

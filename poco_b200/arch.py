@@ -99,6 +99,12 @@ class SpecBackend:
     def join(self):
         pass
 
+    def begin_chain(self):
+        pass
+
+    def end_chain(self):
+        pass
+
 
 def conv_cost(N, cin, cout, k, Hout, Wout):
     """relative SM-cycles of one conv launch, used only to split the SMs between concurrent lanes.
@@ -157,8 +163,10 @@ def hr_module(b, xs, name, chans):
     for i in range(nb):
         b.set_lane(i)
         x = xs[i]
+        b.begin_chain()                 # the branch's eight convs share one geometry: one persistent launch
         for k in range(4):
             x = basic_block(b, x, f'{name}.branches.{i}.{k}', chans[i], chans[i])
+        b.end_chain()
         xs[i] = x
     b.join()
     if nb == 1:

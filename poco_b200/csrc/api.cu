@@ -54,10 +54,37 @@ extern "C" int poco_conv_run(const poco_conv* d, void* stream) {
     return d->impl == 1 ? conv_ref_launch(d, s) : conv_tc_launch(d, s);
 }
 
+extern "C" int64_t poco_conv_chain_flag_count(const poco_conv_chain* d) {
+    if (!d || d->n_seg < 1) return 0;
+    const poco_act& o = d->seg[0].out;
+    const int64_t tiles = (int64_t(o.N) * (o.H + 2) * (o.W + 2) + 127) / 128;
+    return int64_t(d->n_seg - 1) * tiles;
+}
+
+extern "C" int poco_conv_chain_run(const poco_conv_chain* d, void* stream) {
+    POCO_CHECK(d->n_seg >= 1 && d->n_seg <= POCO_MAX_CHAIN, "bad chain length");
+    for (int i = 0; i < d->n_seg; ++i) {
+        const poco_conv& c = d->seg[i];
+        if (check_act(c.in, "in") || check_act(c.out, "out")) return 1;
+        POCO_CHECK(c.weight && c.bias, "null weight / bias");
+        POCO_CHECK(c.impl == 0, "a chain runs on the tcgen05 kernel only");
+        POCO_CHECK(c.max_ctas == d->seg[0].max_ctas, "chain: segments must share one CTA budget");
+        POCO_CHECK(!c.residual || c.res_plane_stride >= int64_t(c.out.N) * (c.out.H + 2) * (c.out.W + 2),
+                   "residual plane stride too small");
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (d->n_seg > 1) {
+        POCO_CHECK(d->flags != nullptr, "chain: null flags");
+        POCO_CUDA(cudaMemsetAsync(d->flags, 0, size_t(poco_conv_chain_flag_count(d)) * sizeof(int32_t), s));
+    }
+    return conv_tc_launch_chain(d->seg, d->n_seg, d->flags, s);
+}
+
 extern "C" int poco_run_op(const poco_op* op, void* stream) {
     switch (op->kind) {
         case POCO_OP_PACK_IMAGE: return poco_pack_image_run(&op->u.pack_image, stream);
         case POCO_OP_CONV: return poco_conv_run(&op->u.conv, stream);
+        case POCO_OP_CONV_CHAIN: return poco_conv_chain_run(&op->u.conv_chain, stream);
         case POCO_OP_FUSE_SUM: return poco_fuse_sum_run(&op->u.fuse_sum, stream);
         case POCO_OP_UPSAMPLE2X: return poco_upsample2x_run(&op->u.upsample2x, stream);
         case POCO_OP_MAXPOOL: return poco_maxpool_run(&op->u.maxpool, stream);
@@ -80,8 +107,10 @@ extern "C" int poco_plan_create(const poco_op* ops, int32_t n_ops, poco_plan** o
     p->ops.assign(ops, ops + n_ops);
     for (const poco_op& op : p->ops) {
         if (op.kind == POCO_OP_CONV) p->flops += conv_flops(&op.u.conv);
+        if (op.kind == POCO_OP_CONV_CHAIN)
+            for (int k = 0; k < op.u.conv_chain.n_seg; ++k) p->flops += conv_flops(&op.u.conv_chain.seg[k]);
         if (op.kind == POCO_OP_LINEAR) p->flops += 2ll * op.u.linear.M * op.u.linear.I * op.u.linear.O;
-        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_JOIN || op.lane < 0 || op.lane >= kMaxLanes) {
+        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_CONV_CHAIN || op.lane < 0 || op.lane >= kMaxLanes) {
             delete p;
             set_error("poco_plan_create: unknown op kind " + std::to_string(op.kind));
             return 1;

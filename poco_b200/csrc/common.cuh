@@ -13,6 +13,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #if !defined(__CUDA_ARCH_FEAT_SM100_ALL) && defined(__CUDA_ARCH__)
 #error "poco_b200 kernels are written for sm_100a only (compile with -gencode arch=compute_100a,code=sm_100a)"
@@ -67,6 +68,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Watchdog for spin waits: a protocol bug must surface as a launch failure with a location, never as
+// a hung GPU.  Cold path only (the clock is read every 1024 failed polls).
+static __device__ __noinline__ void spin_timeout(int tag, unsigned long long t0) {
+    if (global_timer_ns() - t0 > 2000000000ull) {
+        printf("poco_b200: wait timed out (tag %d) block (%d,%d) thread %d\n", tag, blockIdx.x, blockIdx.y, threadIdx.x);
+        __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int tag) {
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0u) {
+            if (t0 == 0) t0 = global_timer_ns();
+            spin_timeout(tag, t0);
+        }
     }
 }
 

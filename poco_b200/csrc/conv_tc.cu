@@ -33,6 +33,8 @@ namespace poco {
 
 namespace {
 
+#define MBAR_WAIT(bar, parity) mbar_wait_tag(bar, parity, __LINE__)
+
 constexpr int kMaxStages = 8;
 constexpr int kMaxAccBufs = 8;                     // TMEM accumulator ring (512 columns / n_tile)
 constexpr int kTileM = 128;
@@ -45,20 +47,32 @@ constexpr int ring_bytes_for(int item_planes) { return 2 * (kOutRing + kResRing)
 
 enum { MODE_LINEAR = 0, MODE_GATHER = 1 };
 
-struct ConvTcParams {
+constexpr int kMaxSegs = POCO_MAX_CHAIN;
+
+// one convolution of a chain: same geometry as every other segment, own tensors
+struct ChainSeg {
     const __half* in;
-    long long in_plane;
-    int Hin, Win;
     __half* out;
-    long long out_plane;
-    int Hout, Wout;
     const __half* res;
-    long long res_plane;
     const __half* w;
     const float* bias;
+    int relu;
+    int pad_;
+};
+
+struct ConvTcParams {
+    ChainSeg seg[kMaxSegs];
+    int n_segs;           // > 1: MODE_LINEAR only; segment s+1 reads what segment s wrote, ordered by per-tile flags
+    int flag_expect;      // epilogue-warp arrivals that complete one tile of one segment
+    int* flags;           // [n_segs - 1][num_m_tiles], zeroed before the launch
+    long long in_plane;
+    int Hin, Win;
+    long long out_plane;
+    int Hout, Wout;
+    long long res_plane;
     int Cin, Cout;
     int kh, kw, stride, pad;
-    int relu;
+    int w_bufs;           // resident-weight buffers (2 = the next segment's weights load while this one computes)
     int kc, n_chunks;
     int n_tile;
     int w_resident;
@@ -81,11 +95,12 @@ struct SmemHeader {
     unsigned long long empty[kMaxStages];
     unsigned long long tmem_full[kMaxAccBufs];
     unsigned long long tmem_empty[kMaxAccBufs];
-    unsigned long long w_ready;
+    unsigned long long w_ready[2];
+    unsigned long long w_free[2];
     unsigned long long res_full[8 * kMaxResRing];      // [epilogue warp][slot]
     uint32_t tmem_base;
-    uint32_t pad_[5];
-    float bias[256];
+    uint32_t pad_[3];
+    float bias[2][256];                                // double buffered across chain segments
 };
 static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
 
@@ -134,6 +149,19 @@ __device__ __forceinline__ void issue_gather(uint32_t d_tmem, uint32_t a_lo, uin
                  tt ? 1u : acc0);
 }
 
+// global-memory helpers of the chain protocol
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// order earlier generic-proxy accesses (here: an acquire of data other threads wrote with st.global)
+// before later async-proxy accesses (bulk copies reading that data)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 template <int MODE, int IPL>
 __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -142,7 +170,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     constexpr int ipl = IPL;                            // output planes (8 columns each) per epilogue work item
     const int warp_ring_bytes = (kOutRing + res_ring_n) * ipl * 512;      // per epilogue warp: out ring + residual ring
     uint8_t* w_res = smem + kHeaderBytes + 8 * warp_ring_bytes;
-    uint8_t* stage0 = w_res + p.w_res_bytes;
+    uint8_t* stage0 = w_res + p.w_res_bytes * p.w_bufs;
     const int stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // provably warp-uniform for ptxas
@@ -153,6 +181,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     const int cin8 = p.Cin >> 3;
     const int kiters = MODE == MODE_LINEAR ? p.n_chunks : p.n_chunks * (taps / p.tap_group);
     const uint32_t slab_bytes = uint32_t(p.n_tile) * 16u;     // one (tap, 8-channel) weight slab
+    const int n_segs = MODE == MODE_LINEAR ? p.n_segs : 1;
+    const int my_tiles = (p.num_m_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // per segment
     using R = Roles<MODE>;
 
     // ---------------------------------------------------------------- setup
@@ -167,11 +197,13 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             mbar_init(smem_u32(&hdr->tmem_full[t - 32]), 1);
             mbar_init(smem_u32(&hdr->tmem_empty[t - 32]), (p.n_tile + ipl * 8 - 1) / (ipl * 8) >= 2 ? 8 : 4);   // epilogue warps draining one tile
         }
-        if (t == 63) mbar_init(smem_u32(&hdr->w_ready), 1);
+        if (t >= 60 && t < 62) {
+            mbar_init(smem_u32(&hdr->w_ready[t - 60]), 1);
+            mbar_init(smem_u32(&hdr->w_free[t - 60]), uint32_t(p.rings));      // every MMA issuer commits once per segment
+        }
         if (t >= 64 && t < 64 + 8 * kMaxResRing) mbar_init(smem_u32(&hdr->res_full[t - 64]), 1);
         mbar_fence_init();
     }
-    for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) hdr->bias[i] = p.bias[nb * p.n_tile + i];
     if (warp == R::kMmaWarp) tmem_alloc(smem_u32(&hdr->tmem_base), uint32_t(p.tmem_cols));
     tc_fence_before();
     __syncthreads();
@@ -183,8 +215,6 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     const uint32_t buf_cols = uint32_t(p.tmem_cols) / uint32_t(p.acc_bufs);
     const uint32_t nacc = uint32_t(p.acc_bufs);
 
-    const __half* wg = p.w + size_t(nb) * p.n_tile * 8;       // this N block's column offset inside a slab row
-
     // ---------------------------------------------------------------- weight loader (shared by both modes)
     // All producer / MMA control flow below is warp-convergent with the single issuing lane chosen by
     // elect.sync: every operand of the bulk copies and of tcgen05.mma is then provably warp-uniform
@@ -193,17 +223,20 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     // When this CTA covers all of Cout (one N block), consecutive 8-channel slabs are contiguous in
     // global and shared memory, so `group` slabs travel as one bulk copy.
     const bool whole_n = p.n_tile == p.Cout;
-    auto load_resident_weights = [&]() {
-        mbar_arrive_expect_tx(smem_u32(&hdr->w_ready), uint32_t(p.w_res_bytes));
+    auto load_resident_weights = [&](int s) {      // weights of segment s -> resident buffer s % w_bufs
+        const int b = p.w_bufs == 2 ? (s & 1) : 0;
+        const __half* wg = p.seg[s].w + size_t(nb) * p.n_tile * 8;
+        const uint32_t dst = smem_u32(w_res) + uint32_t(b) * uint32_t(p.w_res_bytes);
+        const uint32_t bar = smem_u32(&hdr->w_ready[b]);
+        mbar_arrive_expect_tx(bar, uint32_t(p.w_res_bytes));
         const int total = taps * cin8;
         const int group = whole_n ? min(total, 64) : 1;          // <= 64 slabs (<= 256 KB) per copy
-        for (int s = 0; s < total; s += group) {
-            const int g = min(group, total - s);
-            bulk_g2s(smem_u32(w_res) + uint32_t(s) * slab_bytes, wg + size_t(s) * p.Cout * 8, uint32_t(g) * slab_bytes,
-                     smem_u32(&hdr->w_ready));
+        for (int i = 0; i < total; i += group) {
+            const int g = min(group, total - i);
+            bulk_g2s(dst + uint32_t(i) * slab_bytes, wg + size_t(i) * p.Cout * 8, uint32_t(g) * slab_bytes, bar);
         }
     };
-    auto load_stage_weights = [&](uint32_t ws, uint32_t bar, int t0, int t1, int c) {
+    auto load_stage_weights = [&](const __half* wg, uint32_t ws, uint32_t bar, int t0, int t1, int c) {
         // taps [t0, t1) of K chunk c -> ws, slabs ordered [tap][plane]
         for (int t = t0; t < t1; ++t) {
             const uint32_t dst = ws + uint32_t((t - t0) * planes_per_chunk) * slab_bytes;
@@ -216,32 +249,71 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             }
         }
     };
+    // Resident weights of a chain: segment s uses buffer s % w_bufs.  w_ready[b] completes once per
+    // segment that uses buffer b; w_free[b] completes when the MMAs of such a segment have retired.
+    auto wbuf_of = [&](int s) { return p.w_bufs == 2 ? (s & 1) : 0; };
+    auto wuse_of = [&](int s) { return p.w_bufs == 2 ? (s >> 1) : s; };      // how many earlier segments used that buffer
 
     if (MODE == MODE_LINEAR && warp == 0) {
         // ============================================================ producer (bulk copies)
-        if (p.w_resident && elect_one()) load_resident_weights();      // weights are constants: no dependency
+        if (p.w_resident && elect_one()) load_resident_weights(0);      // weights are constants: no dependency
         __syncwarp();
         pdl_wait();
         uint32_t its[2] = {0u, 0u}, tl = 0;
-        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
-            const long long q0 = (long long)tile * kTileM - p.halo;
-            const uint32_t ring = p.rings == 2 ? (tl & 1u) : 0u;
-            for (int c = 0; c < p.n_chunks; ++c) {
-                const uint32_t it = its[ring]++;
-                const uint32_t slot = ring * p.stages + it % p.stages, ph = (it / p.stages) & 1u;
-                mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
-                if (elect_one()) {
-                    const uint32_t bar = smem_u32(&hdr->full[slot]);
-                    const bool skip_a = (p.debug & 4) != 0;
-                    const uint32_t tx = (skip_a ? 0u : uint32_t(planes_per_chunk) * p.a_copy_bytes) +
-                                        (p.w_resident ? 0u : uint32_t(p.w_stage_bytes));
-                    mbar_arrive_expect_tx(bar, tx);
-                    const uint32_t st = smem_u32(stage0 + size_t(slot) * stage_bytes);
-                    const __half* src = p.in + ((long long)(c * planes_per_chunk) * p.in_plane + q0) * 8;
-                    for (int j = 0; j < planes_per_chunk && !skip_a; ++j, src += p.in_plane * 8)
-                        bulk_g2s(st + uint32_t(j) * p.a_plane_bytes, src, uint32_t(p.a_copy_bytes), bar);
-                    if (!p.w_resident) load_stage_weights(st + p.a_stage_bytes, bar, 0, taps, c);
+        // double-buffered weights: fetch the next segment's a few tiles into this one (its buffer was
+        // last read two segments ago); single buffer: after this segment's last MMA has retired
+        const int w_prefetch_at = min(my_tiles - 1, 2 * p.stages * p.rings);
+        for (int s = 0; s < n_segs; ++s) {
+            const ChainSeg& sg = p.seg[s];
+            const __half* wg = sg.w + size_t(nb) * p.n_tile * 8;
+            const int* flags_prev = s > 0 ? p.flags + size_t(s - 1) * p.num_m_tiles : nullptr;
+            int j = 0;
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl, ++j) {
+                if (flags_prev != nullptr) {
+                    // this tile's input run spans output tiles tile-1 .. tile+1 of the previous segment
+                    const int tt = tile - 1 + lane;
+                    const bool need = lane < 3 && tt >= 0 && tt < p.num_m_tiles;
+                    uint32_t spins = 0;
+                    unsigned long long t0 = 0;
+                    for (;;) {
+                        const int v = need ? ld_acquire_gpu(flags_prev + tt) : p.flag_expect;
+                        if (__all_sync(0xffffffffu, v >= p.flag_expect)) break;
+                        if ((++spins & 255u) == 0u) {
+                            if (t0 == 0) t0 = global_timer_ns();
+                            spin_timeout(-(s * 100000 + tile), t0);
+                        }
+                    }
+                    fence_proxy_async_all();
                 }
+                const long long q0 = (long long)tile * kTileM - p.halo;
+                const uint32_t ring = p.rings == 2 ? (tl & 1u) : 0u;
+                for (int c = 0; c < p.n_chunks; ++c) {
+                    const uint32_t it = its[ring]++;
+                    const uint32_t slot = ring * p.stages + it % p.stages, ph = (it / p.stages) & 1u;
+                    MBAR_WAIT(smem_u32(&hdr->empty[slot]), ph ^ 1u);
+                    if (elect_one()) {
+                        const uint32_t bar = smem_u32(&hdr->full[slot]);
+                        const bool skip_a = (p.debug & 4) != 0;
+                        const uint32_t tx = (skip_a ? 0u : uint32_t(planes_per_chunk) * p.a_copy_bytes) +
+                                            (p.w_resident ? 0u : uint32_t(p.w_stage_bytes));
+                        mbar_arrive_expect_tx(bar, tx);
+                        const uint32_t st = smem_u32(stage0 + size_t(slot) * stage_bytes);
+                        const __half* src = sg.in + ((long long)(c * planes_per_chunk) * p.in_plane + q0) * 8;
+                        for (int jj = 0; jj < planes_per_chunk && !skip_a; ++jj, src += p.in_plane * 8)
+                            bulk_g2s(st + uint32_t(jj) * p.a_plane_bytes, src, uint32_t(p.a_copy_bytes), bar);
+                        if (!p.w_resident) load_stage_weights(wg, st + p.a_stage_bytes, bar, 0, taps, c);
+                    }
+                    __syncwarp();
+                }
+                if (p.w_resident && p.w_bufs == 2 && s + 1 < n_segs && j == w_prefetch_at) {
+                    if (s >= 1) MBAR_WAIT(smem_u32(&hdr->w_free[wbuf_of(s + 1)]), uint32_t(wuse_of(s + 1) - 1) & 1u);
+                    if (elect_one()) load_resident_weights(s + 1);
+                    __syncwarp();
+                }
+            }
+            if (p.w_resident && p.w_bufs == 1 && s + 1 < n_segs) {
+                MBAR_WAIT(smem_u32(&hdr->w_free[0]), uint32_t(s) & 1u);
+                if (elect_one()) load_resident_weights(s + 1);
                 __syncwarp();
             }
         }
@@ -251,6 +323,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         // 128 producer threads owns one tile row and issues 2 x tap_group 16-byte cp.async per stage
         // (zero-fill outside the image), so up to (kGatherLag+1) x 18 loads are in flight per thread.
         pdl_wait();
+        const __half* in0 = p.seg[0].in;
         const int r = threadIdx.x;                 // row of the tile
         const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
         const int Wp_i = p.Win + 2, HpWp_i = (p.Hin + 2) * Wp_i;
@@ -278,9 +351,9 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 }
                 for (int c = 0; c < p.n_chunks; ++c, ++it) {
                     const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
-                    mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
+                    MBAR_WAIT(smem_u32(&hdr->empty[slot]), ph ^ 1u);
                     const uint32_t st = smem_u32(stage0 + size_t(slot) * stage_bytes) + uint32_t(r) * 16u;
-                    const __half* src0 = p.in + (long long)(c * 2) * p.in_plane * 8;
+                    const __half* src0 = in0 + (long long)(c * 2) * p.in_plane * 8;
 #pragma unroll
                     for (int tt = 0; tt < 9; ++tt) {
                         if (tt < TG) {
@@ -306,20 +379,21 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     } else if (MODE == MODE_GATHER && warp == R::kWWarp) {
         // ============================================================ W producer (bulk copies)
         if (p.w_resident) {
-            if (elect_one()) load_resident_weights();
+            if (elect_one()) load_resident_weights(0);
             __syncwarp();
         } else {
+            const __half* wg = p.seg[0].w + size_t(nb) * p.n_tile * 8;
             uint32_t it = 0;
             const int TG = p.tap_group, n_groups = taps / TG;
             for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x)
                 for (int tg = 0; tg < n_groups; ++tg)
                     for (int c = 0; c < p.n_chunks; ++c, ++it) {
                         const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
-                        mbar_wait(smem_u32(&hdr->empty[slot]), ph ^ 1u);
+                        MBAR_WAIT(smem_u32(&hdr->empty[slot]), ph ^ 1u);
                         if (elect_one()) {
                             const uint32_t bar = smem_u32(&hdr->full[slot]);
                             mbar_arrive_expect_tx(bar, uint32_t(p.w_stage_bytes));
-                            load_stage_weights(smem_u32(stage0 + size_t(slot) * stage_bytes) + p.a_stage_bytes, bar,
+                            load_stage_weights(wg, smem_u32(stage0 + size_t(slot) * stage_bytes) + p.a_stage_bytes, bar,
                                                tg * TG, tg * TG + TG, c);
                         }
                         __syncwarp();
@@ -327,9 +401,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         }
     } else if (warp == R::kMmaWarp || warp == R::kMmaWarp + 1) {
         // ============================================================ MMA issuers (warp-convergent, one elected lane issues)
-        // tcgen05.mma blocks its issuing thread for about the instruction's execution time (shallow
-        // queue) and the per-tile barrier traffic costs ~1k cycles; two warps taking alternate tiles
-        // keep the tensor pipe fed while the other one synchronises (profiles/r01_conv_role_bench.csv).
+        // Two warps take alternate tiles, one stage ring each, so one warp's barrier round trips overlap
+        // the other's MMAs (profiles/r01_conv_role_bench.csv).
         const uint32_t mw = uint32_t(warp - R::kMmaWarp);
         const uint32_t idesc = umma_idesc_f16(kTileM, uint32_t(p.n_tile));
         // descriptor = hi:lo, lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version<<14: only lo changes
@@ -338,65 +411,72 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         const uint32_t a_kstep = (2u * uint32_t(p.a_plane_bytes)) >> 4, b_kstep = (2u * slab_bytes) >> 4;
         const int ksteps = planes_per_chunk >> 1;
         const int Wp = p.Wout + 2;
-        const uint32_t w_res_u32 = smem_u32(w_res);
         // descriptor-unit (16 B) pitch between the weight slabs of consecutive taps
         const uint32_t w_tap_stride = MODE == MODE_LINEAR
             ? ((p.w_resident ? uint32_t(cin8) : uint32_t(planes_per_chunk)) * slab_bytes) >> 4
             : ((p.w_resident ? uint32_t(cin8) : 2u) * slab_bytes) >> 4;
-        if (p.w_resident) mbar_wait(smem_u32(&hdr->w_ready), 0);
+        const bool active = p.rings == 2 || mw == 0u;       // a single ring is served by warp 0
         uint32_t it = 0, tl = 0;
-        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
-            if (p.rings == 2 ? (tl & 1u) != mw : mw != 0u) continue;   // one ring per issuer; a single ring is served by warp 0
-            const uint32_t buf = tl % nacc;
-            mbar_wait(smem_u32(&hdr->tmem_empty[buf]), ((tl / nacc) & 1u) ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * buf_cols;
-            for (int ki = 0; ki < kiters; ++ki, ++it) {
-                const uint32_t slot = (p.rings == 2 ? mw * p.stages : 0u) + it % p.stages, ph = (it / p.stages) & 1u;
-                mbar_wait(smem_u32(&hdr->full[slot]), ph);
+        for (int s = 0; s < n_segs; ++s) {
+            const uint32_t w_res_u32 = smem_u32(w_res) + uint32_t(wbuf_of(s)) * uint32_t(p.w_res_bytes);
+            if (p.w_resident && active) MBAR_WAIT(smem_u32(&hdr->w_ready[wbuf_of(s)]), uint32_t(wuse_of(s)) & 1u);
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
+                if (p.rings == 2 ? (tl & 1u) != mw : mw != 0u) continue;   // one ring per issuer
+                const uint32_t buf = tl % nacc;
+                MBAR_WAIT(smem_u32(&hdr->tmem_empty[buf]), ((tl / nacc) & 1u) ^ 1u);
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a_base = smem_u32(stage0) + slot * uint32_t(stage_bytes);
-                    const uint32_t w_stage = a_base + p.a_stage_bytes;
-                    const uint32_t acc = ki > 0 ? 1u : 0u;
-                    if (MODE == MODE_LINEAR) {
-                        const uint32_t w0 = p.w_resident ? w_res_u32 + uint32_t(ki * planes_per_chunk) * slab_bytes : w_stage;
-                        const uint32_t a_lo = ((a_base + uint32_t(p.halo) * 16u) >> 4) | a_lbo;
-                        const uint32_t b_lo = (w0 >> 4) | b_lbo;
-                        if (!(p.debug & 2)) {
+                const uint32_t d_tmem = tmem_base + buf * buf_cols;
+                for (int ki = 0; ki < kiters; ++ki, ++it) {
+                    const uint32_t slot = (p.rings == 2 ? mw * p.stages : 0u) + it % p.stages, ph = (it / p.stages) & 1u;
+                    MBAR_WAIT(smem_u32(&hdr->full[slot]), ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_base = smem_u32(stage0) + slot * uint32_t(stage_bytes);
+                        const uint32_t w_stage = a_base + p.a_stage_bytes;
+                        const uint32_t acc = ki > 0 ? 1u : 0u;
+                        if (MODE == MODE_LINEAR) {
+                            const uint32_t w0 = p.w_resident ? w_res_u32 + uint32_t(ki * planes_per_chunk) * slab_bytes : w_stage;
+                            const uint32_t a_lo = ((a_base + uint32_t(p.halo) * 16u) >> 4) | a_lbo;
+                            const uint32_t b_lo = (w0 >> 4) | b_lbo;
+                            if (!(p.debug & 2)) {
 #define POCO_ISSUE(T, K) issue_linear<T, K>(d_tmem, a_lo, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, acc)
-                            if (taps == 9) {
-                                switch (ksteps) {
-                                    case 1: POCO_ISSUE(9, 1); break;
-                                    case 2: POCO_ISSUE(9, 2); break;
-                                    case 3: POCO_ISSUE(9, 3); break;
-                                    default: POCO_ISSUE(9, 4); break;
+                                if (taps == 9) {
+                                    switch (ksteps) {
+                                        case 1: POCO_ISSUE(9, 1); break;
+                                        case 2: POCO_ISSUE(9, 2); break;
+                                        case 3: POCO_ISSUE(9, 3); break;
+                                        default: POCO_ISSUE(9, 4); break;
+                                    }
+                                } else {
+                                    switch (ksteps) {
+                                        case 1: POCO_ISSUE(1, 1); break;
+                                        case 2: POCO_ISSUE(1, 2); break;
+                                        case 3: POCO_ISSUE(1, 3); break;
+                                        default: POCO_ISSUE(1, 4); break;
+                                    }
                                 }
-                            } else {
-                                switch (ksteps) {
-                                    case 1: POCO_ISSUE(1, 1); break;
-                                    case 2: POCO_ISSUE(1, 2); break;
-                                    case 3: POCO_ISSUE(1, 3); break;
-                                    default: POCO_ISSUE(1, 4); break;
-                                }
-                            }
 #undef POCO_ISSUE
+                            }
+                        } else {
+                            const int tg = ki / p.n_chunks, c = ki - tg * p.n_chunks, TG = p.tap_group;
+                            const uint32_t w0 = p.w_resident ? w_res_u32 + uint32_t(tg * TG * cin8 + c * 2) * slab_bytes : w_stage;
+                            const uint32_t a_lo = (a_base >> 4) | a_lbo;
+                            const uint32_t b_lo = (w0 >> 4) | b_lbo;
+                            switch (TG) {
+                                case 9: issue_gather<9>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
+                                case 7: issue_gather<7>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
+                                case 3: issue_gather<3>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
+                                default: issue_gather<1>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
+                            }
                         }
-                    } else {
-                        const int tg = ki / p.n_chunks, c = ki - tg * p.n_chunks, TG = p.tap_group;
-                        const uint32_t w0 = p.w_resident ? w_res_u32 + uint32_t(tg * TG * cin8 + c * 2) * slab_bytes : w_stage;
-                        const uint32_t a_lo = (a_base >> 4) | a_lbo;
-                        const uint32_t b_lo = (w0 >> 4) | b_lbo;
-                        switch (TG) {
-                            case 9: issue_gather<9>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
-                            case 7: issue_gather<7>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
-                            case 3: issue_gather<3>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
-                            default: issue_gather<1>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
-                        }
+                        umma_commit(smem_u32(&hdr->empty[slot]));      // smem slot free once these MMAs retire
+                        if (ki == kiters - 1) umma_commit(smem_u32(&hdr->tmem_full[buf]));   // accumulator complete
                     }
-                    umma_commit(smem_u32(&hdr->empty[slot]));      // smem slot free once these MMAs retire
-                    if (ki == kiters - 1) umma_commit(smem_u32(&hdr->tmem_full[buf]));   // accumulator complete
+                    __syncwarp();
                 }
+            }
+            if (p.w_resident && active && n_segs > 1) {     // this warp's MMAs of the segment no longer read the weight buffer
+                if (elect_one()) umma_commit(smem_u32(&hdr->w_free[wbuf_of(s)]));
                 __syncwarp();
             }
         }
@@ -423,122 +503,159 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         // halves take alternate TILES, so each warp has two tile-times for its waits and index math
         const int odd = items & 1;
         auto k_first = [&](uint32_t tl_) { return (half + (odd ? int(tl_ & 1u) : 0)) & 1; };
-        const bool has_res = p.res != nullptr && !(p.debug & 16);
         const bool skip_store = (p.debug & 8) != 0;
         constexpr uint32_t kSlot = IPL * 512;           // one item slice of this warp: IPL planes x 32 rows x 16 B
         uint8_t* res_ring = smem + kHeaderBytes + ew * warp_ring_bytes;
         unsigned long long* res_full = hdr->res_full + ew * kMaxResRing;
         const uint32_t rr_n = uint32_t(res_ring_n);
-        long long pf_tile = blockIdx.x;                 // prefetch cursor (elected lane): next (tile, item) to fetch
-        uint32_t pf_tl = 0;
-        int pf_k = k_first(0);
-        auto prefetch_residual = [&](uint32_t g) {      // elected lane: residual slice of this warp's g-th item
-            while (pf_k >= items) {                     // (this half has no item in that tile)
-                ++pf_tl;
-                pf_tile += gridDim.x;
-                pf_k = k_first(pf_tl);
+        // Residual prefetch cursor (used by the elected lane): the next residual-bearing (segment, tile,
+        // item) of this warp.  A segment's residual may be the output of the segment two before it, so
+        // the cursor never runs past segment `cur + 1` (everything up to `cur - 1` is complete on this
+        // CTA: all epilogue warps meet at a barrier between segments).
+        int pf_s = 0, pf_j = 0, pf_k = k_first(0);
+        uint32_t pf_issued = 0;
+        auto seg_has_res = [&](int s_) { return p.seg[s_].res != nullptr && !(p.debug & 16); };
+        auto prefetch_residual = [&](int cur_seg, uint32_t upto) {      // elected lane: top the ring up to `upto` items
+            while (pf_issued < upto) {
+                while (pf_s < n_segs) {         // advance to the next residual item
+                    if (seg_has_res(pf_s) && pf_j < my_tiles) {
+                        if (pf_k < items) break;
+                        ++pf_j;
+                        pf_k = k_first(uint32_t(pf_s * my_tiles + pf_j));
+                        continue;
+                    }
+                    ++pf_s;
+                    pf_j = 0;
+                    pf_k = k_first(uint32_t(pf_s * my_tiles));
+                }
+                if (pf_s >= n_segs || pf_s > cur_seg + 1) return;
+                const long long tile_ = (long long)blockIdx.x + (long long)pf_j * gridDim.x;
+                const int item = pf_k;
+                pf_k += 2;
+                const uint32_t slot = pf_issued % rr_n;
+                ++pf_issued;
+                const long long qw = tile_ * kTileM + lg * 32;
+                const long long left = p.P_out - qw;
+                const uint32_t bar = smem_u32(&res_full[slot]);
+                if (left <= 0) {                // rows past the end of the tensor: complete the slot's phase anyway
+                    mbar_arrive(bar);
+                    continue;
+                }
+                const uint32_t rows = uint32_t(left < 32 ? left : 32);
+                const int planes = min(ipl, (p.n_tile >> 3) - item * ipl);
+                mbar_arrive_expect_tx(bar, uint32_t(planes) * rows * 16u);
+                const __half* src = p.seg[pf_s].res + ((long long)(plane0 + item * ipl) * p.res_plane + qw) * 8;
+                const uint32_t dst = smem_u32(res_ring) + slot * kSlot;
+                for (int pl = 0; pl < planes; ++pl, src += p.res_plane * 8)
+                    bulk_g2s(dst + uint32_t(pl) * 512u, src, rows * 16u, bar);
             }
-            const long long tile_ = pf_tile;
-            const int item = pf_k;
-            pf_k += 2;
-            if (tile_ >= p.num_m_tiles) return;
-            const long long qw = tile_ * kTileM + lg * 32;
-            const long long left = p.P_out - qw;
-            if (left <= 0) return;
-            const uint32_t rows = uint32_t(left < 32 ? left : 32);
-            const uint32_t slot = g % rr_n;
-            const uint32_t bar = smem_u32(&res_full[slot]);
-            const int planes = min(ipl, (p.n_tile >> 3) - item * ipl);
-            mbar_arrive_expect_tx(bar, uint32_t(planes) * rows * 16u);
-            const __half* src = p.res + ((long long)(plane0 + item * ipl) * p.res_plane + qw) * 8;
-            const uint32_t dst = smem_u32(res_ring) + slot * kSlot;
-            for (int pl = 0; pl < planes; ++pl, src += p.res_plane * 8)
-                bulk_g2s(dst + uint32_t(pl) * 512u, src, rows * 16u, bar);
         };
-        if (has_res) {
-            if (elect_one())
-                for (uint32_t g0 = 0; g0 < rr_n; ++g0) prefetch_residual(g0);
-            __syncwarp();
-        }
-        // position of this thread's row inside its crop, advanced incrementally from tile to tile
         const uint32_t step = uint32_t(((long long)gridDim.x * kTileM) % HpWp_o);
-        uint32_t rem = uint32_t(((long long)blockIdx.x * kTileM + row) % HpWp_o);
         const uint32_t magic_w = 0xFFFFFFFFu / uint32_t(Wp_o) + 1u;      // exact floor(n / Wp) for n < 2^16
-        uint32_t tl = 0, g = 0;
-        for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
-            const uint32_t buf = tl % nacc;
-            const long long qw = (long long)tile * kTileM + lg * 32;     // first row of this warp's slice
-            const uint32_t yy = __umulhi(rem, magic_w), xx = rem - yy * uint32_t(Wp_o);
-            const bool interior = qw + lane < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout);
-            rem += step;
-            if (rem >= uint32_t(HpWp_o)) rem -= uint32_t(HpWp_o);
-            const long long left = p.P_out - qw;
-            const uint32_t rows_w = left <= 0 ? 0u : uint32_t(left < 32 ? left : 32);
-            const int k0 = k_first(tl);
-            if (k0 >= items) continue;                  // the other half drains this tile
-            mbar_wait(smem_u32(&hdr->tmem_full[buf]), (tl / nacc) & 1u);
-            tc_fence_after();
-            if (p.debug & 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
-                continue;
+        uint32_t tl = 0, g = 0;                         // g counts residual items consumed
+        for (int s = 0; s < n_segs; ++s) {
+            const ChainSeg& sg = p.seg[s];
+            const bool has_res = seg_has_res(s);
+            const int relu = sg.relu;
+            int* flags_cur = s + 1 < n_segs ? p.flags + size_t(s) * p.num_m_tiles : nullptr;
+            float* bias_s = hdr->bias[s & 1];
+            {   // this segment's bias -> shared memory; between segments every epilogue warp has finished
+                // (and fenced) the stores of the previous one, which also bounds the residual prefetch
+                if (s > 0) __threadfence();
+                const int t = threadIdx.x - R::kEpiWarp0 * 32;
+                for (int i = t; i < p.n_tile; i += 256) bias_s[i] = sg.bias[nb * p.n_tile + i];
+                named_barrier_sync(1, 256);
             }
-            const uint32_t taddr = tmem_base + buf * buf_cols + (uint32_t(lg * 32) << 16);
-            for (int item = k0; item < items; item += 2, ++g) {
-                const int c0 = item * ipl * 8;
-                const int planes = min(ipl, (p.n_tile - c0) >> 3);       // 2 or 4
-                uint32_t v[IPL * 8];
-                tmem_ld16(taddr + uint32_t(c0), v);
-                if (IPL == 4 && planes == 4) tmem_ld16(taddr + uint32_t(c0 + 16), v + (IPL == 4 ? 16 : 0));
-                tmem_ld_wait();
-                if (item + 2 >= items) {                // this warp is done with the accumulator buffer
+            if (elect_one()) {
+                fence_proxy_async_all();
+                prefetch_residual(s, g + rr_n);
+            }
+            __syncwarp();
+            // position of this thread's row inside its crop, advanced incrementally from tile to tile
+            uint32_t rem = uint32_t(((long long)blockIdx.x * kTileM + row) % HpWp_o);
+            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
+                const uint32_t buf = tl % nacc;
+                const long long qw = (long long)tile * kTileM + lg * 32;     // first row of this warp's slice
+                const uint32_t yy = __umulhi(rem, magic_w), xx = rem - yy * uint32_t(Wp_o);
+                const bool interior = qw + lane < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout);
+                rem += step;
+                if (rem >= uint32_t(HpWp_o)) rem -= uint32_t(HpWp_o);
+                const long long left = p.P_out - qw;
+                const uint32_t rows_w = left <= 0 ? 0u : uint32_t(left < 32 ? left : 32);
+                const int k0 = k_first(tl);
+                if (k0 >= items) continue;                  // the other half drains this tile
+                MBAR_WAIT(smem_u32(&hdr->tmem_full[buf]), (tl / nacc) & 1u);
+                tc_fence_after();
+                if (p.debug & 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
-                }
-                const uint32_t rslot = g % rr_n;
-                if (has_res && rows_w > 0) mbar_wait(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
-                __half* outp = p.out + ((long long)(plane0 + item * ipl) * p.out_plane + qw + lane) * 8;
-                const uint8_t* rb = res_ring + rslot * kSlot + lane * 16;
-#pragma unroll
-                for (int pl = 0; pl < IPL; ++pl) {
-                    if (IPL == 4 && pl >= planes) break;
-                    const float4 b0 = *reinterpret_cast<const float4*>(&hdr->bias[c0 + pl * 8]);
-                    const float4 b1 = *reinterpret_cast<const float4*>(&hdr->bias[c0 + pl * 8 + 4]);
-                    float f[8] = {__uint_as_float(v[pl * 8 + 0]) + b0.x, __uint_as_float(v[pl * 8 + 1]) + b0.y,
-                                  __uint_as_float(v[pl * 8 + 2]) + b0.z, __uint_as_float(v[pl * 8 + 3]) + b0.w,
-                                  __uint_as_float(v[pl * 8 + 4]) + b1.x, __uint_as_float(v[pl * 8 + 5]) + b1.y,
-                                  __uint_as_float(v[pl * 8 + 6]) + b1.z, __uint_as_float(v[pl * 8 + 7]) + b1.w};
-                    if (p.relu == 2) {                  // ReLU before the residual add (hrnet_cls.py:473-474)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                    if (lane == 0) {
+                        mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
+                        if (flags_cur != nullptr) red_release_gpu_add(flags_cur + tile, 1);
                     }
-                    if (has_res) {
-                        const uint4 r4 = *reinterpret_cast<const uint4*>(rb + pl * 512);
-                        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+                    continue;
+                }
+                const uint32_t taddr = tmem_base + buf * buf_cols + (uint32_t(lg * 32) << 16);
+                for (int item = k0; item < items; item += 2) {
+                    const int c0 = item * ipl * 8;
+                    const int planes = min(ipl, (p.n_tile - c0) >> 3);       // 2 or 4
+                    uint32_t v[IPL * 8];
+                    tmem_ld16(taddr + uint32_t(c0), v);
+                    if (IPL == 4 && planes == 4) tmem_ld16(taddr + uint32_t(c0 + 16), v + (IPL == 4 ? 16 : 0));
+                    tmem_ld_wait();
+                    if (item + 2 >= items) {                // this warp is done with the accumulator buffer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
+                    }
+                    const uint32_t rslot = g % rr_n;
+                    if (has_res) MBAR_WAIT(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
+                    __half* outp = sg.out + ((long long)(plane0 + item * ipl) * p.out_plane + qw + lane) * 8;
+                    const uint8_t* rb = res_ring + rslot * kSlot + lane * 16;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 t2 = unpack_half2(rr[i]);
-                            f[2 * i] += t2.x;
-                            f[2 * i + 1] += t2.y;
+                    for (int pl = 0; pl < IPL; ++pl) {
+                        if (IPL == 4 && pl >= planes) break;
+                        const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c0 + pl * 8]);
+                        const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c0 + pl * 8 + 4]);
+                        float f[8] = {__uint_as_float(v[pl * 8 + 0]) + b0.x, __uint_as_float(v[pl * 8 + 1]) + b0.y,
+                                      __uint_as_float(v[pl * 8 + 2]) + b0.z, __uint_as_float(v[pl * 8 + 3]) + b0.w,
+                                      __uint_as_float(v[pl * 8 + 4]) + b1.x, __uint_as_float(v[pl * 8 + 5]) + b1.y,
+                                      __uint_as_float(v[pl * 8 + 6]) + b1.z, __uint_as_float(v[pl * 8 + 7]) + b1.w};
+                        if (relu == 2) {                    // ReLU before the residual add (hrnet_cls.py:473-474)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                        }
+                        if (has_res) {
+                            const uint4 r4 = *reinterpret_cast<const uint4*>(rb + pl * 512);
+                            const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 t2 = unpack_half2(rr[i]);
+                                f[2 * i] += t2.x;
+                                f[2 * i + 1] += t2.y;
+                            }
+                        }
+                        if (relu == 1) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                        }
+                        if (interior && !skip_store) {      // 32 lanes x 16 B = one contiguous 512-byte run of the plane
+                            uint4 o4;
+                            o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
+                            o4.z = pack_half2(f[4], f[5]); o4.w = pack_half2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(outp + (long long)pl * p.out_plane * 8) = o4;
                         }
                     }
-                    if (p.relu == 1) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-                    }
-                    if (interior && !skip_store) {      // 32 lanes x 16 B = one contiguous 512-byte run of the plane
-                        uint4 o4;
-                        o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
-                        o4.z = pack_half2(f[4], f[5]); o4.w = pack_half2(f[6], f[7]);
-                        *reinterpret_cast<uint4*>(outp + (long long)pl * p.out_plane * 8) = o4;
+                    if (has_res) {
+                        ++g;
+                        __syncwarp();                       // every lane is done with the residual slot
+                        if (elect_one()) prefetch_residual(s, g + rr_n);
+                        __syncwarp();
                     }
                 }
-                if (has_res) {
-                    __syncwarp();                       // every lane is done with the residual slot
-                    if (elect_one()) prefetch_residual(g + rr_n);
+                if (flags_cur != nullptr) {                 // this warp's share of the tile is in global memory
                     __syncwarp();
+                    if (lane == 0) red_release_gpu_add(flags_cur + tile, 1);
                 }
             }
         }
@@ -572,8 +689,13 @@ int64_t conv_flops(const poco_conv* d) {
     return 2ll * d->out.N * d->out.H * d->out.W * d->out.C * d->in.C * d->kh * d->kw;
 }
 
-int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
+int conv_tc_launch(const poco_conv* d, cudaStream_t s) { return conv_tc_launch_chain(d, 1, nullptr, s); }
+
+// segs[0..n): same geometry (3x3/s1/p1 or 1x1/s1 when n > 1), flags: (n-1) * num_m_tiles zeroed ints
+int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cudaStream_t s) {
+    const poco_conv* d = segs;
     const poco_act &in = d->in, &out = d->out;
+    POCO_CHECK(n_segs >= 1 && n_segs <= kMaxSegs, "bad chain length");
     POCO_CHECK(in.C % 16 == 0 && out.C % 16 == 0, "Cin and Cout must be multiples of 16");
     POCO_CHECK(in.N == out.N, "batch mismatch");
     POCO_CHECK(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
@@ -582,19 +704,43 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
     POCO_CHECK((kTileM + out.W + 3) * 16 <= POCO_ACT_GUARD_BYTES, "tile halo exceeds the activation guard");
 
     ConvTcParams p{};
-    p.in = static_cast<const __half*>(in.data);
+    p.n_segs = n_segs;
+    p.flags = flags;
     p.in_plane = in.plane_stride;
     p.Hin = in.H; p.Win = in.W;
-    p.out = static_cast<__half*>(out.data);
     p.out_plane = out.plane_stride;
     p.Hout = out.H; p.Wout = out.W;
-    p.res = static_cast<const __half*>(d->residual);
-    p.res_plane = d->res_plane_stride;
-    p.w = static_cast<const __half*>(d->weight);
-    p.bias = d->bias;
+    p.res_plane = 0;
+    bool any_res = false;
+    for (int i = 0; i < n_segs; ++i) {
+        const poco_conv& c = segs[i];
+        p.seg[i].in = static_cast<const __half*>(c.in.data);
+        p.seg[i].out = static_cast<__half*>(c.out.data);
+        p.seg[i].res = static_cast<const __half*>(c.residual);
+        p.seg[i].w = static_cast<const __half*>(c.weight);
+        p.seg[i].bias = c.bias;
+        p.seg[i].relu = c.relu;
+        if (c.residual) {
+            POCO_CHECK(!any_res || p.res_plane == c.res_plane_stride, "chain: residual plane strides differ");
+            p.res_plane = c.res_plane_stride;
+            any_res = true;
+        }
+        if (i == 0) continue;
+        POCO_CHECK(flags != nullptr, "chain: null flags");
+        POCO_CHECK(c.in.C == in.C && c.out.C == out.C && c.in.N == in.N && c.in.H == in.H && c.in.W == in.W &&
+                       c.out.H == out.H && c.out.W == out.W && c.kh == d->kh && c.kw == d->kw && c.stride == d->stride &&
+                       c.pad == d->pad && c.in.plane_stride == in.plane_stride && c.out.plane_stride == out.plane_stride,
+                   "chain: segments must share one geometry");
+        POCO_CHECK(in.C == out.C, "chain: Cin must equal Cout");
+        POCO_CHECK(c.in.data == segs[i - 1].out.data, "chain: segment i must read what segment i-1 wrote");
+        // a residual is fetched up to one segment ahead of its use: it may come from outside the chain or
+        // from a segment at least two before; and nothing may overwrite a buffer a later segment still reads
+        POCO_CHECK(c.residual != segs[i - 1].out.data, "chain: residual must not be the previous segment's output");
+        POCO_CHECK(c.out.data != c.in.data && c.out.data != c.residual, "chain: in-place segments are not supported");
+    }
     p.Cin = in.C; p.Cout = out.C;
     p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad;
-    p.relu = d->relu;
+    p.w_bufs = 1;
     {
         const char* dbg = getenv("POCO_CONV_DEBUG");
         p.debug = dbg ? atoi(dbg) : 0;
@@ -618,6 +764,7 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
     const bool linear = d->stride == 1 && in.H == out.H && in.W == out.W &&
                         ((d->kh == 3 && d->kw == 3 && d->pad == 1) || (d->kh == 1 && d->kw == 1 && d->pad == 0));
     const int mode = linear ? MODE_LINEAR : MODE_GATHER;
+    POCO_CHECK(n_segs == 1 || (linear && out.W + 3 <= kTileM), "chain: only 3x3/s1/p1 and 1x1/s1 convolutions chain");
     int budget = 0;         // set per attempt below
     const int w_total = taps * in.C * n_tile * 2;
 
@@ -641,18 +788,22 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
         budget = kSmemBudget - kHeaderBytes - ring_bytes_for(p.item_planes);
         if (mode == MODE_LINEAR) {
             const int kcs[4] = {64, 48, 32, 16};
-            for (int resident = 1; resident >= 0 && !found; --resident) {
+            // resident weights: a chain double-buffers them when that still leaves >= 2 operand stages
+            static const int max_wbufs = [] { const char* e = getenv("POCO_CHAIN_WBUFS"); return e ? atoi(e) : 2; }();
+            for (int wb = (n_segs > 1 ? std::min(2, max_wbufs) : 1); wb >= 0 && !found; --wb) {
+                const int resident = wb > 0;
                 if (resident && w_total > 112 * 1024) continue;
                 for (int ki = 0; ki < 4 && !found; ++ki) {
                     const int kc = kcs[ki];
                     if (in.C % kc != 0) continue;
                     const int a_stage = (kc / 8) * p.a_plane_bytes;
                     const int w_stage = resident ? 0 : taps * kc * n_tile * 2;
-                    const int avail = budget - (resident ? w_total : 0);
+                    const int avail = budget - wb * w_total;
                     const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
                     if (stages < (want4 ? 4 : 2)) continue;
                     p.kc = kc; p.n_chunks = in.C / kc;
                     p.w_resident = resident;
+                    p.w_bufs = std::max(1, wb);
                     p.w_res_bytes = resident ? w_total : 0;
                     p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
                     p.rings = stages >= 4 ? 2 : 1;
@@ -686,11 +837,13 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s) {
         }
     }
     POCO_CHECK(found, "no shared-memory configuration fits this convolution");
+    // every epilogue warp that owns a share of a tile signals it once (per N block)
+    p.flag_expect = ((p.n_tile + p.item_planes * 8 - 1) / (p.item_planes * 8) >= 2 ? 8 : 4) * n_blocks;
     // slabs are n_tile*16 bytes (a multiple of 256): the resident region needs no padding and
     // w_res_bytes is both the region size and the mbarrier transaction count
-    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes) + p.w_res_bytes + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
+    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes) + size_t(p.w_res_bytes) * p.w_bufs + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
     p.res_ring = kResRing;
-    if (d->residual != nullptr) {       // spend spare shared memory on a deeper residual prefetch ring
+    if (any_res) {       // spend spare shared memory on a deeper residual prefetch ring
         const int item_bytes = p.item_planes * kPlaneTile;
         const int extra = int((size_t(kSmemBudget) - smem) / (2 * item_bytes));
         p.res_ring = std::min(kMaxResRing, kResRing + std::max(0, extra));

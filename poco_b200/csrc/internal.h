@@ -42,6 +42,7 @@ int check_act(const poco_act& a, const char* what);
 
 // per-TU launchers
 int conv_tc_launch(const poco_conv* d, cudaStream_t s);
+int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cudaStream_t s);
 int conv_ref_launch(const poco_conv* d, cudaStream_t s);
 int64_t conv_flops(const poco_conv* d);
 

@@ -140,6 +140,8 @@ class PlanBuilder:
         self.shares = None      # SM budget per lane inside a fork
         self.num_sms = 148
         self.use_lanes = os.environ.get('POCO_B200_LANES', '1') != '0'
+        self.use_chains = os.environ.get('POCO_B200_CHAINS', '1') != '0'
+        self.chain = None       # pending conv descriptors of an open chain
 
     # -- buffers
     def act(self, C_, H, W):
@@ -256,9 +258,37 @@ class PlanBuilder:
                    residual.plane_stride if residual is not None else 0,
                    k, k, stride, pad, int(relu), self.conv_impl,
                    self.shares[self.lane] if self.shares is not None else 0)
-        self.add(d)
+        if self.chain is not None:
+            self.chain.append(d)
+        else:
+            self.add(d)
         self.conv_log.append((convs[0], x.C, cout, k, stride, x.H, Ho))
         return out
+
+    # -- conv chains: consecutive same-geometry convs (the BasicBlocks of an HRNet branch) as ONE launch
+    def begin_chain(self):
+        assert self.chain is None
+        if self.use_chains and self.conv_impl == 0:
+            self.chain = []
+
+    def end_chain(self):
+        descs, self.chain = self.chain, None
+        if not descs:
+            return
+        for i in range(0, len(descs), L.MAX_CHAIN):
+            grp = descs[i:i + L.MAX_CHAIN]
+            if len(grp) == 1:
+                self.add(grp[0])
+                continue
+            ch = L.ConvChain()
+            for k, d in enumerate(grp):
+                ch.seg[k] = d
+            ch.n_seg = len(grp)
+            n_flags = int(L.lib().poco_conv_chain_flag_count(C.byref(ch)))
+            flags = torch.zeros(max(1, n_flags), dtype=torch.int32, device=self.device)
+            self.keep.append(flags)
+            ch.flags = flags.data_ptr()
+            self.add(ch)
 
     def fuse_sum(self, terms, relu, out=None):
         """terms: list of (ActT, shift)"""

@@ -152,6 +152,12 @@ class Emu:
         f32(d.rotmat, N * 216)[:] = torch.stack((b1, b2, b3), -1).reshape(-1)
 
 
+def _op15(self, d):         # conv chain = its segments in order
+    for k in range(d.n_seg):
+        self._op2(d.seg[k])
+
+
+Emu._op15 = _op15
 Emu._op13 = lambda self, d: None      # fork / join of plan lanes: the interpreter is sequential
 Emu._op14 = lambda self, d: None
 

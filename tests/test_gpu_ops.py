@@ -226,3 +226,75 @@ def test_realnvp_against_reference_goldens(preset):
     # cond_layer
     uf = torch.from_numpy(gold['uncert_feat']).cuda()
     assert rel_err(m.flow_context(uf).cpu().numpy(), gold['flow_ctx']) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# conv chains: the four BasicBlocks of an HRNet branch as one persistent launch (poco_conv_chain)
+# ------------------------------------------------------------------------------------------------
+def _branch_ops(ch, H, N, chained, max_ctas=0, seed=0):
+    """ops + buffers of one HRNet branch (4 BasicBlocks, hrnet.py:42-58) built by the plan builder"""
+    from poco_b200 import arch
+    g = torch.Generator().manual_seed(seed + ch)
+    sd = {}
+    for k in range(4):
+        for c, bn, gamma in (('conv1', 'bn1', 1.0), ('conv2', 'bn2', 0.4)):
+            sd[f'br.{k}.{c}.weight'] = torch.randn(ch, ch, 3, 3, generator=g) * (2.0 / (9 * ch)) ** 0.5
+            sd[f'br.{k}.{bn}.weight'] = gamma * (0.8 + 0.4 * torch.rand(ch, generator=g))
+            sd[f'br.{k}.{bn}.bias'] = 0.1 * torch.randn(ch, generator=g)
+            sd[f'br.{k}.{bn}.running_mean'] = 0.1 * torch.randn(ch, generator=g)
+            sd[f'br.{k}.{bn}.running_var'] = 0.8 + 0.4 * torch.rand(ch, generator=g)
+    b = engine.PlanBuilder(sd, N, 'cuda')
+    b.use_chains = chained
+    if max_ctas:
+        b.shares, b.lane = [max_ctas], 0
+    x0 = torch.randn(N, ch, H, H, generator=g)
+    x = engine.to_planar(x0.cuda())
+    b.keep.append(x.buf)
+    xin = x
+    b.begin_chain()
+    for k in range(4):
+        x = arch.basic_block(b, x, f'br.{k}', ch, ch)
+    b.end_chain()
+    return b, xin, x, x0, sd
+
+
+@pytest.mark.parametrize('ch,H,N,max_ctas', [(32, 56, 12, 0), (32, 56, 5, 7), (64, 28, 20, 0), (128, 14, 40, 0),
+                                             (256, 7, 64, 0), (128, 14, 9, 3), (48, 56, 3, 0)],
+                         ids=lambda v: str(v))
+def test_conv_chain_matches_separate_launches(ch, H, N, max_ctas):
+    """one chained launch == eight separate conv launches, bit for bit, and == the fp32 oracle arithmetic"""
+    outs = []
+    for chained in (False, True):
+        b, xin, xout, x0, sd = _branch_ops(ch, H, N, chained, max_ctas)
+        kinds = [op.kind for op in b.ops]
+        assert kinds == ([L.OP_CONV_CHAIN] if chained else [L.OP_CONV] * 8)
+        for rep in range(3 if chained else 1):          # replays re-zero the tile flags
+            engine.act_view(xin)[:, :, 1:H + 1, 1:H + 1, :] = \
+                x0.cuda().half().view(N, ch // 8, 8, H, H).permute(1, 0, 3, 4, 2)
+            for op in b.ops:
+                L.run_op(op, stream())
+            sync_or_die(30)
+            outs.append(engine.from_planar(xout).cpu())
+        halo = engine.act_view(xout)
+        assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
+                     halo[:, :, :, -1].abs().sum()) == 0.0
+    for o in outs[2:]:
+        assert torch.equal(o, outs[1])                  # replays of the chain are deterministic
+    if ch != 64:
+        assert torch.equal(outs[1], outs[0])            # same tiling and K order as the separate launches
+    else:       # double-buffered resident weights leave room for 32-channel K chunks only: the fp32
+        # accumulation order differs from the separate launches, a few fp16 roundings flip
+        assert rel_err(outs[1].numpy(), outs[0].numpy()) < 2e-3
+    # oracle arithmetic with the engine's roundings (fp16 activations and folded weights, fp32 accumulate)
+    x = x0.half().float()
+    for k in range(4):
+        y = x
+        for c, bn, relu, res in (('conv1', 'bn1', True, False), ('conv2', 'bn2', True, True)):
+            bnp = tuple(sd[f'br.{k}.{bn}{s}'] for s in ('.weight', '.bias', '.running_mean', '.running_var'))
+            wf, bf = engine.fold_bn(sd[f'br.{k}.{c}.weight'], None, bnp)
+            y = F.conv2d(y, wf.half().float(), bf, padding=1)
+            if res:
+                y = y + x
+            y = F.relu(y).half().float()
+        x = y
+    assert rel_err(outs[0].numpy(), x.numpy()) < 4e-3
