@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpoco_b200.so')
+LIB_PATH = os.environ.get('POCO_B200_LIB') or os.path.join(_HERE, 'libpoco_b200.so')     # (override: A/B benchmarking of builds)
 
 MAX_FUSE_INPUTS = 4
 ACT_GUARD_BYTES = 8192

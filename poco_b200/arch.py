@@ -102,7 +102,7 @@ class SpecBackend:
     def begin_chain(self):
         pass
 
-    def end_chain(self):
+    def end_chain(self, groups=1):
         pass
 
 
@@ -152,6 +152,20 @@ def bottleneck(b, x, name, cin, planes, stride=1, downsample=False, free_input=T
 # ------------------------------------------------------------------------------------------------
 # HRNet trunk (shared by the pose variant and the classification variant)
 # ------------------------------------------------------------------------------------------------
+def chain_groups(branch, n_branches):
+    """crop ranges per branch chain (PlanBuilder.end_chain): POCO_B200_GROUPS="g0,g1,g2,g3" overrides"""
+    import os
+    env = os.environ.get('POCO_B200_GROUPS')
+    table = [int(v) for v in env.split(',')] if env else [1, 1, 1, 1]
+    return table[branch] if branch < len(table) else 1
+
+
+def chain_policy(channels):
+    """POCO_B200_CHAIN_MIN_C=<c>: chain the BasicBlocks of branches with at least c channels (default 128)"""
+    import os
+    return channels >= int(os.environ.get('POCO_B200_CHAIN_MIN_C', '100000'))
+
+
 def hr_module(b, xs, name, chans):
     """HighResolutionModule: 4 BasicBlocks per branch, then the multi-resolution fuse
     (hrnet.py:188-266).  Inputs are consumed (freed).  The branches, and afterwards the per-output
@@ -163,10 +177,17 @@ def hr_module(b, xs, name, chans):
     for i in range(nb):
         b.set_lane(i)
         x = xs[i]
-        b.begin_chain()                 # the branch's eight convs share one geometry: one persistent launch
+        # The branch's eight convs share one geometry.  For the low-resolution branches (few tiles per SM,
+        # so the ~8 us launch + pipeline fill of a conv is most of its time) they run as ONE persistent
+        # chained launch; measured at batch 256 (tools/chain_bench.py) the chain wins from 128 channels up
+        # and loses below (the flag protocol's fences cost more than the launches they replace).
+        chained = chain_policy(chans[i])
+        if chained:
+            b.begin_chain()
         for k in range(4):
             x = basic_block(b, x, f'{name}.branches.{i}.{k}', chans[i], chans[i])
-        b.end_chain()
+        if chained:
+            b.end_chain(groups=chain_groups(i, nb))
         xs[i] = x
     b.join()
     if nb == 1:

@@ -33,7 +33,14 @@ namespace poco {
 
 namespace {
 
+// -DPOCO_MBAR_WATCHDOG: every mbarrier wait gets a 2 s watchdog that reports its source line and traps
+// (bring-up builds only: the bookkeeping in the hot wait loops costs 8-14 % of every conv, measured).
+// The global-memory flag spin of the chain protocol always carries the watchdog.
+#ifdef POCO_MBAR_WATCHDOG
 #define MBAR_WAIT(bar, parity) mbar_wait_tag(bar, parity, __LINE__)
+#else
+#define MBAR_WAIT(bar, parity) mbar_wait(bar, parity)
+#endif
 
 constexpr int kMaxStages = 8;
 constexpr int kMaxAccBufs = 8;                     // TMEM accumulator ring (512 columns / n_tile)
@@ -155,11 +162,12 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
-    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void red_relaxed_gpu_add(int* p, int v) {
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // order earlier generic-proxy accesses (here: an acquire of data other threads wrote with st.global)
 // before later async-proxy accesses (bulk copies reading that data)
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 template <int MODE, int IPL>
@@ -268,16 +276,23 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             const __half* wg = sg.w + size_t(nb) * p.n_tile * 8;
             const int* flags_prev = s > 0 ? p.flags + size_t(s - 1) * p.num_m_tiles : nullptr;
             int j = 0;
+            int ready_upto = flags_prev != nullptr ? 0 : my_tiles;     // local tiles [0, ready_upto) may be loaded
             for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl, ++j) {
-                if (flags_prev != nullptr) {
-                    // this tile's input run spans output tiles tile-1 .. tile+1 of the previous segment
-                    const int tt = tile - 1 + lane;
-                    const bool need = lane < 3 && tt >= 0 && tt < p.num_m_tiles;
+                if (j >= ready_upto) {
+                    // Tile t reads output tiles t-1 .. t+1 of the previous segment.  One poll covers this
+                    // CTA's next 10 tiles (3 flags each, one per lane): in steady state the neighbours
+                    // finished them a whole segment ago, so the L2 round trip is paid once per 10 tiles.
                     uint32_t spins = 0;
                     unsigned long long t0 = 0;
-                    for (;;) {
+                    while (j >= ready_upto) {
+                        const int jj = ready_upto + lane / 3;
+                        const int tt = int(blockIdx.x) + jj * int(gridDim.x) - 1 + lane % 3;
+                        const bool need = lane < 30 && jj < my_tiles && tt >= 0 && tt < p.num_m_tiles;
                         const int v = need ? ld_acquire_gpu(flags_prev + tt) : p.flag_expect;
-                        if (__all_sync(0xffffffffu, v >= p.flag_expect)) break;
+                        const uint32_t ok = __ballot_sync(0xffffffffu, v >= p.flag_expect);
+                        int cnt = 0;
+                        while (cnt < 10 && ((ok >> (3 * cnt)) & 7u) == 7u) ++cnt;
+                        ready_upto = min(my_tiles, ready_upto + cnt);
                         if ((++spins & 255u) == 0u) {
                             if (t0 == 0) t0 = global_timer_ns();
                             spin_timeout(-(s * 100000 + tile), t0);
@@ -512,24 +527,32 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         // item) of this warp.  A segment's residual may be the output of the segment two before it, so
         // the cursor never runs past segment `cur + 1` (everything up to `cur - 1` is complete on this
         // CTA: all epilogue warps meet at a barrier between segments).
-        int pf_s = 0, pf_j = 0, pf_k = k_first(0);
-        uint32_t pf_issued = 0;
         auto seg_has_res = [&](int s_) { return p.seg[s_].res != nullptr && !(p.debug & 16); };
+        int pf_s = 0;
+        while (pf_s < n_segs && !seg_has_res(pf_s)) ++pf_s;
+        int pf_j = 0, pf_k = k_first(uint32_t(pf_s * my_tiles));
+        uint32_t pf_tl = uint32_t(pf_s * my_tiles);
+        long long pf_tile = blockIdx.x;
+        const __half* pf_res = pf_s < n_segs ? p.seg[pf_s].res : nullptr;
+        uint32_t pf_issued = 0;
         auto prefetch_residual = [&](int cur_seg, uint32_t upto) {      // elected lane: top the ring up to `upto` items
             while (pf_issued < upto) {
-                while (pf_s < n_segs) {         // advance to the next residual item
-                    if (seg_has_res(pf_s) && pf_j < my_tiles) {
-                        if (pf_k < items) break;
-                        ++pf_j;
-                        pf_k = k_first(uint32_t(pf_s * my_tiles + pf_j));
-                        continue;
+                while (pf_k >= items) {         // advance to the next tile (segment) with an item for this half
+                    ++pf_j;
+                    ++pf_tl;
+                    pf_tile += gridDim.x;
+                    if (pf_j >= my_tiles) {
+                        do { ++pf_s; } while (pf_s < n_segs && !seg_has_res(pf_s));
+                        if (pf_s >= n_segs) { pf_k = 0; pf_s = n_segs; return; }
+                        pf_j = 0;
+                        pf_tl = uint32_t(pf_s * my_tiles);
+                        pf_tile = blockIdx.x;
+                        pf_res = p.seg[pf_s].res;
                     }
-                    ++pf_s;
-                    pf_j = 0;
-                    pf_k = k_first(uint32_t(pf_s * my_tiles));
+                    pf_k = k_first(pf_tl);
                 }
                 if (pf_s >= n_segs || pf_s > cur_seg + 1) return;
-                const long long tile_ = (long long)blockIdx.x + (long long)pf_j * gridDim.x;
+                const long long tile_ = pf_tile;
                 const int item = pf_k;
                 pf_k += 2;
                 const uint32_t slot = pf_issued % rr_n;
@@ -544,7 +567,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 const uint32_t rows = uint32_t(left < 32 ? left : 32);
                 const int planes = min(ipl, (p.n_tile >> 3) - item * ipl);
                 mbar_arrive_expect_tx(bar, uint32_t(planes) * rows * 16u);
-                const __half* src = p.seg[pf_s].res + ((long long)(plane0 + item * ipl) * p.res_plane + qw) * 8;
+                const __half* src = pf_res + ((long long)(plane0 + item * ipl) * p.res_plane + qw) * 8;
                 const uint32_t dst = smem_u32(res_ring) + slot * kSlot;
                 for (int pl = 0; pl < planes; ++pl, src += p.res_plane * 8)
                     bulk_g2s(dst + uint32_t(pl) * 512u, src, rows * 16u, bar);
@@ -560,8 +583,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             int* flags_cur = s + 1 < n_segs ? p.flags + size_t(s) * p.num_m_tiles : nullptr;
             float* bias_s = hdr->bias[s & 1];
             {   // this segment's bias -> shared memory; between segments every epilogue warp has finished
-                // (and fenced) the stores of the previous one, which also bounds the residual prefetch
-                if (s > 0) __threadfence();
+                // (and fenced, in its last signal_tiles) the stores of the previous one, which also bounds the
+                // residual prefetch
                 const int t = threadIdx.x - R::kEpiWarp0 * 32;
                 for (int i = t; i < p.n_tile; i += 256) bias_s[i] = sg.bias[nb * p.n_tile + i];
                 named_barrier_sync(1, 256);
@@ -573,7 +596,24 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             __syncwarp();
             // position of this thread's row inside its crop, advanced incrementally from tile to tile
             uint32_t rem = uint32_t(((long long)blockIdx.x * kTileM + row) % HpWp_o);
+            // Completion flags are published in batches: one gpu-scope fence (it waits for the warp's
+            // outstanding stores, ~1 us) covers the last kSignalEvery tiles this warp had a share of.
+            // Consumers run a whole segment behind, so the delay costs nothing; the segment end flushes.
+            const int kSignalEvery = max(1, min(8, my_tiles / (odd ? 8 : 4)));
+            int sig_first = 0, sig_owned = 0;               // local tiles [sig_first, j] still unpublished
+            const uint32_t tl_seg0 = tl;
+            auto signal_tiles = [&](int j_last) {
+                fence_acq_rel_gpu();
+                __syncwarp();
+                const int jl = sig_first + lane;
+                if (jl <= j_last && k_first(tl_seg0 + uint32_t(jl)) < items)
+                    red_relaxed_gpu_add(flags_cur + (int(blockIdx.x) + jl * int(gridDim.x)), 1);
+                sig_first = j_last + 1;
+                sig_owned = 0;
+            };
+            int j = -1;
             for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
+                ++j;
                 const uint32_t buf = tl % nacc;
                 const long long qw = (long long)tile * kTileM + lg * 32;     // first row of this warp's slice
                 const uint32_t yy = __umulhi(rem, magic_w), xx = rem - yy * uint32_t(Wp_o);
@@ -589,10 +629,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 if (p.debug & 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
-                        if (flags_cur != nullptr) red_release_gpu_add(flags_cur + tile, 1);
-                    }
+                    if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
+                    if (flags_cur != nullptr && (++sig_owned >= kSignalEvery)) signal_tiles(j);
                     continue;
                 }
                 const uint32_t taddr = tmem_base + buf * buf_cols + (uint32_t(lg * 32) << 16);
@@ -653,11 +691,9 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                         __syncwarp();
                     }
                 }
-                if (flags_cur != nullptr) {                 // this warp's share of the tile is in global memory
-                    __syncwarp();
-                    if (lane == 0) red_release_gpu_add(flags_cur + tile, 1);
-                }
+                if (flags_cur != nullptr && (++sig_owned >= kSignalEvery)) signal_tiles(j);
             }
+            if (flags_cur != nullptr) signal_tiles(my_tiles - 1);
         }
     }
 

@@ -92,6 +92,29 @@ __global__ void conv_ref_kernel(Act in, Act out, const __half* __restrict__ w, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Thread mapping of the element-wise kernels: a 256-thread block covers 256 / slots image rows, where
+// slots = W rounded up to a power of two; thread t handles column t % slots of row t / slots.  All index
+// math is 32-bit with one division per thread (the first version's 64-bit div / mod per pixel kept
+// these kernels at ~1 TB/s).  blockIdx.y = plane group.
+struct RowMap {
+    int slots_log2;
+    int rows;           // N * H
+};
+inline RowMap row_map(int N, int H, int W) {
+    int l = 0;
+    while ((1 << l) < W) ++l;
+    return RowMap{std::min(l, 8), N * H};
+}
+inline unsigned row_blocks(const RowMap& m) { return unsigned((m.rows + (256 >> m.slots_log2) - 1) / (256 >> m.slots_log2)); }
+__device__ __forceinline__ bool row_coords(const RowMap& m, int H, int W, int& n, int& y, int& x) {
+    x = threadIdx.x & ((1 << m.slots_log2) - 1);
+    const int row = blockIdx.x * (256 >> m.slots_log2) + (threadIdx.x >> m.slots_log2);
+    if (row >= m.rows || x >= W) return false;
+    n = row / H;
+    y = row - n * H;
+    return true;
+}
+
 __global__ void pack_image_kernel(const float* __restrict__ img, Act out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long npix = (long long)out.N * out.H * out.W;
@@ -111,45 +134,63 @@ struct FuseArgs {
     int shift[POCO_MAX_FUSE_INPUTS];
     int n_in, relu;
 };
-__global__ void fuse_sum_kernel(FuseArgs a) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long npix = (long long)a.out.N * a.out.H * a.out.W;
-    if (idx >= npix) return;
-    const int pl = blockIdx.y;
-    const int x = int(idx % a.out.W), y = int((idx / a.out.W) % a.out.H), n = int(idx / ((long long)a.out.W * a.out.H));
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = 0; k < a.n_in; ++k) {
-        float f[8];
-        unpack8(ld16(a.in[k], pl, pix_index(a.in[k], n, y >> a.shift[k], x >> a.shift[k])), f);
+__global__ void __launch_bounds__(256) fuse_sum_kernel(FuseArgs a, RowMap m, int planes_per_thread) {
+    int n, y, x;
+    if (!row_coords(m, a.out.H, a.out.W, n, y, x)) return;
+    long long pin[POCO_MAX_FUSE_INPUTS];
+    for (int k = 0; k < a.n_in; ++k) pin[k] = pix_index(a.in[k], n, y >> a.shift[k], x >> a.shift[k]);
+    const long long po = pix_index(a.out, n, y, x);
+    const int pl0 = blockIdx.y * planes_per_thread;
+    for (int pl = pl0; pl < pl0 + planes_per_thread; ++pl) {
+        uint4 v[POCO_MAX_FUSE_INPUTS];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += f[i];
-    }
-    if (a.relu) {
+        for (int k = 0; k < POCO_MAX_FUSE_INPUTS; ++k)
+            if (k < a.n_in) v[k] = ld16(a.in[k], pl, pin[k]);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+        for (int k = 0; k < POCO_MAX_FUSE_INPUTS; ++k)
+            if (k < a.n_in) {
+                float f[8];
+                unpack8(v[k], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += f[i];
+            }
+        if (a.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+        }
+        st16(a.out, pl, po, pack8(acc));
     }
-    st16(a.out, pl, pix_index(a.out, n, y, x), pack8(acc));
 }
 
 // bilinear x2, align_corners=True: src = dst * (in-1)/(out-1)  (matches aten upsample_bilinear2d)
-__global__ void upsample2x_kernel(Act in, Act out, float sy, float sx) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long npix = (long long)out.N * out.H * out.W;
-    if (idx >= npix) return;
-    const int pl = blockIdx.y;
-    const int x = int(idx % out.W), y = int((idx / out.W) % out.H), n = int(idx / ((long long)out.W * out.H));
+__global__ void __launch_bounds__(256) upsample2x_kernel(Act in, Act out, float sy, float sx, RowMap m, int planes_per_thread) {
+    int n, y, x;
+    if (!row_coords(m, out.H, out.W, n, y, x)) return;
     const float fy = sy * y, fx = sx * x;
     const int y0 = min(int(fy), in.H - 1), x0 = min(int(fx), in.W - 1);
     const int y1 = min(y0 + 1, in.H - 1), x1 = min(x0 + 1, in.W - 1);
     const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    float a[8], b[8], c[8], d[8], o[8];
-    unpack8(ld16(in, pl, pix_index(in, n, y0, x0)), a);
-    unpack8(ld16(in, pl, pix_index(in, n, y0, x1)), b);
-    unpack8(ld16(in, pl, pix_index(in, n, y1, x0)), c);
-    unpack8(ld16(in, pl, pix_index(in, n, y1, x1)), d);
+    const long long p00 = pix_index(in, n, y0, x0), p01 = pix_index(in, n, y0, x1);
+    const long long p10 = pix_index(in, n, y1, x0), p11 = pix_index(in, n, y1, x1);
+    const long long po = pix_index(out, n, y, x);
+    const int pl0 = blockIdx.y * planes_per_thread;
+    for (int pl = pl0; pl < pl0 + planes_per_thread; pl += 2) {       // two planes = eight 16-byte loads in flight
+        uint4 v[2][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
-    st16(out, pl, pix_index(out, n, y, x), pack8(o));
+        for (int q = 0; q < 2; ++q) {
+            v[q][0] = ld16(in, pl + q, p00); v[q][1] = ld16(in, pl + q, p01);
+            v[q][2] = ld16(in, pl + q, p10); v[q][3] = ld16(in, pl + q, p11);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float a[8], b[8], c[8], d[8], o[8];
+            unpack8(v[q][0], a); unpack8(v[q][1], b); unpack8(v[q][2], c); unpack8(v[q][3], d);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+            st16(out, pl + q, po, pack8(o));
+        }
+    }
 }
 
 __global__ void maxpool_kernel(Act in, Act out) {
@@ -258,6 +299,7 @@ extern "C" int poco_fuse_sum_run(const poco_fuse_sum* d, void* stream) {
     a.out = mk(d->out);
     a.n_in = d->n_in;
     a.relu = d->relu;
+    POCO_CHECK(d->out.W <= 256, "fuse_sum: W <= 256");
     for (int k = 0; k < d->n_in; ++k) {
         if (check_act(d->in[k], "in")) return 1;
         POCO_CHECK(d->in[k].C == d->out.C && d->in[k].N == d->out.N, "fuse input channel/batch mismatch");
@@ -266,9 +308,11 @@ extern "C" int poco_fuse_sum_run(const poco_fuse_sum* d, void* stream) {
         a.in[k] = mk(d->in[k]);
         a.shift[k] = d->shift[k];
     }
-    const long long npix = (long long)d->out.N * d->out.H * d->out.W;
-    dim3 grid(blocks_for(npix, 256), d->out.C / 8);
-    fuse_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    const RowMap m = row_map(d->out.N, d->out.H, d->out.W);
+    const int planes = d->out.C / 8;
+    const int ppt = planes % 4 == 0 ? 4 : (planes % 2 == 0 ? 2 : 1);      // planes per thread: independent loads in flight
+    dim3 grid(row_blocks(m), planes / ppt);
+    fuse_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, m, ppt);
     POCO_LAUNCHED();
     return 0;
 }
@@ -279,9 +323,12 @@ extern "C" int poco_upsample2x_run(const poco_upsample2x* d, void* stream) {
                "upsample geometry mismatch");
     const float sy = d->out.H > 1 ? float(d->in.H - 1) / float(d->out.H - 1) : 0.f;
     const float sx = d->out.W > 1 ? float(d->in.W - 1) / float(d->out.W - 1) : 0.f;
-    const long long npix = (long long)d->out.N * d->out.H * d->out.W;
-    dim3 grid(blocks_for(npix, 256), d->out.C / 8);
-    upsample2x_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(d->in), mk(d->out), sy, sx);
+    POCO_CHECK(d->out.C % 16 == 0 && d->out.W <= 256, "upsample2x: channels must be a multiple of 16 and W <= 256");
+    const RowMap m = row_map(d->out.N, d->out.H, d->out.W);
+    const int planes = d->out.C / 8;
+    const int ppt = planes % 4 == 0 ? 4 : 2;
+    dim3 grid(row_blocks(m), planes / ppt);
+    upsample2x_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(d->in), mk(d->out), sy, sx, m, ppt);
     POCO_LAUNCHED();
     return 0;
 }

@@ -271,24 +271,42 @@ class PlanBuilder:
         if self.use_chains and self.conv_impl == 0:
             self.chain = []
 
-    def end_chain(self):
+    def end_chain(self, groups=1):
+        """emit the pending convs as chain launches.  groups > 1: the batch is cut into that many contiguous
+        crop ranges and the whole chain runs range by range, so that the activations one range passes from
+        conv to conv stay in the 126 MB L2 instead of making an HBM round trip per conv (crops are
+        independent; a range is a pointer offset and a smaller N in the planar layout)."""
         descs, self.chain = self.chain, None
         if not descs:
             return
-        for i in range(0, len(descs), L.MAX_CHAIN):
-            grp = descs[i:i + L.MAX_CHAIN]
-            if len(grp) == 1:
-                self.add(grp[0])
-                continue
-            ch = L.ConvChain()
-            for k, d in enumerate(grp):
-                ch.seg[k] = d
-            ch.n_seg = len(grp)
-            n_flags = int(L.lib().poco_conv_chain_flag_count(C.byref(ch)))
-            flags = torch.zeros(max(1, n_flags), dtype=torch.int32, device=self.device)
-            self.keep.append(flags)
-            ch.flags = flags.data_ptr()
-            self.add(ch)
+        groups = max(1, min(int(groups), self.N)) if len(descs) > 1 else 1
+        bounds = [self.N * g // groups for g in range(groups + 1)]
+        for g in range(groups):
+            n0, n1 = bounds[g], bounds[g + 1]
+            sub = []
+            for d in descs:
+                e = L.Conv.from_buffer_copy(d)
+                if groups > 1:
+                    for a in (e.in_, e.out):
+                        a.data += n0 * (a.H + 2) * (a.W + 2) * 16
+                        a.N = n1 - n0
+                    if e.residual:
+                        e.residual += n0 * (e.out.H + 2) * (e.out.W + 2) * 16
+                sub.append(e)
+            for i in range(0, len(sub), L.MAX_CHAIN):
+                grp = sub[i:i + L.MAX_CHAIN]
+                if len(grp) == 1:
+                    self.add(grp[0])
+                    continue
+                ch = L.ConvChain()
+                for k, d in enumerate(grp):
+                    ch.seg[k] = d
+                ch.n_seg = len(grp)
+                n_flags = int(L.lib().poco_conv_chain_flag_count(C.byref(ch)))
+                flags = torch.zeros(max(1, n_flags), dtype=torch.int32, device=self.device)
+                self.keep.append(flags)
+                ch.flags = flags.data_ptr()
+                self.add(ch)
 
     def fuse_sum(self, terms, relu, out=None):
         """terms: list of (ActT, shift)"""

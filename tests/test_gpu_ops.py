@@ -231,7 +231,7 @@ def test_realnvp_against_reference_goldens(preset):
 # ------------------------------------------------------------------------------------------------
 # conv chains: the four BasicBlocks of an HRNet branch as one persistent launch (poco_conv_chain)
 # ------------------------------------------------------------------------------------------------
-def _branch_ops(ch, H, N, chained, max_ctas=0, seed=0):
+def _branch_ops(ch, H, N, chained, max_ctas=0, seed=0, groups=1):
     """ops + buffers of one HRNet branch (4 BasicBlocks, hrnet.py:42-58) built by the plan builder"""
     from poco_b200 import arch
     g = torch.Generator().manual_seed(seed + ch)
@@ -254,20 +254,23 @@ def _branch_ops(ch, H, N, chained, max_ctas=0, seed=0):
     b.begin_chain()
     for k in range(4):
         x = arch.basic_block(b, x, f'br.{k}', ch, ch)
-    b.end_chain()
+    b.end_chain(groups=groups)
     return b, xin, x, x0, sd
 
 
-@pytest.mark.parametrize('ch,H,N,max_ctas', [(32, 56, 12, 0), (32, 56, 5, 7), (64, 28, 20, 0), (128, 14, 40, 0),
-                                             (256, 7, 64, 0), (128, 14, 9, 3), (48, 56, 3, 0)],
+@pytest.mark.parametrize('ch,H,N,max_ctas,groups', [(32, 56, 12, 0, 1), (32, 56, 5, 7, 1), (64, 28, 20, 0, 1),
+                                                    (128, 14, 40, 0, 1), (256, 7, 64, 0, 1), (128, 14, 9, 3, 1),
+                                                    (48, 56, 3, 0, 1), (32, 56, 11, 0, 3), (256, 7, 13, 0, 4),
+                                                    (64, 28, 9, 5, 2)],
                          ids=lambda v: str(v))
-def test_conv_chain_matches_separate_launches(ch, H, N, max_ctas):
-    """one chained launch == eight separate conv launches, bit for bit, and == the fp32 oracle arithmetic"""
+def test_conv_chain_matches_separate_launches(ch, H, N, max_ctas, groups):
+    """one chained launch (or one per crop range) == eight separate conv launches, bit for bit, and == the
+    fp32 oracle arithmetic"""
     outs = []
     for chained in (False, True):
-        b, xin, xout, x0, sd = _branch_ops(ch, H, N, chained, max_ctas)
+        b, xin, xout, x0, sd = _branch_ops(ch, H, N, chained, max_ctas, groups=groups)
         kinds = [op.kind for op in b.ops]
-        assert kinds == ([L.OP_CONV_CHAIN] if chained else [L.OP_CONV] * 8)
+        assert kinds == ([L.OP_CONV_CHAIN] * groups if chained else [L.OP_CONV] * 8)
         for rep in range(3 if chained else 1):          # replays re-zero the tile flags
             engine.act_view(xin)[:, :, 1:H + 1, 1:H + 1, :] = \
                 x0.cuda().half().view(N, ch // 8, 8, H, H).permute(1, 0, 3, 4, 2)
@@ -298,3 +301,34 @@ def test_conv_chain_matches_separate_launches(ch, H, N, max_ctas):
             y = F.relu(y).half().float()
         x = y
     assert rel_err(outs[0].numpy(), x.numpy()) < 4e-3
+
+
+@pytest.mark.parametrize('C,H,N', [(24, 28, 3), (48, 14, 2), (64, 56, 2), (256, 7, 5)])
+def test_fuse_sum_and_upsample_odd_geometries(C, H, N):
+    """row-mapped element-wise kernels: widths that are not powers of two, plane counts 3 / 6 / 8 / 32"""
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(C + H)
+    xs = [torch.randn(N, C, H, H, generator=g).half().float(), torch.randn(N, C, H // 2, H // 2, generator=g).half().float()] \
+        if H % 2 == 0 else [torch.randn(N, C, H, H, generator=g).half().float()]
+    acts = [engine.to_planar(x.to(dev)) for x in xs]
+    out = engine.alloc_act(C, N, H, H, dev)
+    d = L.FuseSum()
+    d.out = out.desc()
+    for i, a in enumerate(acts):
+        d.in_[i] = a.desc()
+        d.shift[i] = i
+    d.n_in, d.relu = len(acts), 0
+    L.run_op(d, stream())
+    sync_or_die()
+    ref = xs[0] + (F.interpolate(xs[1], scale_factor=2, mode='nearest') if len(xs) > 1 else 0)
+    assert rel_err(engine.from_planar(out).cpu().numpy(), ref.numpy()) < 1e-3
+    hv = engine.act_view(out)
+    assert float(hv[:, :, 0].abs().sum() + hv[:, :, -1].abs().sum() + hv[:, :, :, 0].abs().sum() + hv[:, :, :, -1].abs().sum()) == 0.0
+    if C % 16 == 0:
+        up = engine.alloc_act(C, N, 2 * H, 2 * H, dev)
+        L.run_op(L.Upsample2x(acts[0].desc(), up.desc()), stream())
+        sync_or_die()
+        ref = F.interpolate(xs[0], scale_factor=2, mode='bilinear', align_corners=True)
+        assert rel_err(engine.from_planar(up).cpu().numpy(), ref.numpy()) < 1e-3
+        hv = engine.act_view(up)
+        assert float(hv[:, :, 0].abs().sum() + hv[:, :, -1].abs().sum() + hv[:, :, :, 0].abs().sum() + hv[:, :, :, -1].abs().sum()) == 0.0
