@@ -69,6 +69,13 @@ typedef struct poco_conv_chain {
 typedef struct poco_pack_image {
     const float* img;
     poco_act out;
+    /* 0: out = [16 ch][N][H][W], channels 3..15 zero.
+     * 1: im2col of a 3x3 / stride 2 / pad 1 window (the HRNet stem conv1, hrnet.py:299-301, :467-469):
+     *    img is [N,3,2*out.H,2*out.W], out = [32 ch][N][out.H][out.W] with channel (r*3+s)*3+c =
+     *    img[n, c, 2y+r-1, 2x+s-1] (0 outside), channels 27..31 zero -- the stem conv then runs as a 1x1 conv
+     *    with K = 32 instead of a 3x3 conv over 16 zero-padded channels (half the activation bytes). */
+    int32_t im2col;
+    int32_t pad_;
 } poco_pack_image;
 
 /* out = relu?( sum_k nearest_upsample(in[k], 2^shift[k]) ): the HRNet multi-resolution fuse

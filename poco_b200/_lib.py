@@ -34,7 +34,7 @@ class ConvChain(C.Structure):
 
 
 class PackImage(C.Structure):
-    _fields_ = [('img', C.c_void_p), ('out', Act)]
+    _fields_ = [('img', C.c_void_p), ('out', Act), ('im2col', C.c_int32), ('pad_', C.c_int32)]
 
 
 class FuseSum(C.Structure):

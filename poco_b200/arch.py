@@ -44,6 +44,11 @@ class SpecBackend:
     def pack_image(self, img, H, W):
         return SymAct(16, H, W)
 
+    def stem_conv(self, img, H, W, conv, bn, cout):
+        self._p(conv + '.weight', (cout, 3, 3, 3))
+        self._bn(bn, cout)
+        return SymAct(cout, H // 2, W // 2)
+
     def conv_bn(self, x, conv, bn, cin, cout, k, stride=1, relu=True, residual=None, out=None, pad=None, bias=False):
         convs = conv if isinstance(conv, (list, tuple)) else [conv]
         bns = bn if isinstance(bn, (list, tuple)) else [bn] * len(convs)
@@ -242,9 +247,7 @@ def hr_module(b, xs, name, chans):
 
 def hrnet_trunk(b, img, widths, H=224, W=224, prefix='backbone.'):
     p = prefix
-    x = b.pack_image(img, H, W)
-    y = b.conv_bn(x, p + 'conv1', p + 'bn1', 3, 64, 3, 2)
-    b.free(x)
+    y = b.stem_conv(img, H, W, p + 'conv1', p + 'bn1', 64)
     x = b.conv_bn(y, p + 'conv2', p + 'bn2', 64, 64, 3, 2)
     b.free(y)
     for k in range(4):

@@ -128,6 +128,33 @@ __global__ void pack_image_kernel(const float* __restrict__ img, Act out) {
     for (int pl = 1; pl < (out.C >> 3); ++pl) st16(out, pl, op, make_uint4(0, 0, 0, 0));
 }
 
+// im2col of the 3x3 / stride-2 / pad-1 stem window: 27 taps x channels -> 32 fp16 channels per output pixel
+__global__ void __launch_bounds__(256) pack_stem_kernel(const float* __restrict__ img, Act out, RowMap m) {
+    int n, y, x;
+    if (!row_coords(m, out.H, out.W, n, y, x)) return;
+    const int Hi = 2 * out.H, Wi = 2 * out.W;
+    const long long hw = (long long)Hi * Wi;
+    const float* src = img + (long long)n * 3 * hw;
+    float f[32];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int yi = 2 * y + r - 1;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int xi = 2 * x + s - 1;
+            const bool ok = yi >= 0 && yi < Hi && xi >= 0 && xi < Wi;
+            const long long o = (long long)yi * Wi + xi;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[(r * 3 + s) * 3 + c] = ok ? __ldg(src + c * hw + o) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int k = 27; k < 32; ++k) f[k] = 0.f;
+    const long long op = pix_index(out, n, y, x);
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl) st16(out, pl, op, pack8(f + pl * 8));
+}
+
 struct FuseArgs {
     Act out;
     Act in[POCO_MAX_FUSE_INPUTS];
@@ -286,6 +313,13 @@ using namespace poco;
 extern "C" int poco_pack_image_run(const poco_pack_image* d, void* stream) {
     if (check_act(d->out, "out")) return 1;
     POCO_CHECK(d->img != nullptr, "null image");
+    if (d->im2col) {
+        POCO_CHECK(d->out.C == 32 && d->out.W <= 256, "im2col stem packing writes 32 channels, W <= 256");
+        const RowMap m = row_map(d->out.N, d->out.H, d->out.W);
+        pack_stem_kernel<<<row_blocks(m), 256, 0, static_cast<cudaStream_t>(stream)>>>(d->img, mk(d->out), m);
+        POCO_LAUNCHED();
+        return 0;
+    }
     const long long npix = (long long)d->out.N * d->out.H * d->out.W;
     pack_image_kernel<<<blocks_for(npix, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d->img, mk(d->out));
     POCO_LAUNCHED();

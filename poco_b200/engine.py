@@ -221,7 +221,32 @@ class PlanBuilder:
     # -- ops
     def pack_image(self, img, H, W):
         out = self.act(16, H, W)
-        self.add(L.PackImage(img.data_ptr(), out.desc()))
+        self.add(L.PackImage(img.data_ptr(), out.desc(), 0, 0))
+        return out
+
+    def stem_conv(self, img, H, W, conv, bn, cout):
+        """conv3x3(3 -> cout, stride 2, pad 1) + BN + ReLU straight from the f32 image (hrnet.py:299-301,
+        :467-469): the packing kernel writes the 27-tap im2col (32 fp16 channels at half resolution) and the
+        conv runs as a 1x1 conv with K = 32 -- half the activation bytes of a 3x3 conv over 16 zero-padded
+        channels and no strided gather."""
+        sd = self.sd
+        col = self.act(32, H // 2, W // 2)
+        self.add(L.PackImage(img.data_ptr(), col.desc(), 1, 0))
+        w = sd[conv + '.weight'].to(self.device)
+        assert tuple(w.shape) == (cout, 3, 3, 3), (conv, tuple(w.shape))
+        bnp = tuple(sd[bn + s].to(self.device) for s in ('.weight', '.bias', '.running_mean', '.running_var'))
+        wf, bf = fold_bn(w, None, bnp)
+        w1 = wf.permute(0, 2, 3, 1).reshape(cout, 27)               # k = (r*3+s)*3 + c
+        w1 = torch.cat([w1, w1.new_zeros(cout, 5)], 1).reshape(cout, 32, 1, 1)
+        wp = pack_conv_weight(w1)
+        bf = bf.contiguous()
+        self.keep += [wp, bf]
+        out = self.act(cout, H // 2, W // 2)
+        d = L.Conv(col.desc(), out.desc(), wp.data_ptr(), bf.data_ptr(), None, 0, 1, 1, 1, 0, 1, self.conv_impl,
+                   self.shares[self.lane] if self.shares is not None else 0)
+        self.add(d)
+        self.conv_log.append((conv, 32, cout, 1, 1, H // 2, H // 2))
+        self.free(col)
         return out
 
     def conv_bn(self, x, conv, bn, cin, cout, k, stride=1, relu=True, residual=None, out=None, pad=None, bias=False):

@@ -55,6 +55,13 @@ class Emu:
 
     def _op1(self, d):      # pack image
         o = d.out
+        if d.im2col:
+            img = self.flat(d.img, torch.float32)[:o.N * 3 * 4 * o.H * o.W].view(o.N, 3, 2 * o.H, 2 * o.W)
+            cols = F.unfold(img, 3, padding=1, stride=2).view(o.N, 3, 9, o.H, o.W)      # [N, c, r*3+s, H, W]
+            x = torch.zeros(o.N, 32, o.H, o.W)
+            x[:, :27] = cols.permute(0, 2, 1, 3, 4).reshape(o.N, 27, o.H, o.W)
+            self.act_set(o, x)
+            return
         img = self.flat(d.img, torch.float32)[:o.N * 3 * o.H * o.W].view(o.N, 3, o.H, o.W)
         x = torch.zeros(o.N, o.C, o.H, o.W)
         x[:, :3] = img

@@ -30,6 +30,10 @@ CONV_CASES = [
     (3, 64, 3, 2, 224, 1, False, 1), (64, 64, 3, 2, 112, 1, False, 1), (32, 64, 3, 2, 56, 2, False, 1),
     (256, 256, 3, 2, 14, 2, True, 2), (3, 64, 7, 2, 224, 1, False, 1), (256, 512, 1, 2, 56, 1, False, 0),
     (128, 256, 3, 2, 14, 3, True, 1),
+    # stride-2 3x3 on even inputs: phase-split producer (MODE_S2) when its stages fit, else the gather
+    (32, 32, 3, 2, 56, 3, False, 1), (64, 128, 3, 2, 28, 5, True, 1), (32, 128, 3, 2, 28, 2, True, 0),
+    (256, 64, 3, 2, 56, 1, False, 1), (48, 96, 3, 2, 28, 2, True, 1), (32, 32, 3, 2, 28, 3, False, 1),
+    (64, 256, 3, 2, 14, 2, True, 1), (16, 64, 3, 2, 224, 2, False, 1),
 ]
 
 
@@ -332,3 +336,23 @@ def test_fuse_sum_and_upsample_odd_geometries(C, H, N):
         assert rel_err(engine.from_planar(up).cpu().numpy(), ref.numpy()) < 1e-3
         hv = engine.act_view(up)
         assert float(hv[:, :, 0].abs().sum() + hv[:, :, -1].abs().sum() + hv[:, :, :, 0].abs().sum() + hv[:, :, :, -1].abs().sum()) == 0.0
+
+
+def test_stem_im2col_conv_matches_strided_conv():
+    """pack_image(im2col=1) + 1x1 conv (K = 32) == conv3x3(3 -> 64, stride 2, pad 1) + BN + ReLU of the HRNet stem"""
+    from poco_b200 import arch
+    g = torch.Generator().manual_seed(11)
+    N, H = 3, 64
+    img = torch.randn(N, 3, H, H, generator=g)
+    sd = {'c.weight': torch.randn(64, 3, 3, 3, generator=g) * 0.2, 'b.weight': 0.8 + 0.4 * torch.rand(64, generator=g),
+          'b.bias': 0.1 * torch.randn(64, generator=g), 'b.running_mean': 0.1 * torch.randn(64, generator=g),
+          'b.running_var': 0.8 + 0.4 * torch.rand(64, generator=g)}
+    b = engine.PlanBuilder(sd, N, 'cuda')
+    imgd = img.cuda()
+    out = b.stem_conv(imgd, H, H, 'c', 'b', 64)
+    for op in b.ops:
+        L.run_op(op, stream())
+    sync_or_die()
+    wf, bf = engine.fold_bn(sd['c.weight'], None, tuple(sd['b' + s] for s in ('.weight', '.bias', '.running_mean', '.running_var')))
+    ref = F.relu(F.conv2d(img.half().float(), wf.half().float(), bf, stride=2, padding=1))
+    assert rel_err(engine.from_planar(out).cpu().numpy(), ref.numpy()) < CONV_TOL
