@@ -46,7 +46,9 @@ typedef struct poco_conv {
     int32_t relu; /* 0 none; 1 ReLU after the residual add; 2 ReLU before the residual add */
     int32_t impl; /* 0 = tcgen05 implicit GEMM (product path); 1 = CUDA-core debug kernel */
     int32_t max_ctas; /* 0 = one CTA per SM; else cap on the persistent grid (concurrent plan lanes share the SMs) */
-    int32_t pad_;
+    int32_t wfmt; /* weight layout: 0 = [kh*kw][Cin/8][Cout][8]; 1 = "dx in N" for 3x3 / stride 1 / pad 1 with
+                   * Cout in {32, 64}: [kh][Cin/8][kw*Cout][8] (column s*Cout + co of filter row r) -- the three
+                   * horizontal taps share one MMA, a third of the shared-memory operand reads */
 } poco_conv;
 
 /* A chain of convolutions of ONE geometry (3x3/s1/p1 or 1x1/s1, Cin == Cout) executed by one persistent

@@ -26,7 +26,7 @@ class Conv(C.Structure):
     _fields_ = [('in_', Act), ('out', Act), ('weight', C.c_void_p), ('bias', C.c_void_p),
                 ('residual', C.c_void_p), ('res_plane_stride', C.c_int64),
                 ('kh', C.c_int32), ('kw', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
-                ('relu', C.c_int32), ('impl', C.c_int32), ('max_ctas', C.c_int32), ('pad_', C.c_int32)]
+                ('relu', C.c_int32), ('impl', C.c_int32), ('max_ctas', C.c_int32), ('wfmt', C.c_int32)]
 
 
 class ConvChain(C.Structure):

@@ -50,6 +50,7 @@ extern "C" int poco_conv_run(const poco_conv* d, void* stream) {
     POCO_CHECK(d->kh >= 1 && d->kw >= 1 && d->pad >= 0, "bad kernel geometry");
     POCO_CHECK(!d->residual || d->res_plane_stride >= int64_t(d->out.N) * (d->out.H + 2) * (d->out.W + 2),
                "residual plane stride too small");
+    POCO_CHECK(d->impl == 0 || d->wfmt == 0, "the debug kernel reads the standard weight layout only");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return d->impl == 1 ? conv_ref_launch(d, s) : conv_tc_launch(d, s);
 }

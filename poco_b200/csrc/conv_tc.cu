@@ -46,7 +46,7 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxAccBufs = 8;                     // TMEM accumulator ring (512 columns / n_tile)
 constexpr int kTileM = 128;
 constexpr int kSmemBudget = 225 * 1024;   // of 227 KB usable per CTA
-constexpr int kHeaderBytes = 4096;        // barriers + bias
+constexpr int kHeaderBytes = 8192;        // barriers + bias + dx-in-N exchange buffers
 constexpr int kGatherLag = 2;
 constexpr int kPlaneTile = kTileM * 16;            // one output plane of one tile: 2 KB, contiguous in HBM
 constexpr int kOutRing = 0, kResRing = 4, kMaxResRing = 16;     // residual prefetch depth grows into spare smem
@@ -79,6 +79,11 @@ struct ConvTcParams {
     long long res_plane;
     int Cin, Cout;
     int kh, kw, stride, pad;
+    int taps;             // filter taps the MMA loop walks (kh*kw; 3 in dx-in-N mode: the rows of the 3x3)
+    int tile_stride;      // output pixels between consecutive tiles (128; 126 in dx-in-N mode) ...
+    int tile_origin;      // ... and the pixel of tile 0 / row 0 (0; -1 in dx-in-N mode)
+    int n_out;            // output channels this CTA's epilogue writes (n_tile; Cout in dx-in-N mode)
+    int epi_items;        // epilogue work items per tile
     int w_bufs;           // resident-weight buffers (2 = the next segment's weights load while this one computes)
     int kc, n_chunks;
     int n_tile;
@@ -108,6 +113,7 @@ struct SmemHeader {
     uint32_t tmem_base;
     uint32_t pad_[3];
     float bias[2][256];                                // double buffered across chain segments
+    float xch[2][2][4][2][32];                         // dx-in-N: [half][buffer][warp][D0 of row 31 | D2 of row 0][channel]
 };
 static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
 
@@ -138,7 +144,7 @@ __device__ __forceinline__ void issue_linear(uint32_t d_tmem, uint32_t a_lo, uin
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) {
         // tap (r,s): shift of (r-1) rows and (s-1) pixels inside the landed run (16 B per pixel = 1 descriptor unit)
-        const uint32_t at = a_lo + (TAPS == 1 ? 0u : uint32_t((t / 3 - 1) * Wp + (t % 3 - 1)));
+        const uint32_t at = a_lo + (TAPS == 1 ? 0u : TAPS == 3 ? uint32_t((t - 1) * Wp) : uint32_t((t / 3 - 1) * Wp + (t % 3 - 1)));
         const uint32_t bt = b_lo + uint32_t(t) * b_tap;
 #pragma unroll
         for (int k = 0; k < KS; ++k)
@@ -170,7 +176,14 @@ __device__ __forceinline__ void red_relaxed_gpu_add(int* p, int v) {
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int MODE, int IPL>
+// DXN ("dx in N", 3x3 / stride 1 with Cout <= 64): the three horizontal taps of a filter row ride in the N
+// dimension (N = 3 * Cout), so a tile costs 3 * Cin/16 MMAs instead of 9 * Cin/16 and its A operand is
+// fetched from shared memory 3 times instead of 9 -- for Cout = 32 / 64 the tensor pipe is otherwise busy
+// re-reading A (ncu: 58 % tensor-pipe-active for 32->32 with 12 % of the MMA rate used).  The accumulator
+// then holds D_s[p] = sum_{r,c} in[p + (r-1) Wp][c] W[r][s][c] and the epilogue forms
+// out[q] = D_0[q-1] + D_1[q] + D_2[q+1] with warp shuffles (+ a 2 x 32-float exchange between the four warps
+// of a tile); tiles advance by 126 pixels so that rows 0 and 127 of a tile are never outputs.
+template <int MODE, int IPL, bool DXN>
 __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
@@ -184,7 +197,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // provably warp-uniform for ptxas
     const int lane = threadIdx.x & 31;
     const int nb = blockIdx.y;                      // N block
-    const int taps = p.kh * p.kw;
+    const int taps = p.taps;
     const int planes_per_chunk = p.kc >> 3;
     const int cin8 = p.Cin >> 3;
     const int kiters = MODE == MODE_LINEAR ? p.n_chunks : p.n_chunks * (taps / p.tap_group);
@@ -203,7 +216,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         }
         if (t >= 32 && t < 32 + p.acc_bufs) {
             mbar_init(smem_u32(&hdr->tmem_full[t - 32]), 1);
-            mbar_init(smem_u32(&hdr->tmem_empty[t - 32]), (p.n_tile + ipl * 8 - 1) / (ipl * 8) >= 2 ? 8 : 4);   // epilogue warps draining one tile
+            mbar_init(smem_u32(&hdr->tmem_empty[t - 32]), p.epi_items >= 2 ? 8 : 4);   // epilogue warps draining one tile
         }
         if (t >= 60 && t < 62) {
             mbar_init(smem_u32(&hdr->w_ready[t - 60]), 1);
@@ -230,7 +243,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     // UTCHMMA in a vote + branch "waterfall", ~60 issue slots per MMA -- see profiles/).
     // When this CTA covers all of Cout (one N block), consecutive 8-channel slabs are contiguous in
     // global and shared memory, so `group` slabs travel as one bulk copy.
-    const bool whole_n = p.n_tile == p.Cout;
+    const int w_n = DXN ? 3 * p.Cout : p.Cout;       // columns of one (tap, 8-channel) slab of the weight tensor
+    const bool whole_n = p.n_tile == w_n;
     auto load_resident_weights = [&](int s) {      // weights of segment s -> resident buffer s % w_bufs
         const int b = p.w_bufs == 2 ? (s & 1) : 0;
         const __half* wg = p.seg[s].w + size_t(nb) * p.n_tile * 8;
@@ -241,19 +255,19 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         const int group = whole_n ? min(total, 64) : 1;          // <= 64 slabs (<= 256 KB) per copy
         for (int i = 0; i < total; i += group) {
             const int g = min(group, total - i);
-            bulk_g2s(dst + uint32_t(i) * slab_bytes, wg + size_t(i) * p.Cout * 8, uint32_t(g) * slab_bytes, bar);
+            bulk_g2s(dst + uint32_t(i) * slab_bytes, wg + size_t(i) * w_n * 8, uint32_t(g) * slab_bytes, bar);
         }
     };
     auto load_stage_weights = [&](const __half* wg, uint32_t ws, uint32_t bar, int t0, int t1, int c) {
         // taps [t0, t1) of K chunk c -> ws, slabs ordered [tap][plane]
         for (int t = t0; t < t1; ++t) {
             const uint32_t dst = ws + uint32_t((t - t0) * planes_per_chunk) * slab_bytes;
-            const __half* src = wg + size_t(t * cin8 + c * planes_per_chunk) * p.Cout * 8;
+            const __half* src = wg + size_t(t * cin8 + c * planes_per_chunk) * w_n * 8;
             if (whole_n) {
                 bulk_g2s(dst, src, uint32_t(planes_per_chunk) * slab_bytes, bar);
             } else {
                 for (int j = 0; j < planes_per_chunk; ++j)
-                    bulk_g2s(dst + uint32_t(j) * slab_bytes, src + size_t(j) * p.Cout * 8, slab_bytes, bar);
+                    bulk_g2s(dst + uint32_t(j) * slab_bytes, src + size_t(j) * w_n * 8, slab_bytes, bar);
             }
         }
     };
@@ -300,7 +314,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     }
                     fence_proxy_async_all();
                 }
-                const long long q0 = (long long)tile * kTileM - p.halo;
+                const long long q0 = (long long)tile * p.tile_stride + p.tile_origin - p.halo;
                 const uint32_t ring = p.rings == 2 ? (tl & 1u) : 0u;
                 for (int c = 0; c < p.n_chunks; ++c) {
                     const uint32_t it = its[ring]++;
@@ -462,6 +476,13 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                                         case 3: POCO_ISSUE(9, 3); break;
                                         default: POCO_ISSUE(9, 4); break;
                                     }
+                                } else if (DXN) {
+                                    switch (ksteps) {
+                                        case 1: POCO_ISSUE(3, 1); break;
+                                        case 2: POCO_ISSUE(3, 2); break;
+                                        case 3: POCO_ISSUE(3, 3); break;
+                                        default: POCO_ISSUE(3, 4); break;
+                                    }
                                 } else {
                                     switch (ksteps) {
                                         case 1: POCO_ISSUE(1, 1); break;
@@ -512,8 +533,9 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         const int lg = warp & 3;                        // TMEM lane group this warp may access
         const int row = lg * 32 + lane;
         const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
-        const int plane0 = (nb * p.n_tile) >> 3;
-        const int items = (p.n_tile + ipl * 8 - 1) / (ipl * 8);      // work items per tile
+        const int n_out = p.n_out;
+        const int plane0 = DXN ? 0 : (nb * p.n_tile) >> 3;
+        const int items = p.epi_items;                  // work items per tile
         // (tile, item) pairs are dealt alternately to the two halves: with one item per tile (N <= 32) the
         // halves take alternate TILES, so each warp has two tile-times for its waits and index math
         const int odd = items & 1;
@@ -557,7 +579,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 pf_k += 2;
                 const uint32_t slot = pf_issued % rr_n;
                 ++pf_issued;
-                const long long qw = tile_ * kTileM + lg * 32;
+                const long long qw = tile_ * p.tile_stride + p.tile_origin + lg * 32;
                 const long long left = p.P_out - qw;
                 const uint32_t bar = smem_u32(&res_full[slot]);
                 if (left <= 0) {                // rows past the end of the tensor: complete the slot's phase anyway
@@ -565,7 +587,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     continue;
                 }
                 const uint32_t rows = uint32_t(left < 32 ? left : 32);
-                const int planes = min(ipl, (p.n_tile >> 3) - item * ipl);
+                const int planes = min(ipl, (n_out >> 3) - item * ipl);
                 mbar_arrive_expect_tx(bar, uint32_t(planes) * rows * 16u);
                 const __half* src = pf_res + ((long long)(plane0 + item * ipl) * p.res_plane + qw) * 8;
                 const uint32_t dst = smem_u32(res_ring) + slot * kSlot;
@@ -573,9 +595,10 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     bulk_g2s(dst + uint32_t(pl) * 512u, src, rows * 16u, bar);
             }
         };
-        const uint32_t step = uint32_t(((long long)gridDim.x * kTileM) % HpWp_o);
+        const uint32_t step = uint32_t(((long long)gridDim.x * p.tile_stride) % HpWp_o);
         const uint32_t magic_w = 0xFFFFFFFFu / uint32_t(Wp_o) + 1u;      // exact floor(n / Wp) for n < 2^16
         uint32_t tl = 0, g = 0;                         // g counts residual items consumed
+        int xbuf = 0;                                   // dx-in-N exchange buffer of this half (alternates per item)
         for (int s = 0; s < n_segs; ++s) {
             const ChainSeg& sg = p.seg[s];
             const bool has_res = seg_has_res(s);
@@ -586,7 +609,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 // (and fenced, in its last signal_tiles) the stores of the previous one, which also bounds the
                 // residual prefetch
                 const int t = threadIdx.x - R::kEpiWarp0 * 32;
-                for (int i = t; i < p.n_tile; i += 256) bias_s[i] = sg.bias[nb * p.n_tile + i];
+                for (int i = t; i < n_out; i += 256) bias_s[i] = sg.bias[(DXN ? 0 : nb * p.n_tile) + i];
                 named_barrier_sync(1, 256);
             }
             if (elect_one()) {
@@ -595,7 +618,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             }
             __syncwarp();
             // position of this thread's row inside its crop, advanced incrementally from tile to tile
-            uint32_t rem = uint32_t(((long long)blockIdx.x * kTileM + row) % HpWp_o);
+            uint32_t rem = uint32_t(((long long)blockIdx.x * p.tile_stride + p.tile_origin + row + HpWp_o) % HpWp_o);
             // Completion flags are published in batches: one gpu-scope fence (it waits for the warp's
             // outstanding stores, ~1 us) covers the last kSignalEvery tiles this warp had a share of.
             // Consumers run a whole segment behind, so the delay costs nothing; the segment end flushes.
@@ -615,9 +638,10 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
                 ++j;
                 const uint32_t buf = tl % nacc;
-                const long long qw = (long long)tile * kTileM + lg * 32;     // first row of this warp's slice
+                const long long qw = (long long)tile * p.tile_stride + p.tile_origin + lg * 32;     // first row of this warp's slice
                 const uint32_t yy = __umulhi(rem, magic_w), xx = rem - yy * uint32_t(Wp_o);
-                const bool interior = qw + lane < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout);
+                const bool interior = qw + lane < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout) &&
+                                      !(DXN && (row == 0 || row == kTileM - 1));     // (dx-in-N: the tile's edge rows belong to its neighbours)
                 rem += step;
                 if (rem >= uint32_t(HpWp_o)) rem -= uint32_t(HpWp_o);
                 const long long left = p.P_out - qw;
@@ -636,15 +660,65 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 const uint32_t taddr = tmem_base + buf * buf_cols + (uint32_t(lg * 32) << 16);
                 for (int item = k0; item < items; item += 2) {
                     const int c0 = item * ipl * 8;
-                    const int planes = min(ipl, (p.n_tile - c0) >> 3);       // 2 or 4
+                    const int planes = min(ipl, (n_out - c0) >> 3);         // 2 or 4
                     uint32_t v[IPL * 8];
-                    tmem_ld16(taddr + uint32_t(c0), v);
-                    if (IPL == 4 && planes == 4) tmem_ld16(taddr + uint32_t(c0 + 16), v + (IPL == 4 ? 16 : 0));
-                    tmem_ld_wait();
-                    if (item + 2 >= items) {                // this warp is done with the accumulator buffer
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
+                    if (DXN && IPL == 4) {
+                        // the three column groups D_0 | D_1 | D_2 of these 32 output channels
+                        uint32_t d0[32], d1[32], d2[32];
+                        tmem_ld16(taddr + uint32_t(c0), d0);
+                        tmem_ld16(taddr + uint32_t(c0 + 16), d0 + 16);
+                        tmem_ld16(taddr + uint32_t(n_out + c0), d1);
+                        tmem_ld16(taddr + uint32_t(n_out + c0 + 16), d1 + 16);
+                        tmem_ld16(taddr + uint32_t(2 * n_out + c0), d2);
+                        tmem_ld16(taddr + uint32_t(2 * n_out + c0 + 16), d2 + 16);
+                        tmem_ld_wait();
+                        if (item + 2 >= items) {            // this warp is done with the accumulator buffer
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
+                        }
+                        // rows 31 / 0 of this warp are the left / right neighbours of the adjacent warps' edge rows
+                        float(*xs)[2][32] = hdr->xch[half][xbuf];
+                        xbuf ^= 1;
+                        if (lane == 31) {
+#pragma unroll
+                            for (int c = 0; c < 32; c += 4)
+                                *reinterpret_cast<uint4*>(&xs[lg][0][c]) = make_uint4(d0[c], d0[c + 1], d0[c + 2], d0[c + 3]);
+                        }
+                        if (lane == 0) {
+#pragma unroll
+                            for (int c = 0; c < 32; c += 4)
+                                *reinterpret_cast<uint4*>(&xs[lg][1][c]) = make_uint4(d2[c], d2[c + 1], d2[c + 2], d2[c + 3]);
+                        }
+                        named_barrier_sync(2 + half, 128);
+                        // every lane reads the neighbour warps' edge rows (broadcast loads, no divergence) and
+                        // selects them only at its own edge lanes; rows 0 / 127 of the tile are never stored
+                        const float* nl = xs[lg > 0 ? lg - 1 : 0][0];
+                        const float* nr = xs[lg < 3 ? lg + 1 : 3][1];
+#pragma unroll
+                        for (int c4 = 0; c4 < 32; c4 += 4) {
+                            const float4 l4 = *reinterpret_cast<const float4*>(nl + c4);
+                            const float4 r4 = *reinterpret_cast<const float4*>(nr + c4);
+                            const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int c = c4 + i;
+                                float a = __shfl_up_sync(0xffffffffu, __uint_as_float(d0[c]), 1);
+                                float b = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[c]), 1);
+                                a = lane == 0 ? lv[i] : a;
+                                b = lane == 31 ? rv[i] : b;
+                                v[c] = __float_as_uint(a + __uint_as_float(d1[c]) + b);
+                            }
+                        }
+                    } else {
+                        tmem_ld16(taddr + uint32_t(c0), v);
+                        if (IPL == 4 && planes == 4) tmem_ld16(taddr + uint32_t(c0 + 16), v + (IPL == 4 ? 16 : 0));
+                        tmem_ld_wait();
+                        if (item + 2 >= items) {            // this warp is done with the accumulator buffer
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
+                        }
                     }
                     const uint32_t rslot = g % rr_n;
                     if (has_res) MBAR_WAIT(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
@@ -782,30 +856,40 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         p.debug = dbg ? atoi(dbg) : 0;
     }
     p.P_out = int64_t(out.N) * (out.H + 2) * (out.W + 2);
-    p.num_m_tiles = int((p.P_out + kTileM - 1) / kTileM);
+    // weight format 1 = dx-in-N: [3 filter rows][Cin/8][3 * Cout (s-major)][8], see conv_tc_kernel
+    const bool dxn = d->wfmt == 1;
+    POCO_CHECK(d->wfmt == 0 || d->wfmt == 1, "unknown weight format");
+    p.tile_stride = dxn ? kTileM - 2 : kTileM;
+    p.tile_origin = dxn ? -1 : 0;
+    p.num_m_tiles = int((p.P_out + p.tile_stride - 1) / p.tile_stride);
 
-    // N blocking: largest multiple-of-16 divisor of Cout that is <= 256
+    // N blocking: largest multiple-of-16 divisor of Cout that is <= 256 (dx-in-N: the three column groups)
     int n_tile = 0;
     for (int t = std::min(256, out.C); t >= 16; t -= 16)
         if (out.C % t == 0) { n_tile = t; break; }
-    POCO_CHECK(n_tile > 0, "no valid N tile");
+    if (dxn) n_tile = 3 * out.C;
+    POCO_CHECK(n_tile > 0 && n_tile <= 256, "no valid N tile");
     p.n_tile = n_tile;
-    const int n_blocks = out.C / n_tile;
+    const int n_blocks = dxn ? 1 : out.C / n_tile;
     int cols = 32;                      // accumulator buffer pitch: power of two >= n_tile
     while (cols < n_tile) cols <<= 1;
     p.acc_bufs = std::min(kMaxAccBufs, 512 / cols);      // the MMA warp may run this many tiles ahead of the epilogue
     p.tmem_cols = cols * p.acc_bufs;
 
-    const int taps = d->kh * d->kw;
+    const int taps = dxn ? 3 : d->kh * d->kw;       // taps the MMA loop walks
+    p.taps = taps;
     const bool linear = d->stride == 1 && in.H == out.H && in.W == out.W &&
                         ((d->kh == 3 && d->kw == 3 && d->pad == 1) || (d->kh == 1 && d->kw == 1 && d->pad == 0));
     const int mode = linear ? MODE_LINEAR : MODE_GATHER;
+    POCO_CHECK(!dxn || (linear && d->kh == 3 && n_segs == 1 && out.C % 32 == 0 && 3 * out.C <= 256),
+               "dx-in-N weights need a single 3x3 / stride 1 / pad 1 conv with 32 or 64 output channels");
+    for (int i = 1; i < n_segs; ++i) POCO_CHECK(segs[i].wfmt == 0, "chain: dx-in-N weights are not supported");
     POCO_CHECK(n_segs == 1 || (linear && out.W + 3 <= kTileM), "chain: only 3x3/s1/p1 and 1x1/s1 convolutions chain");
     int budget = 0;         // set per attempt below
     const int w_total = taps * in.C * n_tile * 2;
 
     if (mode == MODE_LINEAR) {
-        p.halo = taps == 9 ? (out.W + 2) + 1 : 0;
+        p.halo = dxn ? (out.W + 2) : (taps == 9 ? (out.W + 2) + 1 : 0);
         p.a_copy_bytes = (kTileM + 2 * p.halo) * 16;
         p.a_plane_bytes = round_up(p.a_copy_bytes, 128);
     } else {
@@ -819,7 +903,7 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     // other shape the operand stages are the better use of shared memory (measured, profiles/).
     bool found = false;
     p.tap_group = 1;
-    for (int want4 = (mode == MODE_LINEAR && ((n_tile >= 64 && taps == 1) || n_tile == 32) ? 1 : 0); want4 >= 0 && !found; --want4) {
+    for (int want4 = (mode == MODE_LINEAR && (dxn || (n_tile >= 64 && taps == 1) || n_tile == 32) ? 1 : 0); want4 >= (dxn ? 1 : 0) && !found; --want4) {
         p.item_planes = want4 ? 4 : 2;
         budget = kSmemBudget - kHeaderBytes - ring_bytes_for(p.item_planes);
         if (mode == MODE_LINEAR) {
@@ -874,7 +958,9 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     }
     POCO_CHECK(found, "no shared-memory configuration fits this convolution");
     // every epilogue warp that owns a share of a tile signals it once (per N block)
-    p.flag_expect = ((p.n_tile + p.item_planes * 8 - 1) / (p.item_planes * 8) >= 2 ? 8 : 4) * n_blocks;
+    p.n_out = dxn ? out.C : n_tile;
+    p.epi_items = (p.n_out + p.item_planes * 8 - 1) / (p.item_planes * 8);
+    p.flag_expect = (p.epi_items >= 2 ? 8 : 4) * n_blocks;
     // slabs are n_tile*16 bytes (a multiple of 256): the resident region needs no padding and
     // w_res_bytes is both the region size and the mbarrier transaction count
     size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes) + size_t(p.w_res_bytes) * p.w_bufs + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
@@ -903,15 +989,17 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         cfg.blockDim = dim3(threads);
         return cudaLaunchKernelEx(&cfg, kernel, pk);
     };
-    static std::once_flag once4[4];
-    if (mode == MODE_LINEAR && p.item_planes == 2)
-        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2>, once4[0], Roles<MODE_LINEAR>::kThreads));
+    static std::once_flag once4[5];
+    if (dxn)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, true>, once4[4], Roles<MODE_LINEAR>::kThreads));
+    else if (mode == MODE_LINEAR && p.item_planes == 2)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false>, once4[0], Roles<MODE_LINEAR>::kThreads));
     else if (mode == MODE_LINEAR)
-        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4>, once4[1], Roles<MODE_LINEAR>::kThreads));
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false>, once4[1], Roles<MODE_LINEAR>::kThreads));
     else if (p.item_planes == 2)
-        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 2>, once4[2], Roles<MODE_GATHER>::kThreads));
+        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 2, false>, once4[2], Roles<MODE_GATHER>::kThreads));
     else
-        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 4>, once4[3], Roles<MODE_GATHER>::kThreads));
+        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 4, false>, once4[3], Roles<MODE_GATHER>::kThreads));
     POCO_LAUNCHED();
     return 0;
 }

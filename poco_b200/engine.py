@@ -106,6 +106,25 @@ def pack_conv_weight(w, cin_pad=None):
     return p.contiguous().to(torch.float16)
 
 
+def pack_conv_weight_dxn(w):
+    """[Cout, Cin, 3, 3] f32 -> fp16 [3 (filter row r)][Cin/8][3*Cout (column s*Cout + co)][8]: the "dx in N"
+    layout of poco_conv.wfmt = 1 (the three taps of a filter row share one MMA)"""
+    cout, cin, kh, kw = w.shape
+    assert (kh, kw) == (3, 3) and cin % 16 == 0 and cout % 32 == 0 and 3 * cout <= 256, tuple(w.shape)
+    p = w.permute(2, 1, 3, 0).reshape(3, cin // 8, 8, 3 * cout).permute(0, 1, 3, 2)
+    return p.contiguous().to(torch.float16)
+
+
+def dxn_applies(cin, cout, k, stride, pad):
+    """3x3 / stride 1 / pad 1 convs with 32 or 64 output channels CAN run in dx-in-N mode (POCO_B200_DXN=1).
+    Off by default: measured at batch 256 (tools/conv_bench.py ... dxn) the mode cuts the MMA work of a tile
+    from 18 to 6 instructions, but these layers are bound by the operand-load pipeline (26 us with MMAs and
+    epilogue skipped) and the 3x wider TMEM read + shuffle epilogue costs more than the MMAs it saves
+    (32->32 @56: 49 vs 36 us, 64->64 @28: 35 vs 31 us)."""
+    return (os.environ.get('POCO_B200_DXN', '0') == '1' and k == 3 and stride == 1 and pad == 1 and
+            cout in (32, 64) and cin % 16 == 0)
+
+
 def pack_realnvp(sd, prefix='flow_head.flow.'):
     """flat fp32 parameter block of poco_realnvp (include/poco_b200.h)"""
     mask = sd[prefix + 'mask']
@@ -267,10 +286,11 @@ class PlanBuilder:
             wf, bf = fold_bn(w, cb.to(self.device) if cb is not None else None, bnp)
             ws.append(wf)
             bs.append(bf)
-        wp = pack_conv_weight(torch.cat(ws, 0), cin_pad=x.C)
+        pad = k // 2 if pad is None else pad
+        wfmt = 1 if (self.conv_impl == 0 and self.chain is None and x.C == cin and dxn_applies(cin, cout, k, stride, pad)) else 0
+        wp = pack_conv_weight_dxn(torch.cat(ws, 0)) if wfmt else pack_conv_weight(torch.cat(ws, 0), cin_pad=x.C)
         bf = torch.cat(bs, 0).contiguous()
         self.keep += [wp, bf]
-        pad = k // 2 if pad is None else pad
         Ho = (x.H + 2 * pad - k) // stride + 1
         Wo = (x.W + 2 * pad - k) // stride + 1
         if out is None:
@@ -282,7 +302,7 @@ class PlanBuilder:
                    residual.ptr if residual is not None else None,
                    residual.plane_stride if residual is not None else 0,
                    k, k, stride, pad, int(relu), self.conv_impl,
-                   self.shares[self.lane] if self.shares is not None else 0)
+                   self.shares[self.lane] if self.shares is not None else 0, wfmt)
         if self.chain is not None:
             self.chain.append(d)
         else:

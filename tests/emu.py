@@ -70,8 +70,12 @@ class Emu:
     def _op2(self, d):      # conv
         i, o = d.in_, d.out
         taps = d.kh * d.kw
-        wp = self.flat(d.weight, torch.float16)[:taps * i.C * o.C].view(taps, i.C // 8, o.C, 8).float()
-        w = wp.permute(2, 1, 3, 0).reshape(o.C, i.C, d.kh, d.kw)
+        if d.wfmt == 1:     # dx-in-N layout [r][Cin/8][s*Cout + co][8]
+            wp = self.flat(d.weight, torch.float16)[:taps * i.C * o.C].view(3, i.C // 8, 3, o.C, 8).float()
+            w = wp.permute(3, 1, 4, 0, 2).reshape(o.C, i.C, 3, 3)
+        else:
+            wp = self.flat(d.weight, torch.float16)[:taps * i.C * o.C].view(taps, i.C // 8, o.C, 8).float()
+            w = wp.permute(2, 1, 3, 0).reshape(o.C, i.C, d.kh, d.kw)
         b = self.flat(d.bias, torch.float32)[:o.C]
         y = F.conv2d(self.act_get(i), w, b, stride=d.stride, padding=d.pad)
         if d.relu == 2:

@@ -27,7 +27,7 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def run_conv(x, w, bias, stride=1, pad=None, relu=1, residual=None, impl=0):
+def run_conv(x, w, bias, stride=1, pad=None, relu=1, residual=None, impl=0, dxn=False):
     """x [N,Cin,H,W], w [Cout,Cin,k,k], bias [Cout] (CPU float) -> [N,Cout,Ho,Wo] float (CPU).
     Inputs are rounded to fp16 exactly as the engine does."""
     dev = 'cuda'
@@ -38,11 +38,11 @@ def run_conv(x, w, bias, stride=1, pad=None, relu=1, residual=None, impl=0):
     a = engine.to_planar(x.to(dev), c_pad=cin_p)
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     o = engine.alloc_act(Cout, N, Ho, Wo, dev)
-    wp = engine.pack_conv_weight(w.to(dev).float(), cin_pad=cin_p)
+    wp = engine.pack_conv_weight_dxn(w.to(dev).float()) if dxn else engine.pack_conv_weight(w.to(dev).float(), cin_pad=cin_p)
     b = bias.to(dev).float().contiguous()
     r = engine.to_planar(residual.to(dev)) if residual is not None else None
     d = L.Conv(a.desc(), o.desc(), wp.data_ptr(), b.data_ptr(), r.ptr if r is not None else None,
-               r.plane_stride if r is not None else 0, k, k, stride, pad, relu, impl)
+               r.plane_stride if r is not None else 0, k, k, stride, pad, relu, impl, 0, 1 if dxn else 0)
     L.run_op(d, stream())
     sync_or_die()
     out = engine.from_planar(o).cpu()

@@ -15,6 +15,7 @@ from gpu_util import sync_or_die  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 DBG = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 1, 2, 3]
+DXN = len(sys.argv) > 3 and sys.argv[3] == 'dxn'
 CASES = [(32, 32, 3, 1, 56, False), (32, 32, 3, 1, 56, True), (64, 64, 3, 1, 28, True), (128, 128, 3, 1, 14, True),
          (256, 256, 3, 1, 7, True), (64, 256, 1, 1, 56, True), (256, 256, 3, 1, 56, False), (16, 64, 3, 2, 224, False),
          (32, 64, 3, 2, 56, True)]
@@ -29,7 +30,7 @@ for cin, cout, k, st, H, res in CASES:
     w = (torch.randn(k * k, cin // 8, cout, 8, device='cuda') * 0.05).half()
     b = torch.zeros(cout, device='cuda')
     d = L.Conv(a.desc(), o.desc(), w.data_ptr(), b.data_ptr(), r.ptr if r else None, r.plane_stride if r else 0,
-               k, k, st, k // 2, 1, 0)
+               k, k, st, k // 2, 1, 0, 0, 1 if (DXN and k == 3 and st == 1 and cout in (32, 64)) else 0)
     op = L.make_op(d)
     for dbg in DBG:
         os.environ['POCO_CONV_DEBUG'] = str(dbg)

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_ops.py -q -x > gpurun_out/t_ops.log 2>&1; rc=$?; echo "ops tests rc=$rc"; tail -n 12 gpurun_out/t_ops.log
+timeout 200 python -m pytest tests/test_gpu_ops.py -q -x -k "dx_in_n" > gpurun_out/t_dxn.log 2>&1; echo "dxn rc=$?"; tail -n 6 gpurun_out/t_dxn.log; timeout 600 python -m pytest tests/test_gpu_ops.py -q -x > gpurun_out/t_ops.log 2>&1; rc=$?; echo "ops tests rc=$rc"; tail -n 12 gpurun_out/t_ops.log
 if [ $rc -ne 0 ]; then exit 1; fi
 timeout 600 python -m pytest tests -q -m gpu -x --deselect tests/test_gpu_ops.py > gpurun_out/t_gpu.log 2>&1; echo "pytest gpu rest rc=$?"; tail -n 4 gpurun_out/t_gpu.log
 timeout 300 python tools/region_times.py 256 > gpurun_out/region_times.txt 2>&1; head -3 gpurun_out/region_times.txt; tail -n 3 gpurun_out/region_times.txt
