@@ -79,6 +79,7 @@ struct ConvTcParams {
     long long res_plane;
     int Cin, Cout;
     int kh, kw, stride, pad;
+    int m_group;          // MODE_LINEAR: adjacent tiles fetched as one run (one halo per group) and walked per stage: 1, 2 or 4
     int taps;             // filter taps the MMA loop walks (kh*kw; 3 in dx-in-N mode: the rows of the 3x3)
     int tile_stride;      // output pixels between consecutive tiles (128; 126 in dx-in-N mode) ...
     int tile_origin;      // ... and the pixel of tile 0 / row 0 (0; -1 in dx-in-N mode)
@@ -203,7 +204,15 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     const int kiters = MODE == MODE_LINEAR ? p.n_chunks : p.n_chunks * (taps / p.tap_group);
     const uint32_t slab_bytes = uint32_t(p.n_tile) * 16u;     // one (tap, 8-channel) weight slab
     const int n_segs = MODE == MODE_LINEAR ? p.n_segs : 1;
-    const int my_tiles = (p.num_m_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // per segment
+    // Work unit = G adjacent tiles (G = 1 outside MODE_LINEAR): unit u of this CTA's j-th turn is
+    // blockIdx.x + j * gridDim.x and covers tiles [u * G, u * G + G); only the globally last unit can be short.
+    const int G = MODE == MODE_LINEAR ? p.m_group : 1;
+    const int num_units = (p.num_m_tiles + G - 1) / G;
+    const int my_units = (num_units - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+    auto unit_of = [&](int j) { return int(blockIdx.x) + j * int(gridDim.x); };
+    auto unit_tiles = [&](int u) { return min(G, p.num_m_tiles - u * G); };
+    auto tile_of = [&](int jt) { return unit_of(jt / G) * G + jt % G; };        // local tile index -> tile
+    const int my_tiles = my_units > 0 ? (my_units - 1) * G + unit_tiles(unit_of(my_units - 1)) : 0;   // per segment
     using R = Roles<MODE>;
 
     // ---------------------------------------------------------------- setup
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         if (p.w_resident && elect_one()) load_resident_weights(0);      // weights are constants: no dependency
         __syncwarp();
         pdl_wait();
-        uint32_t its[2] = {0u, 0u}, tl = 0;
+        uint32_t its[2] = {0u, 0u}, tl = 0, ul = 0;      // ul: units so far (the two issuers take alternate units)
         // double-buffered weights: fetch the next segment's a few tiles into this one (its buffer was
         // last read two segments ago); single buffer: after this segment's last MMA has retired
         const int w_prefetch_at = min(my_tiles - 1, 2 * p.stages * p.rings);
@@ -289,18 +298,19 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             const ChainSeg& sg = p.seg[s];
             const __half* wg = sg.w + size_t(nb) * p.n_tile * 8;
             const int* flags_prev = s > 0 ? p.flags + size_t(s - 1) * p.num_m_tiles : nullptr;
-            int j = 0;
             int ready_upto = flags_prev != nullptr ? 0 : my_tiles;     // local tiles [0, ready_upto) may be loaded
-            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl, ++j) {
-                if (j >= ready_upto) {
+            for (int ju = 0; ju < my_units; ++ju) {
+                const int unit = unit_of(ju), gcount = unit_tiles(unit);
+                const int j = ju * G;                       // first local tile of the unit
+                if (j + gcount > ready_upto) {
                     // Tile t reads output tiles t-1 .. t+1 of the previous segment.  One poll covers this
                     // CTA's next 10 tiles (3 flags each, one per lane): in steady state the neighbours
                     // finished them a whole segment ago, so the L2 round trip is paid once per 10 tiles.
                     uint32_t spins = 0;
                     unsigned long long t0 = 0;
-                    while (j >= ready_upto) {
+                    while (j + gcount > ready_upto) {
                         const int jj = ready_upto + lane / 3;
-                        const int tt = int(blockIdx.x) + jj * int(gridDim.x) - 1 + lane % 3;
+                        const int tt = tile_of(jj) - 1 + lane % 3;
                         const bool need = lane < 30 && jj < my_tiles && tt >= 0 && tt < p.num_m_tiles;
                         const int v = need ? ld_acquire_gpu(flags_prev + tt) : p.flag_expect;
                         const uint32_t ok = __ballot_sync(0xffffffffu, v >= p.flag_expect);
@@ -309,13 +319,16 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                         ready_upto = min(my_tiles, ready_upto + cnt);
                         if ((++spins & 255u) == 0u) {
                             if (t0 == 0) t0 = global_timer_ns();
-                            spin_timeout(-(s * 100000 + tile), t0);
+                            spin_timeout(-(s * 100000 + j), t0);
                         }
                     }
                     fence_proxy_async_all();
                 }
-                const long long q0 = (long long)tile * p.tile_stride + p.tile_origin - p.halo;
-                const uint32_t ring = p.rings == 2 ? (tl & 1u) : 0u;
+                // one contiguous run per plane: the unit's tiles plus ONE halo on each side
+                const long long q0 = (long long)unit * G * p.tile_stride + p.tile_origin - p.halo;
+                const uint32_t copy_bytes = uint32_t(((gcount - 1) * p.tile_stride + kTileM + 2 * p.halo) * 16);
+                const uint32_t ring = p.rings == 2 ? (ul & 1u) : 0u;
+                ++ul;
                 for (int c = 0; c < p.n_chunks; ++c) {
                     const uint32_t it = its[ring]++;
                     const uint32_t slot = ring * p.stages + it % p.stages, ph = (it / p.stages) & 1u;
@@ -323,17 +336,18 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     if (elect_one()) {
                         const uint32_t bar = smem_u32(&hdr->full[slot]);
                         const bool skip_a = (p.debug & 4) != 0;
-                        const uint32_t tx = (skip_a ? 0u : uint32_t(planes_per_chunk) * p.a_copy_bytes) +
+                        const uint32_t tx = (skip_a ? 0u : uint32_t(planes_per_chunk) * copy_bytes) +
                                             (p.w_resident ? 0u : uint32_t(p.w_stage_bytes));
                         mbar_arrive_expect_tx(bar, tx);
                         const uint32_t st = smem_u32(stage0 + size_t(slot) * stage_bytes);
                         const __half* src = sg.in + ((long long)(c * planes_per_chunk) * p.in_plane + q0) * 8;
                         for (int jj = 0; jj < planes_per_chunk && !skip_a; ++jj, src += p.in_plane * 8)
-                            bulk_g2s(st + uint32_t(jj) * p.a_plane_bytes, src, uint32_t(p.a_copy_bytes), bar);
+                            bulk_g2s(st + uint32_t(jj) * p.a_plane_bytes, src, copy_bytes, bar);
                         if (!p.w_resident) load_stage_weights(wg, st + p.a_stage_bytes, bar, 0, taps, c);
                     }
                     __syncwarp();
                 }
+                tl += uint32_t(gcount);
                 if (p.w_resident && p.w_bufs == 2 && s + 1 < n_segs && j == w_prefetch_at) {
                     if (s >= 1) MBAR_WAIT(smem_u32(&hdr->w_free[wbuf_of(s + 1)]), uint32_t(wuse_of(s + 1) - 1) & 1u);
                     if (elect_one()) load_resident_weights(s + 1);
@@ -445,24 +459,32 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             ? ((p.w_resident ? uint32_t(cin8) : uint32_t(planes_per_chunk)) * slab_bytes) >> 4
             : ((p.w_resident ? uint32_t(cin8) : 2u) * slab_bytes) >> 4;
         const bool active = p.rings == 2 || mw == 0u;       // a single ring is served by warp 0
-        uint32_t it = 0, tl = 0;
+        uint32_t it = 0, tl = 0, ul = 0;
         for (int s = 0; s < n_segs; ++s) {
             const uint32_t w_res_u32 = smem_u32(w_res) + uint32_t(wbuf_of(s)) * uint32_t(p.w_res_bytes);
             if (p.w_resident && active) MBAR_WAIT(smem_u32(&hdr->w_ready[wbuf_of(s)]), uint32_t(wuse_of(s)) & 1u);
-            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
-                if (p.rings == 2 ? (tl & 1u) != mw : mw != 0u) continue;   // one ring per issuer
-                const uint32_t buf = tl % nacc;
-                MBAR_WAIT(smem_u32(&hdr->tmem_empty[buf]), ((tl / nacc) & 1u) ^ 1u);
+            for (int ju = 0; ju < my_units; ++ju) {
+                const int gcount = unit_tiles(unit_of(ju));
+                const uint32_t tl0 = tl;
+                tl += uint32_t(gcount);
+                const uint32_t ul0 = ul++;
+                if (p.rings == 2 ? (ul0 & 1u) != mw : mw != 0u) continue;   // one ring per issuer
+                for (int g = 0; g < gcount; ++g) {          // every accumulator of the unit must have been drained
+                    const uint32_t t_ = tl0 + uint32_t(g);
+                    MBAR_WAIT(smem_u32(&hdr->tmem_empty[t_ % nacc]), ((t_ / nacc) & 1u) ^ 1u);
+                }
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * buf_cols;
                 for (int ki = 0; ki < kiters; ++ki, ++it) {
                     const uint32_t slot = (p.rings == 2 ? mw * p.stages : 0u) + it % p.stages, ph = (it / p.stages) & 1u;
                     MBAR_WAIT(smem_u32(&hdr->full[slot]), ph);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_base = smem_u32(stage0) + slot * uint32_t(stage_bytes);
-                        const uint32_t w_stage = a_base + p.a_stage_bytes;
+                        const uint32_t a_base0 = smem_u32(stage0) + slot * uint32_t(stage_bytes);
+                        const uint32_t w_stage = a_base0 + p.a_stage_bytes;
                         const uint32_t acc = ki > 0 ? 1u : 0u;
+                        for (int g = 0; g < gcount; ++g) {
+                        const uint32_t d_tmem = tmem_base + ((tl0 + uint32_t(g)) % nacc) * buf_cols;
+                        const uint32_t a_base = a_base0 + uint32_t(g * p.tile_stride) * 16u;     // tile g of the run
                         if (MODE == MODE_LINEAR) {
                             const uint32_t w0 = p.w_resident ? w_res_u32 + uint32_t(ki * planes_per_chunk) * slab_bytes : w_stage;
                             const uint32_t a_lo = ((a_base + uint32_t(p.halo) * 16u) >> 4) | a_lbo;
@@ -505,8 +527,10 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                                 default: issue_gather<1>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
                             }
                         }
+                        }
                         umma_commit(smem_u32(&hdr->empty[slot]));      // smem slot free once these MMAs retire
-                        if (ki == kiters - 1) umma_commit(smem_u32(&hdr->tmem_full[buf]));   // accumulator complete
+                        if (ki == kiters - 1)                             // accumulators complete
+                            for (int g = 0; g < gcount; ++g) umma_commit(smem_u32(&hdr->tmem_full[(tl0 + uint32_t(g)) % nacc]));
                     }
                     __syncwarp();
                 }
@@ -554,7 +578,6 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
         while (pf_s < n_segs && !seg_has_res(pf_s)) ++pf_s;
         int pf_j = 0, pf_k = k_first(uint32_t(pf_s * my_tiles));
         uint32_t pf_tl = uint32_t(pf_s * my_tiles);
-        long long pf_tile = blockIdx.x;
         const __half* pf_res = pf_s < n_segs ? p.seg[pf_s].res : nullptr;
         uint32_t pf_issued = 0;
         auto prefetch_residual = [&](int cur_seg, uint32_t upto) {      // elected lane: top the ring up to `upto` items
@@ -562,19 +585,17 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 while (pf_k >= items) {         // advance to the next tile (segment) with an item for this half
                     ++pf_j;
                     ++pf_tl;
-                    pf_tile += gridDim.x;
                     if (pf_j >= my_tiles) {
                         do { ++pf_s; } while (pf_s < n_segs && !seg_has_res(pf_s));
                         if (pf_s >= n_segs) { pf_k = 0; pf_s = n_segs; return; }
                         pf_j = 0;
                         pf_tl = uint32_t(pf_s * my_tiles);
-                        pf_tile = blockIdx.x;
                         pf_res = p.seg[pf_s].res;
                     }
                     pf_k = k_first(pf_tl);
                 }
                 if (pf_s >= n_segs || pf_s > cur_seg + 1) return;
-                const long long tile_ = pf_tile;
+                const long long tile_ = tile_of(pf_j);
                 const int item = pf_k;
                 pf_k += 2;
                 const uint32_t slot = pf_issued % rr_n;
@@ -595,7 +616,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     bulk_g2s(dst + uint32_t(pl) * 512u, src, rows * 16u, bar);
             }
         };
-        const uint32_t step = uint32_t(((long long)gridDim.x * p.tile_stride) % HpWp_o);
+        const uint32_t step_in = uint32_t(p.tile_stride % HpWp_o);       // tile -> next tile of the same unit
         const uint32_t magic_w = 0xFFFFFFFFu / uint32_t(Wp_o) + 1u;      // exact floor(n / Wp) for n < 2^16
         uint32_t tl = 0, g = 0;                         // g counts residual items consumed
         int xbuf = 0;                                   // dx-in-N exchange buffer of this half (alternates per item)
@@ -618,7 +639,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             }
             __syncwarp();
             // position of this thread's row inside its crop, advanced incrementally from tile to tile
-            uint32_t rem = uint32_t(((long long)blockIdx.x * p.tile_stride + p.tile_origin + row + HpWp_o) % HpWp_o);
+            uint32_t rem = 0;
             // Completion flags are published in batches: one gpu-scope fence (it waits for the warp's
             // outstanding stores, ~1 us) covers the last kSignalEvery tiles this warp had a share of.
             // Consumers run a whole segment behind, so the delay costs nothing; the segment end flushes.
@@ -630,19 +651,21 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 __syncwarp();
                 const int jl = sig_first + lane;
                 if (jl <= j_last && k_first(tl_seg0 + uint32_t(jl)) < items)
-                    red_relaxed_gpu_add(flags_cur + (int(blockIdx.x) + jl * int(gridDim.x)), 1);
+                    red_relaxed_gpu_add(flags_cur + tile_of(jl), 1);
                 sig_first = j_last + 1;
                 sig_owned = 0;
             };
             int j = -1;
-            for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tl) {
+            for (int ju = 0; ju < my_units; ++ju)
+            for (int g_ = 0, tile = unit_of(ju) * G; g_ < unit_tiles(unit_of(ju)); ++g_, ++tile, ++tl) {
                 ++j;
+                if (g_ == 0) rem = uint32_t(((long long)tile * p.tile_stride + p.tile_origin + row + HpWp_o) % HpWp_o);
                 const uint32_t buf = tl % nacc;
                 const long long qw = (long long)tile * p.tile_stride + p.tile_origin + lg * 32;     // first row of this warp's slice
                 const uint32_t yy = __umulhi(rem, magic_w), xx = rem - yy * uint32_t(Wp_o);
                 const bool interior = qw + lane < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout) &&
                                       !(DXN && (row == 0 || row == kTileM - 1));     // (dx-in-N: the tile's edge rows belong to its neighbours)
-                rem += step;
+                rem += step_in;
                 if (rem >= uint32_t(HpWp_o)) rem -= uint32_t(HpWp_o);
                 const long long left = p.P_out - qw;
                 const uint32_t rows_w = left <= 0 ? 0u : uint32_t(left < 32 ? left : 32);
@@ -888,11 +911,30 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     int budget = 0;         // set per attempt below
     const int w_total = taps * in.C * n_tile * 2;
 
-    if (mode == MODE_LINEAR) {
+    // M grouping: G adjacent tiles of a 3x3 conv are fetched as ONE run per plane, so the (W+3)-pixel halo is
+    // paid once per G tiles (a 128-pixel tile of a 56-wide image reads 246 pixels: 1.9x the data it owns;
+    // four tiles read 630 for 512: 1.23x) and one barrier round trip feeds G tiles.  Each tile keeps its own
+    // accumulator; 2 G accumulators must fit so that the epilogue still overlaps the next unit's MMAs.
+    // Measured at batch 256 (tools/conv_bench.py, POCO_B200_MGROUP=1|2|4): 32->32 @56 36.3 / 47.7 us (no residual /
+    // residual) with G = 2 against 39.8 / 54.4 with G = 1 and 36.9 / 50.3 with G = 4; 64->64 @28 and 128->128 @14
+    // do not gain (their halo is a smaller share and G > 1 leaves them fewer stages), so the default groups
+    // only N <= 32.  POCO_B200_MGROUP=<g> forces up to g everywhere.
+    static const int max_group = [] { const char* e = getenv("POCO_B200_MGROUP"); return e ? atoi(e) : 0; }();
+    int g_first = 1;
+    if (mode == MODE_LINEAR && n_segs == 1 && (taps == 9 || dxn)) {
+        const int cap = max_group > 0 ? max_group : (n_tile <= 32 ? 2 : 1);
+        while (g_first * 2 <= cap && g_first * 4 <= p.acc_bufs) g_first *= 2;
+    }
+    auto set_group = [&](int G) {
+        p.m_group = G;
         p.halo = dxn ? (out.W + 2) : (taps == 9 ? (out.W + 2) + 1 : 0);
-        p.a_copy_bytes = (kTileM + 2 * p.halo) * 16;
+        p.a_copy_bytes = ((G - 1) * p.tile_stride + kTileM + 2 * p.halo) * 16;
         p.a_plane_bytes = round_up(p.a_copy_bytes, 128);
+    };
+    if (mode == MODE_LINEAR) {
+        set_group(g_first);
     } else {
+        p.m_group = 1;
         p.halo = 0;
         p.a_copy_bytes = kTileM * 16;
         p.a_plane_bytes = kTileM * 16;
@@ -903,6 +945,8 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     // other shape the operand stages are the better use of shared memory (measured, profiles/).
     bool found = false;
     p.tap_group = 1;
+    for (int G = p.m_group; G >= 1 && !found; G >>= 1) {
+    if (mode == MODE_LINEAR) set_group(G);
     for (int want4 = (mode == MODE_LINEAR && (dxn || (n_tile >= 64 && taps == 1) || n_tile == 32) ? 1 : 0); want4 >= (dxn ? 1 : 0) && !found; --want4) {
         p.item_planes = want4 ? 4 : 2;
         budget = kSmemBudget - kHeaderBytes - ring_bytes_for(p.item_planes);
@@ -956,6 +1000,7 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
             }
         }
     }
+    }
     POCO_CHECK(found, "no shared-memory configuration fits this convolution");
     // every epilogue warp that owns a share of a tile signals it once (per N block)
     p.n_out = dxn ? out.C : n_tile;
@@ -972,7 +1017,8 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         smem += size_t(p.res_ring - kResRing) * 2 * item_bytes;
     }
     const int sm_budget = d->max_ctas > 0 ? std::min(d->max_ctas, num_sms()) : num_sms();
-    dim3 grid(std::max(1, std::min(p.num_m_tiles, sm_budget / n_blocks)), n_blocks);
+    const int num_units = (p.num_m_tiles + p.m_group - 1) / p.m_group;
+    dim3 grid(std::max(1, std::min(num_units, sm_budget / n_blocks)), n_blocks);
     const ConvTcParams& pk = p;
     static const bool use_pdl = [] { const char* e = getenv("POCO_B200_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg{};
