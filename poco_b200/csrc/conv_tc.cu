@@ -50,7 +50,15 @@ constexpr int kHeaderBytes = 8192;        // barriers + bias + dx-in-N exchange 
 constexpr int kGatherLag = 2;
 constexpr int kPlaneTile = kTileM * 16;            // one output plane of one tile: 2 KB, contiguous in HBM
 constexpr int kOutRing = 0, kResRing = 4, kMaxResRing = 16;     // residual prefetch depth grows into spare smem
-constexpr int ring_bytes_for(int item_planes) { return 2 * (kOutRing + kResRing) * item_planes * kPlaneTile; }   // 8 warps x (out + res ring) x item slice
+// residual ring: 8 warps x depth x item slice; depth 0 = register mode (POCO_B200_RES_RING=0), no ring at all
+// Default: register mode when a warp has at most one item per tile in flight (<= 2 items per tile: the next
+// item's loads have a tile time to land; +2.2 % end to end at batch 256), the ring for wide N (64->256 1x1:
+// four back-to-back items per warp and tile, 265 us with the ring against 300 us without).
+static int res_ring_base(int epi_items) {
+    static const int v = [] { const char* e = getenv("POCO_B200_RES_RING"); return e ? atoi(e) : -1; }();
+    return v >= 0 ? v : (epi_items <= 2 ? 0 : kResRing);
+}
+static int ring_bytes_for(int item_planes, int epi_items) { return 2 * (kOutRing + res_ring_base(epi_items)) * item_planes * kPlaneTile; }
 
 enum { MODE_LINEAR = 0, MODE_GATHER = 1 };
 
@@ -174,6 +182,12 @@ __device__ __forceinline__ void red_relaxed_gpu_add(int* p, int v) {
 }
 // order earlier generic-proxy accesses (here: an acquire of data other threads wrote with st.global)
 // before later async-proxy accesses (bulk copies reading that data)
+// 16-byte load that bypasses L1 (the residual of a chain segment was written earlier by this very kernel)
+__device__ __forceinline__ uint4 ld_global_cg_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -616,6 +630,37 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     bulk_g2s(dst + uint32_t(pl) * 512u, src, rows * 16u, bar);
             }
         };
+        // Register mode (res_ring == 0): the residual slice of the warp's NEXT residual item is loaded straight
+        // into registers (one coalesced 512-byte request per plane) right after the current item's stores; the
+        // cursor is then advanced by every lane (uniform integer math) instead of an elected one.
+        const bool res_ldg = rr_n == 0u;
+        uint4 rres[IPL];
+        bool res_ready = false;
+        auto res_fetch = [&](int cur_seg) -> bool {
+            while (pf_k >= items) {             // advance to the next tile (segment) with an item for this half
+                ++pf_j;
+                ++pf_tl;
+                if (pf_j >= my_tiles) {
+                    do { ++pf_s; } while (pf_s < n_segs && !seg_has_res(pf_s));
+                    if (pf_s >= n_segs) { pf_k = 0; pf_s = n_segs; return false; }
+                    pf_j = 0;
+                    pf_tl = uint32_t(pf_s * my_tiles);
+                    pf_res = p.seg[pf_s].res;
+                }
+                pf_k = k_first(pf_tl);
+            }
+            if (pf_s >= n_segs || pf_s > cur_seg + 1) return false;
+            const long long qw_ = (long long)tile_of(pf_j) * p.tile_stride + p.tile_origin + lg * 32;
+            const int item = pf_k;
+            pf_k += 2;
+            const int planes = min(ipl, (n_out >> 3) - item * ipl);
+            const bool lane_ok = qw_ + lane < p.P_out && qw_ + lane >= 0;
+            const __half* src = pf_res + ((long long)(plane0 + item * ipl) * p.res_plane + qw_ + lane) * 8;
+#pragma unroll
+            for (int pl = 0; pl < IPL; ++pl)
+                rres[pl] = (pl < planes && lane_ok) ? ld_global_cg_v4(src + (long long)pl * p.res_plane * 8) : make_uint4(0, 0, 0, 0);
+            return true;
+        };
         const uint32_t step_in = uint32_t(p.tile_stride % HpWp_o);       // tile -> next tile of the same unit
         const uint32_t magic_w = 0xFFFFFFFFu / uint32_t(Wp_o) + 1u;      // exact floor(n / Wp) for n < 2^16
         uint32_t tl = 0, g = 0;                         // g counts residual items consumed
@@ -633,11 +678,15 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 for (int i = t; i < n_out; i += 256) bias_s[i] = sg.bias[(DXN ? 0 : nb * p.n_tile) + i];
                 named_barrier_sync(1, 256);
             }
-            if (elect_one()) {
-                fence_proxy_async_all();
-                prefetch_residual(s, g + rr_n);
+            if (res_ldg) {
+                if (!res_ready) res_ready = res_fetch(s);
+            } else {
+                if (elect_one()) {
+                    fence_proxy_async_all();
+                    prefetch_residual(s, g + rr_n);
+                }
+                __syncwarp();
             }
-            __syncwarp();
             // position of this thread's row inside its crop, advanced incrementally from tile to tile
             uint32_t rem = 0;
             // Completion flags are published in batches: one gpu-scope fence (it waits for the warp's
@@ -743,8 +792,14 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                             if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
                         }
                     }
-                    const uint32_t rslot = g % rr_n;
-                    if (has_res) MBAR_WAIT(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
+                    const uint32_t rslot = res_ldg ? 0u : g % rr_n;
+                    if (has_res) {
+                        if (res_ldg) {
+                            if (!res_ready) res_ready = res_fetch(s);       // (was gated at prefetch time: load it now)
+                        } else {
+                            MBAR_WAIT(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
+                        }
+                    }
                     __half* outp = sg.out + ((long long)(plane0 + item * ipl) * p.out_plane + qw + lane) * 8;
                     const uint8_t* rb = res_ring + rslot * kSlot + lane * 16;
 #pragma unroll
@@ -761,7 +816,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                             for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
                         }
                         if (has_res) {
-                            const uint4 r4 = *reinterpret_cast<const uint4*>(rb + pl * 512);
+                            const uint4 r4 = res_ldg ? rres[pl] : *reinterpret_cast<const uint4*>(rb + pl * 512);
                             const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -783,9 +838,13 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     }
                     if (has_res) {
                         ++g;
-                        __syncwarp();                       // every lane is done with the residual slot
-                        if (elect_one()) prefetch_residual(s, g + rr_n);
-                        __syncwarp();
+                        if (res_ldg) {
+                            res_ready = res_fetch(s);
+                        } else {
+                            __syncwarp();                   // every lane is done with the residual slot
+                            if (elect_one()) prefetch_residual(s, g + rr_n);
+                            __syncwarp();
+                        }
                     }
                 }
                 if (flags_cur != nullptr && (++sig_owned >= kSignalEvery)) signal_tiles(j);
@@ -949,7 +1008,8 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     if (mode == MODE_LINEAR) set_group(G);
     for (int want4 = (mode == MODE_LINEAR && (dxn || (n_tile >= 64 && taps == 1) || n_tile == 32) ? 1 : 0); want4 >= (dxn ? 1 : 0) && !found; --want4) {
         p.item_planes = want4 ? 4 : 2;
-        budget = kSmemBudget - kHeaderBytes - ring_bytes_for(p.item_planes);
+        const int items_here = ((dxn ? out.C : n_tile) + p.item_planes * 8 - 1) / (p.item_planes * 8);
+        budget = kSmemBudget - kHeaderBytes - ring_bytes_for(p.item_planes, items_here);
         if (mode == MODE_LINEAR) {
             const int kcs[4] = {64, 48, 32, 16};
             // resident weights: a chain double-buffers them when that still leaves >= 2 operand stages
@@ -1008,13 +1068,14 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     p.flag_expect = (p.epi_items >= 2 ? 8 : 4) * n_blocks;
     // slabs are n_tile*16 bytes (a multiple of 256): the resident region needs no padding and
     // w_res_bytes is both the region size and the mbarrier transaction count
-    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes) + size_t(p.w_res_bytes) * p.w_bufs + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
-    p.res_ring = kResRing;
-    if (any_res) {       // spend spare shared memory on a deeper residual prefetch ring
+    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes, p.epi_items) + size_t(p.w_res_bytes) * p.w_bufs + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
+    p.res_ring = res_ring_base(p.epi_items);
+    if (any_res && p.res_ring > 0) {       // spend spare shared memory on a deeper residual prefetch ring
         const int item_bytes = p.item_planes * kPlaneTile;
         const int extra = int((size_t(kSmemBudget) - smem) / (2 * item_bytes));
-        p.res_ring = std::min(kMaxResRing, kResRing + std::max(0, extra));
-        smem += size_t(p.res_ring - kResRing) * 2 * item_bytes;
+        const int base = p.res_ring;
+        p.res_ring = std::min(kMaxResRing, base + std::max(0, extra));
+        smem += size_t(p.res_ring - base) * 2 * item_bytes;
     }
     const int sm_budget = d->max_ctas > 0 ? std::min(d->max_ctas, num_sms()) : num_sms();
     const int num_units = (p.num_m_tiles + p.m_group - 1) / p.m_group;
