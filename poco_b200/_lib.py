@@ -145,8 +145,9 @@ def lib():
         L.poco_plan_num_ops.argtypes = [C.c_void_p]
         L.poco_pare_scratch_floats.restype = C.c_int64
         L.poco_pare_scratch_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32]
-        L.poco_conv_chain_flag_count.restype = C.c_int64
-        L.poco_conv_chain_flag_count.argtypes = [C.POINTER(ConvChain)]
+        if hasattr(L, 'poco_conv_chain_flag_count'):        # (absent only in old builds loaded through POCO_B200_LIB)
+            L.poco_conv_chain_flag_count.restype = C.c_int64
+            L.poco_conv_chain_flag_count.argtypes = [C.POINTER(ConvChain)]
         L.poco_run_op.argtypes = [C.POINTER(Op), C.c_void_p]
         L.poco_plan_create.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p)]
         L.poco_plan_run.argtypes = [C.c_void_p, C.c_void_p]

@@ -51,12 +51,12 @@ constexpr int kGatherLag = 2;
 constexpr int kPlaneTile = kTileM * 16;            // one output plane of one tile: 2 KB, contiguous in HBM
 constexpr int kOutRing = 0, kResRing = 4, kMaxResRing = 16;     // residual prefetch depth grows into spare smem
 // residual ring: 8 warps x depth x item slice; depth 0 = register mode (POCO_B200_RES_RING=0), no ring at all
-// Default: register mode when a warp has at most one item per tile in flight (<= 2 items per tile: the next
-// item's loads have a tile time to land; +2.2 % end to end at batch 256), the ring for wide N (64->256 1x1:
-// four back-to-back items per warp and tile, 265 us with the ring against 300 us without).
-static int res_ring_base(int epi_items) {
-    static const int v = [] { const char* e = getenv("POCO_B200_RES_RING"); return e ? atoi(e) : -1; }();
-    return v >= 0 ? v : (epi_items <= 2 ? 0 : kResRing);
+// (A register-prefetch variant of the residual path -- one coalesced 512-byte load per plane issued an item
+// ahead, no ring -- was measured and removed: carrying both paths cost 30 registers and 5-12 % on every
+// residual conv, and alone it was slower than the ring for 32->32 @56: 49 vs 45.6 us.)
+static int res_ring_base(int) {
+    static const int v = [] { const char* e = getenv("POCO_B200_RES_RING"); return e ? std::max(1, atoi(e)) : kResRing; }();
+    return v;
 }
 static int ring_bytes_for(int item_planes, int epi_items) { return 2 * (kOutRing + res_ring_base(epi_items)) * item_planes * kPlaneTile; }
 
@@ -182,12 +182,6 @@ __device__ __forceinline__ void red_relaxed_gpu_add(int* p, int v) {
 }
 // order earlier generic-proxy accesses (here: an acquire of data other threads wrote with st.global)
 // before later async-proxy accesses (bulk copies reading that data)
-// 16-byte load that bypasses L1 (the residual of a chain segment was written earlier by this very kernel)
-__device__ __forceinline__ uint4 ld_global_cg_v4(const void* p) {
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -220,13 +214,14 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
     const int n_segs = MODE == MODE_LINEAR ? p.n_segs : 1;
     // Work unit = G adjacent tiles (G = 1 outside MODE_LINEAR): unit u of this CTA's j-th turn is
     // blockIdx.x + j * gridDim.x and covers tiles [u * G, u * G + G); only the globally last unit can be short.
-    const int G = MODE == MODE_LINEAR ? p.m_group : 1;
-    const int num_units = (p.num_m_tiles + G - 1) / G;
+    const int G = MODE == MODE_LINEAR ? p.m_group : 1;          // 1, 2 or 4
+    const int g_log2 = G == 4 ? 2 : (G == 2 ? 1 : 0);
+    const int num_units = (p.num_m_tiles + G - 1) >> g_log2;
     const int my_units = (num_units - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
     auto unit_of = [&](int j) { return int(blockIdx.x) + j * int(gridDim.x); };
-    auto unit_tiles = [&](int u) { return min(G, p.num_m_tiles - u * G); };
-    auto tile_of = [&](int jt) { return unit_of(jt / G) * G + jt % G; };        // local tile index -> tile
-    const int my_tiles = my_units > 0 ? (my_units - 1) * G + unit_tiles(unit_of(my_units - 1)) : 0;   // per segment
+    auto unit_tiles = [&](int u) { return min(G, p.num_m_tiles - (u << g_log2)); };
+    auto tile_of = [&](int jt) { return (unit_of(jt >> g_log2) << g_log2) + (jt & (G - 1)); };     // local tile index -> tile (no division)
+    const int my_tiles = my_units > 0 ? ((my_units - 1) << g_log2) + unit_tiles(unit_of(my_units - 1)) : 0;   // per segment
     using R = Roles<MODE>;
 
     // ---------------------------------------------------------------- setup
@@ -473,6 +468,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             ? ((p.w_resident ? uint32_t(cin8) : uint32_t(planes_per_chunk)) * slab_bytes) >> 4
             : ((p.w_resident ? uint32_t(cin8) : 2u) * slab_bytes) >> 4;
         const bool active = p.rings == 2 || mw == 0u;       // a single ring is served by warp 0
+        const uint32_t tile_bytes = uint32_t(p.tile_stride) * 16u;
         uint32_t it = 0, tl = 0, ul = 0;
         for (int s = 0; s < n_segs; ++s) {
             const uint32_t w_res_u32 = smem_u32(w_res) + uint32_t(wbuf_of(s)) * uint32_t(p.w_res_bytes);
@@ -483,9 +479,18 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 tl += uint32_t(gcount);
                 const uint32_t ul0 = ul++;
                 if (p.rings == 2 ? (ul0 & 1u) != mw : mw != 0u) continue;   // one ring per issuer
-                for (int g = 0; g < gcount; ++g) {          // every accumulator of the unit must have been drained
-                    const uint32_t t_ = tl0 + uint32_t(g);
-                    MBAR_WAIT(smem_u32(&hdr->tmem_empty[t_ % nacc]), ((t_ / nacc) & 1u) ^ 1u);
+                // accumulator of every tile of the unit (all must have been drained); computed here, outside the
+                // elected region, so that the MMA descriptors below stay pure uniform-register arithmetic
+                uint32_t dt[4], bufg[4];
+                {
+                    uint32_t b = tl0 % nacc, par = ((tl0 / nacc) & 1u) ^ 1u;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        bufg[g] = b;
+                        dt[g] = tmem_base + b * buf_cols;
+                        if (g < gcount) MBAR_WAIT(smem_u32(&hdr->tmem_empty[b]), par);
+                        if (++b == nacc) { b = 0; par ^= 1u; }
+                    }
                 }
                 tc_fence_after();
                 for (int ki = 0; ki < kiters; ++ki, ++it) {
@@ -496,9 +501,11 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                         const uint32_t a_base0 = smem_u32(stage0) + slot * uint32_t(stage_bytes);
                         const uint32_t w_stage = a_base0 + p.a_stage_bytes;
                         const uint32_t acc = ki > 0 ? 1u : 0u;
-                        for (int g = 0; g < gcount; ++g) {
-                        const uint32_t d_tmem = tmem_base + ((tl0 + uint32_t(g)) % nacc) * buf_cols;
-                        const uint32_t a_base = a_base0 + uint32_t(g * p.tile_stride) * 16u;     // tile g of the run
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                        if (g >= gcount) break;
+                        const uint32_t d_tmem = dt[g];
+                        const uint32_t a_base = a_base0 + uint32_t(g) * tile_bytes;     // tile g of the run
                         if (MODE == MODE_LINEAR) {
                             const uint32_t w0 = p.w_resident ? w_res_u32 + uint32_t(ki * planes_per_chunk) * slab_bytes : w_stage;
                             const uint32_t a_lo = ((a_base + uint32_t(p.halo) * 16u) >> 4) | a_lbo;
@@ -544,7 +551,11 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                         }
                         umma_commit(smem_u32(&hdr->empty[slot]));      // smem slot free once these MMAs retire
                         if (ki == kiters - 1)                             // accumulators complete
-                            for (int g = 0; g < gcount; ++g) umma_commit(smem_u32(&hdr->tmem_full[(tl0 + uint32_t(g)) % nacc]));
+                        {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                if (g < gcount) umma_commit(smem_u32(&hdr->tmem_full[bufg[g]]));
+                        }
                     }
                     __syncwarp();
                 }
@@ -630,38 +641,10 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     bulk_g2s(dst + uint32_t(pl) * 512u, src, rows * 16u, bar);
             }
         };
-        // Register mode (res_ring == 0): the residual slice of the warp's NEXT residual item is loaded straight
-        // into registers (one coalesced 512-byte request per plane) right after the current item's stores; the
-        // cursor is then advanced by every lane (uniform integer math) instead of an elected one.
-        const bool res_ldg = rr_n == 0u;
-        uint4 rres[IPL];
-        bool res_ready = false;
-        auto res_fetch = [&](int cur_seg) -> bool {
-            while (pf_k >= items) {             // advance to the next tile (segment) with an item for this half
-                ++pf_j;
-                ++pf_tl;
-                if (pf_j >= my_tiles) {
-                    do { ++pf_s; } while (pf_s < n_segs && !seg_has_res(pf_s));
-                    if (pf_s >= n_segs) { pf_k = 0; pf_s = n_segs; return false; }
-                    pf_j = 0;
-                    pf_tl = uint32_t(pf_s * my_tiles);
-                    pf_res = p.seg[pf_s].res;
-                }
-                pf_k = k_first(pf_tl);
-            }
-            if (pf_s >= n_segs || pf_s > cur_seg + 1) return false;
-            const long long qw_ = (long long)tile_of(pf_j) * p.tile_stride + p.tile_origin + lg * 32;
-            const int item = pf_k;
-            pf_k += 2;
-            const int planes = min(ipl, (n_out >> 3) - item * ipl);
-            const bool lane_ok = qw_ + lane < p.P_out && qw_ + lane >= 0;
-            const __half* src = pf_res + ((long long)(plane0 + item * ipl) * p.res_plane + qw_ + lane) * 8;
-#pragma unroll
-            for (int pl = 0; pl < IPL; ++pl)
-                rres[pl] = (pl < planes && lane_ok) ? ld_global_cg_v4(src + (long long)pl * p.res_plane * 8) : make_uint4(0, 0, 0, 0);
-            return true;
-        };
-        const uint32_t step_in = uint32_t(p.tile_stride % HpWp_o);       // tile -> next tile of the same unit
+        // position of a row inside its crop, advanced incrementally: tile -> next tile of the unit, and last
+        // tile of a unit -> first tile of this CTA's next unit (only the globally last unit can be short)
+        const uint32_t step_in = uint32_t(p.tile_stride % HpWp_o);
+        const uint32_t step_unit = uint32_t((((long long)gridDim.x * G - (G - 1)) * p.tile_stride) % HpWp_o);
         const uint32_t magic_w = 0xFFFFFFFFu / uint32_t(Wp_o) + 1u;      // exact floor(n / Wp) for n < 2^16
         uint32_t tl = 0, g = 0;                         // g counts residual items consumed
         int xbuf = 0;                                   // dx-in-N exchange buffer of this half (alternates per item)
@@ -678,17 +661,13 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                 for (int i = t; i < n_out; i += 256) bias_s[i] = sg.bias[(DXN ? 0 : nb * p.n_tile) + i];
                 named_barrier_sync(1, 256);
             }
-            if (res_ldg) {
-                if (!res_ready) res_ready = res_fetch(s);
-            } else {
-                if (elect_one()) {
-                    fence_proxy_async_all();
-                    prefetch_residual(s, g + rr_n);
-                }
-                __syncwarp();
+            if (elect_one()) {
+                fence_proxy_async_all();
+                prefetch_residual(s, g + rr_n);
             }
+            __syncwarp();
             // position of this thread's row inside its crop, advanced incrementally from tile to tile
-            uint32_t rem = 0;
+            uint32_t rem = uint32_t((((long long)blockIdx.x << g_log2) * p.tile_stride + p.tile_origin + row + HpWp_o) % HpWp_o);
             // Completion flags are published in batches: one gpu-scope fence (it waits for the warp's
             // outstanding stores, ~1 us) covers the last kSignalEvery tiles this warp had a share of.
             // Consumers run a whole segment behind, so the delay costs nothing; the segment end flushes.
@@ -708,13 +687,12 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
             for (int ju = 0; ju < my_units; ++ju)
             for (int g_ = 0, tile = unit_of(ju) * G; g_ < unit_tiles(unit_of(ju)); ++g_, ++tile, ++tl) {
                 ++j;
-                if (g_ == 0) rem = uint32_t(((long long)tile * p.tile_stride + p.tile_origin + row + HpWp_o) % HpWp_o);
                 const uint32_t buf = tl % nacc;
                 const long long qw = (long long)tile * p.tile_stride + p.tile_origin + lg * 32;     // first row of this warp's slice
                 const uint32_t yy = __umulhi(rem, magic_w), xx = rem - yy * uint32_t(Wp_o);
                 const bool interior = qw + lane < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout) &&
                                       !(DXN && (row == 0 || row == kTileM - 1));     // (dx-in-N: the tile's edge rows belong to its neighbours)
-                rem += step_in;
+                rem += (g_ + 1 == G) ? step_unit : step_in;
                 if (rem >= uint32_t(HpWp_o)) rem -= uint32_t(HpWp_o);
                 const long long left = p.P_out - qw;
                 const uint32_t rows_w = left <= 0 ? 0u : uint32_t(left < 32 ? left : 32);
@@ -792,14 +770,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                             if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
                         }
                     }
-                    const uint32_t rslot = res_ldg ? 0u : g % rr_n;
-                    if (has_res) {
-                        if (res_ldg) {
-                            if (!res_ready) res_ready = res_fetch(s);       // (was gated at prefetch time: load it now)
-                        } else {
-                            MBAR_WAIT(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
-                        }
-                    }
+                    const uint32_t rslot = g % rr_n;
+                    if (has_res) MBAR_WAIT(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
                     __half* outp = sg.out + ((long long)(plane0 + item * ipl) * p.out_plane + qw + lane) * 8;
                     const uint8_t* rb = res_ring + rslot * kSlot + lane * 16;
 #pragma unroll
@@ -816,7 +788,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                             for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
                         }
                         if (has_res) {
-                            const uint4 r4 = res_ldg ? rres[pl] : *reinterpret_cast<const uint4*>(rb + pl * 512);
+                            const uint4 r4 = *reinterpret_cast<const uint4*>(rb + pl * 512);
                             const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -838,13 +810,9 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const
                     }
                     if (has_res) {
                         ++g;
-                        if (res_ldg) {
-                            res_ready = res_fetch(s);
-                        } else {
-                            __syncwarp();                   // every lane is done with the residual slot
-                            if (elect_one()) prefetch_residual(s, g + rr_n);
-                            __syncwarp();
-                        }
+                        __syncwarp();                       // every lane is done with the residual slot
+                        if (elect_one()) prefetch_residual(s, g + rr_n);
+                        __syncwarp();
                     }
                 }
                 if (flags_cur != nullptr && (++sig_owned >= kSignalEvery)) signal_tiles(j);
