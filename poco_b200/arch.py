@@ -113,13 +113,26 @@ class SpecBackend:
 
 def conv_cost(N, cin, cout, k, Hout, Wout):
     """relative SM-cycles of one conv launch, used only to split the SMs between concurrent lanes.
-    tiles x MMAs x effective cycles per MMA, calibrated on measured per-tile times at batch 256
-    (profiles/r01_ops_b256_v7*.csv): ~105 clk for N <= 64 (issue floor 77 + epilogue exposure), ~170 at
-    N = 128 and ~260 at N = 256 when the weights are re-streamed from L2 for every tile."""
+    tiles x MMAs x effective cycles per MMA + a fixed launch cost; the per-MMA constants (N <= 32, N = 64,
+    N = 128, N = 256 with weights re-streamed from L2 per tile) were calibrated on per-tile times at batch 256.
+    Re-weighting them from the measured lane end times of the HR modules (tools/region_times.py: in eager replay
+    the 256-channel lane of a stage-4 module ends at 1.00 ms, the 32-channel one at 0.73 ms) did NOT improve the
+    captured-graph step (A/B: 20.18 k vs 20.13-20.19 k crops/s, more aggressive weights 19.3-19.7 k), so they
+    stay.  POCO_B200_COST="c32,c64,c128,c256" overrides them."""
+    import os
+    env = os.environ.get('POCO_B200_COST')
+    c32, c64, c128, c256 = [float(v) for v in env.split(',')] if env else (105.0, 105.0, 170.0, 260.0)
     tiles = -(-N * (Hout + 2) * (Wout + 2) // 128)
     n_tile = min(cout, 256)
     streamed = k * k * cin * n_tile * 2 > 112 * 1024
-    cyc = 105 if n_tile <= 64 else ((170 if streamed else 110) if n_tile <= 128 else (260 if streamed else 160))
+    if n_tile <= 32:
+        cyc = c32
+    elif n_tile <= 64:
+        cyc = c64
+    elif n_tile <= 128:
+        cyc = c128 if streamed else 0.6 * c128
+    else:
+        cyc = c256 if streamed else 0.5 * c256
     return tiles * (k * k * -(-cin // 16)) * -(-cout // n_tile) * cyc + 1500000
 
 

@@ -30,18 +30,23 @@ def replay(marks):
         if op.kind == L.OP_FORK:
             e = torch.cuda.Event(enable_timing=True)
             e.record(main)
-            marks.append((i, 'fork', e))
+            marks.append((i, 'fork', e, None))
             for k in range(1, op.u.sync.n_lanes):
                 sides[k].wait_event(e)
             continue
         if op.kind == L.OP_JOIN:
+            lane_ends = []
+            e0_ = torch.cuda.Event(enable_timing=True)
+            e0_.record(main)
+            lane_ends.append(e0_)
             for k in range(1, op.u.sync.n_lanes):
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=True)
                 ev.record(sides[k])
                 main.wait_event(ev)
+                lane_ends.append(ev)
             e = torch.cuda.Event(enable_timing=True)
             e.record(main)
-            marks.append((i, 'join', e))
+            marks.append((i, 'join', e, lane_ends))
             continue
         s = main if op.lane == 0 else sides[op.lane]
         L.run_op(op, s.cuda_stream)
@@ -59,7 +64,7 @@ e1.record(main)
 torch.cuda.synchronize()
 print(f'total {e0.elapsed_time(e1):.3f} ms  ({len(ops)} ops)')
 prev, prev_i, prev_kind = e0, 0, 'start'
-for i, kind, e in marks + [(len(ops), 'end', e1)]:
+for i, kind, e, lane_ends in marks + [(len(ops), 'end', e1, None)]:
     n = sum(1 for o in ops[prev_i:i] if o.kind not in (L.OP_FORK, L.OP_JOIN))
     what = 'lanes' if prev_kind == 'fork' else 'serial'
     labels = {}
@@ -69,5 +74,8 @@ for i, kind, e in marks + [(len(ops), 'end', e1)]:
         lab = bench.op_label(o)
         labels[lab] = labels.get(lab, 0) + 1
     top = ', '.join(f'{v}x {k}' for k, v in sorted(labels.items(), key=lambda kv: -kv[1])[:4])
-    print(f'ops {prev_i:4d}-{i:4d} {what:6s} {n:3d} ops {prev.elapsed_time(e):8.3f} ms   {top}')
+    lanes_txt = ''
+    if lane_ends:
+        lanes_txt = '  lanes end at ' + ' '.join(f'{prev.elapsed_time(le):.3f}' for le in lane_ends)
+    print(f'ops {prev_i:4d}-{i:4d} {what:6s} {n:3d} ops {prev.elapsed_time(e):8.3f} ms   {top}{lanes_txt}')
     prev, prev_i, prev_kind = e, i, kind
