@@ -46,6 +46,7 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxAccBufs = 8;                     // TMEM accumulator ring (512 columns / n_tile)
 constexpr int kTileM = 128;
 constexpr int kSmemBudget = 225 * 1024;   // of 227 KB usable per CTA
+constexpr int kSmemBudgetHalf = 110 * 1024;       // two CTAs per SM (small-N layers, see conv_tc_launch_chain)
 constexpr int kHeaderBytes = 8192;        // barriers + bias + dx-in-N exchange buffers
 constexpr int kGatherLag = 2;
 constexpr int kPlaneTile = kTileM * 16;            // one output plane of one tile: 2 KB, contiguous in HBM
@@ -54,11 +55,11 @@ constexpr int kOutRing = 0, kResRing = 4, kMaxResRing = 16;     // residual pref
 // (A register-prefetch variant of the residual path -- one coalesced 512-byte load per plane issued an item
 // ahead, no ring -- was measured and removed: carrying both paths cost 30 registers and 5-12 % on every
 // residual conv, and alone it was slower than the ring for 32->32 @56: 49 vs 45.6 us.)
-static int res_ring_base(int) {
+static int res_ring_base(bool half) {
     static const int v = [] { const char* e = getenv("POCO_B200_RES_RING"); return e ? std::max(1, atoi(e)) : kResRing; }();
-    return v;
+    return half ? std::min(v, 2) : v;
 }
-static int ring_bytes_for(int item_planes, int epi_items) { return 2 * (kOutRing + res_ring_base(epi_items)) * item_planes * kPlaneTile; }
+static int ring_bytes_for(int item_planes, bool half) { return 2 * (kOutRing + res_ring_base(half)) * item_planes * kPlaneTile; }
 
 enum { MODE_LINEAR = 0, MODE_GATHER = 1 };
 
@@ -192,8 +193,10 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // then holds D_s[p] = sum_{r,c} in[p + (r-1) Wp][c] W[r][s][c] and the epilogue forms
 // out[q] = D_0[q-1] + D_1[q] + D_2[q+1] with warp shuffles (+ a 2 x 32-float exchange between the four warps
 // of a tile); tiles advance by 126 pixels so that rows 0 and 127 of a tile are never outputs.
-template <int MODE, int IPL, bool DXN>
-__global__ void __launch_bounds__(Roles<MODE>::kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
+// MINB = 2: the "half" configuration (two CTAs per SM), which needs the register cap of __launch_bounds__(.., 2);
+// the one-CTA instantiations keep their registers (capping them cost the wide-N epilogue 20 %).
+template <int MODE, int IPL, bool DXN, int MINB = 1>
+__global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
     const int res_ring_n = p.res_ring;
@@ -923,8 +926,24 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     const int n_blocks = dxn ? 1 : out.C / n_tile;
     int cols = 32;                      // accumulator buffer pitch: power of two >= n_tile
     while (cols < n_tile) cols <<= 1;
-    p.acc_bufs = std::min(kMaxAccBufs, 512 / cols);      // the MMA warp may run this many tiles ahead of the epilogue
-    p.tmem_cols = cols * p.acc_bufs;
+    // Two CTAs per SM ("half" configuration: <= 110 KB of shared memory, <= 256 TMEM columns) for the layers with
+    // N <= 64: measured on one box against the one-CTA configuration, 32->32 @56 33.6 -> 30.3 us (no residual) and
+    // 42.6 -> 40.0 us (residual), 64->64 @28 29.5 -> 27.2 us -- two independent producer / issuer / epilogue sets
+    // hide each other's barrier round trips, and a finishing CTA's slot is refilled while its neighbour still
+    // computes.  POCO_B200_HALF=0 disables it.
+    // Only outside plan lanes (max_ctas == 0): a lane's half-size CTAs would spread one per SM and leave the
+    // other lanes' full-size CTAs no empty SM (A/B inside the HR modules: 19.5 k vs 19.8 k crops/s).
+    static const int half_mode = [] { const char* e = getenv("POCO_B200_HALF"); return e ? atoi(e) : 1; }();   // 0 off, 1 outside lanes, 2 always
+    const bool half_stride1 = d->stride == 1 && in.H == out.H && in.W == out.W && d->kh == 3 && d->pad == 1;
+    bool half = half_mode > 0 && (half_mode == 2 || d->max_ctas == 0) && !dxn && n_segs == 1 && n_tile <= 64 && half_stride1;
+    int smem_budget = kSmemBudget;
+    auto set_half = [&](bool h) {
+        half = h;
+        smem_budget = h ? kSmemBudgetHalf : kSmemBudget;
+        p.acc_bufs = std::max(1, std::min(kMaxAccBufs, (h ? 256 : 512) / cols));      // the MMA warp may run this many tiles ahead of the epilogue
+        p.tmem_cols = cols * p.acc_bufs;
+    };
+    set_half(half);
 
     const int taps = dxn ? 3 : d->kh * d->kw;       // taps the MMA loop walks
     p.taps = taps;
@@ -972,12 +991,15 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     // other shape the operand stages are the better use of shared memory (measured, profiles/).
     bool found = false;
     p.tap_group = 1;
-    for (int G = p.m_group; G >= 1 && !found; G >>= 1) {
+    for (int attempt = half ? 0 : 1; attempt < 2 && !found; ++attempt) {       // the half configuration first, when eligible
+    set_half(attempt == 0);
+    for (int G = std::min(p.acc_bufs >= 4 ? g_first : 1, g_first); G >= 1 && !found; G >>= 1) {
     if (mode == MODE_LINEAR) set_group(G);
     for (int want4 = (mode == MODE_LINEAR && (dxn || (n_tile >= 64 && taps == 1) || n_tile == 32) ? 1 : 0); want4 >= (dxn ? 1 : 0) && !found; --want4) {
         p.item_planes = want4 ? 4 : 2;
         const int items_here = ((dxn ? out.C : n_tile) + p.item_planes * 8 - 1) / (p.item_planes * 8);
-        budget = kSmemBudget - kHeaderBytes - ring_bytes_for(p.item_planes, items_here);
+        budget = smem_budget - kHeaderBytes - ring_bytes_for(p.item_planes, half);
+        (void)items_here;
         if (mode == MODE_LINEAR) {
             const int kcs[4] = {64, 48, 32, 16};
             // resident weights: a chain double-buffers them when that still leaves >= 2 operand stages
@@ -1029,6 +1051,7 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         }
     }
     }
+    }
     POCO_CHECK(found, "no shared-memory configuration fits this convolution");
     // every epilogue warp that owns a share of a tile signals it once (per N block)
     p.n_out = dxn ? out.C : n_tile;
@@ -1036,20 +1059,23 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     p.flag_expect = (p.epi_items >= 2 ? 8 : 4) * n_blocks;
     // slabs are n_tile*16 bytes (a multiple of 256): the resident region needs no padding and
     // w_res_bytes is both the region size and the mbarrier transaction count
-    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes, p.epi_items) + size_t(p.w_res_bytes) * p.w_bufs + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
-    p.res_ring = res_ring_base(p.epi_items);
+    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes, half) + size_t(p.w_res_bytes) * p.w_bufs + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
+    p.res_ring = res_ring_base(half);
     if (any_res && p.res_ring > 0) {       // spend spare shared memory on a deeper residual prefetch ring
         const int item_bytes = p.item_planes * kPlaneTile;
-        const int extra = int((size_t(kSmemBudget) - smem) / (2 * item_bytes));
+        const int extra = int((size_t(smem_budget) - smem) / (2 * item_bytes));
         const int base = p.res_ring;
         p.res_ring = std::min(kMaxResRing, base + std::max(0, extra));
         smem += size_t(p.res_ring - base) * 2 * item_bytes;
     }
-    const int sm_budget = d->max_ctas > 0 ? std::min(d->max_ctas, num_sms()) : num_sms();
+    const int sm_budget = (half ? 2 : 1) * (d->max_ctas > 0 ? std::min(d->max_ctas, num_sms()) : num_sms());
     const int num_units = (p.num_m_tiles + p.m_group - 1) / p.m_group;
     dim3 grid(std::max(1, std::min(num_units, sm_budget / n_blocks)), n_blocks);
     const ConvTcParams& pk = p;
-    static const bool use_pdl = [] { const char* e = getenv("POCO_B200_PDL"); return !(e && e[0] == '0'); }();
+    // Programmatic dependent launch is opt-in (POCO_B200_PDL=1): one-CTA-per-SM kernels leave the dependent grid no
+    // room to start early, and its CTAs parked in griddepcontrol.wait cost 1.7 % end to end (A/B: 20.0 k with,
+    // 20.4 k crops/s without).
+    static const bool use_pdl = [] { const char* e = getenv("POCO_B200_PDL"); return e && e[0] == '1'; }();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.dynamicSmemBytes = smem;
@@ -1064,8 +1090,12 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         cfg.blockDim = dim3(threads);
         return cudaLaunchKernelEx(&cfg, kernel, pk);
     };
-    static std::once_flag once4[5];
-    if (dxn)
+    static std::once_flag once4[7];
+    if (half && p.item_planes == 2)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 2>, once4[5], Roles<MODE_LINEAR>::kThreads));
+    else if (half)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false, 2>, once4[6], Roles<MODE_LINEAR>::kThreads));
+    else if (dxn)
         POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, true>, once4[4], Roles<MODE_LINEAR>::kThreads));
     else if (mode == MODE_LINEAR && p.item_planes == 2)
         POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false>, once4[0], Roles<MODE_LINEAR>::kThreads));

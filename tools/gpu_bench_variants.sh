@@ -1,7 +1,7 @@
 #!/bin/bash
 # bench.py under several env configurations (one line each)
 mkdir -p gpurun_out
-run() { echo "== $1"; env $1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_var.err | python -c "
+run() { echo "== $1"; env $1 timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_var.err | python -c "
 import sys, json
 for l in sys.stdin:
     l = l.strip()
