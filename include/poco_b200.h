@@ -128,6 +128,8 @@ typedef struct poco_linear {
     int64_t ldy;
     int32_t M, I, O;
     int32_t act;
+    float* scratch;          /* optional split-K workspace (or NULL): partial sums [splits][M][O] */
+    int64_t scratch_floats;  /* its capacity; the library picks splits <= scratch_floats / (M*O) */
 } poco_linear;
 
 /* dst[r, c] = src[(bcast ? 0 : r), c]  (torch.cat / .expand plumbing of cliff_head.py:85-101) */

@@ -61,7 +61,8 @@ class Unpack(C.Structure):
 class Linear(C.Structure):
     _fields_ = [('x', C.c_void_p), ('ldx', C.c_int64), ('w', C.c_void_p), ('b', C.c_void_p),
                 ('res', C.c_void_p), ('ldres', C.c_int64), ('y', C.c_void_p), ('ldy', C.c_int64),
-                ('M', C.c_int32), ('I', C.c_int32), ('O', C.c_int32), ('act', C.c_int32)]
+                ('M', C.c_int32), ('I', C.c_int32), ('O', C.c_int32), ('act', C.c_int32),
+                ('scratch', C.c_void_p), ('scratch_floats', C.c_int64)]
 
 
 class Copy2d(C.Structure):

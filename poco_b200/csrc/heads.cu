@@ -17,11 +17,14 @@ constexpr int LBM = 32, LBN = 32, LBK = 32;
 
 // 32x32 output tile, K step 32, 256 threads (2x2 outputs each); the next K tile is prefetched into
 // registers while the current one is multiplied, so a CTA has two tiles of loads in flight.
-__global__ void __launch_bounds__(256) linear_kernel(poco_linear d) {
+// blockIdx.z = K split: with `splits` > 1 every CTA multiplies one K range and writes its partial sums to
+// d.scratch [split][M][O]; linear_reduce_kernel then adds them up and applies bias / activation / residual.
+__global__ void __launch_bounds__(256) linear_kernel(poco_linear d, int splits, int k_per_split) {
     __shared__ float xs[LBK][LBM + 1];
     __shared__ float ws[LBK][LBN + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // tx -> O, ty -> M
     const int m0 = blockIdx.y * LBM, o0 = blockIdx.x * LBN;
+    const int k_begin = blockIdx.z * k_per_split, k_end = min(d.I, k_begin + k_per_split);
     // each thread stages 4 x elements and 4 w elements per K tile: element e = threadIdx.x + 256*i
     const int lk = threadIdx.x & 31, lr = threadIdx.x >> 5;     // k within tile, row group (8 groups x 4 rows)
     float px[4], pw[4];
@@ -29,20 +32,20 @@ __global__ void __launch_bounds__(256) linear_kernel(poco_linear d) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = lr + 8 * i, k = k0 + lk;
-            px[i] = (m0 + r < d.M && k < d.I) ? d.x[(long long)(m0 + r) * d.ldx + k] : 0.f;
-            pw[i] = (o0 + r < d.O && k < d.I) ? d.w[(long long)(o0 + r) * d.I + k] : 0.f;
+            px[i] = (m0 + r < d.M && k < k_end) ? d.x[(long long)(m0 + r) * d.ldx + k] : 0.f;
+            pw[i] = (o0 + r < d.O && k < k_end) ? d.w[(long long)(o0 + r) * d.I + k] : 0.f;
         }
     };
     float acc[2][2] = {};
-    fetch(0);
-    for (int k0 = 0; k0 < d.I; k0 += LBK) {
+    fetch(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += LBK) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             xs[lk][lr + 8 * i] = px[i];
             ws[lk][lr + 8 * i] = pw[i];
         }
         __syncthreads();
-        if (k0 + LBK < d.I) fetch(k0 + LBK);
+        if (k0 + LBK < k_end) fetch(k0 + LBK);
 #pragma unroll
         for (int k = 0; k < LBK; ++k) {
             const float a0 = xs[k][ty], a1 = xs[k][ty + 16];
@@ -60,6 +63,10 @@ __global__ void __launch_bounds__(256) linear_kernel(poco_linear d) {
         for (int j = 0; j < 2; ++j) {
             const int m = m0 + ty + 16 * i, o = o0 + tx + 16 * j;
             if (m < d.M && o < d.O) {
+                if (splits > 1) {
+                    d.scratch[((long long)blockIdx.z * d.M + m) * d.O + o] = acc[i][j];
+                    continue;
+                }
                 float v = acc[i][j] + (d.b ? d.b[o] : 0.f);
                 if (d.act == 1) v = 1.f / (1.f + expf(-v));
                 else if (d.act == 2) v = v > 20.f ? v : log1pf(expf(v));      // nn.Softplus (beta=1, threshold=20)
@@ -67,6 +74,18 @@ __global__ void __launch_bounds__(256) linear_kernel(poco_linear d) {
                 d.y[(long long)m * d.ldy + o] = v;
             }
         }
+}
+
+__global__ void __launch_bounds__(256) linear_reduce_kernel(poco_linear d, int splits) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= d.M * d.O) return;
+    const int m = idx / d.O, o = idx - m * d.O;
+    float v = d.b ? d.b[o] : 0.f;
+    for (int s = 0; s < splits; ++s) v += d.scratch[((long long)s * d.M + m) * d.O + o];
+    if (d.act == 1) v = 1.f / (1.f + expf(-v));
+    else if (d.act == 2) v = v > 20.f ? v : log1pf(expf(v));
+    if (d.res) v += d.res[(long long)m * d.ldres + o];
+    d.y[(long long)m * d.ldy + o] = v;
 }
 
 __global__ void copy2d_kernel(poco_copy2d d) {
@@ -414,8 +433,22 @@ extern "C" int poco_linear_run(const poco_linear* d, void* stream) {
     POCO_CHECK(d->M > 0 && d->I > 0 && d->O > 0, "empty problem");
     POCO_CHECK(d->ldx >= d->I && d->ldy >= d->O && (!d->res || d->ldres >= d->O), "leading dimension too small");
     dim3 grid((d->O + LBN - 1) / LBN, (d->M + LBM - 1) / LBM);
-    linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*d);
+    // split K when the output tiles alone cannot fill the GPU: aim at ~4 CTAs per SM, >= 4 K tiles per split
+    int splits = 1;
+    if (d->scratch != nullptr) {
+        const int ctas = int(grid.x * grid.y), ktiles = (d->I + LBK - 1) / LBK;
+        splits = std::max(1, std::min(std::min(592 / std::max(1, ctas), ktiles / 4), 8));
+        splits = int(std::min<int64_t>(splits, d->scratch_floats / (int64_t(d->M) * d->O)));
+        if (splits < 2) splits = 1;
+    }
+    const int k_per_split = ((d->I + splits - 1) / splits + LBK - 1) / LBK * LBK;
+    grid.z = splits;
+    linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, splits, k_per_split);
     POCO_LAUNCHED();
+    if (splits > 1) {
+        linear_reduce_kernel<<<(d->M * d->O + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, splits);
+        POCO_LAUNCHED();
+    }
     return 0;
 }
 

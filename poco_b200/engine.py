@@ -396,10 +396,16 @@ class PlanBuilder:
         w, b = self.dev(w), self.dev(b)
         O = w.shape[0]
         assert w.shape[1] == I, (tuple(w.shape), I)
+        # one split-K workspace for all linear ops of the plan (they run one after the other on the main lane)
+        need = 8 * x.shape[0] * O
+        if getattr(self, '_lin_scratch', None) is None or self._lin_scratch.numel() < need:
+            self._lin_scratch = torch.empty(max(need, 8 * x.shape[0] * 1024), dtype=torch.float32, device=self.device)
+            self.keep.append(self._lin_scratch)
         self.add(L.Linear(x.data_ptr() + 4 * xcol, x.stride(0), w.data_ptr(), b.data_ptr(),
                           (res.data_ptr() + 4 * rescol) if res is not None else None,
                           res.stride(0) if res is not None else 0,
-                          y.data_ptr() + 4 * ycol, y.stride(0), x.shape[0], I, O, act))
+                          y.data_ptr() + 4 * ycol, y.stride(0), x.shape[0], I, O, act,
+                          self._lin_scratch.data_ptr(), self._lin_scratch.numel()))
 
     def copy2d(self, src, scol, dst, dcol, cols, bcast=False):
         self.add(L.Copy2d(src.data_ptr() + 4 * scol, src.stride(0), dst.data_ptr() + 4 * dcol, dst.stride(0),

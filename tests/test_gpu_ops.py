@@ -150,6 +150,14 @@ def test_linear(M, I, O, act):
     y = torch.zeros(M, O + 3, device='cuda')
     L.run_op(L.Linear(xd.data_ptr(), I, wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), O, y.data_ptr() + 4, O + 3, M, I, O, act), stream())
     sync_or_die()
+    # the same problem with a split-K workspace (several CTAs per output tile + reduce kernel)
+    y2 = torch.zeros(M, O + 3, device='cuda')
+    scratch = torch.empty(8 * M * O, device='cuda')
+    L.run_op(L.Linear(xd.data_ptr(), I, wd.data_ptr(), bd.data_ptr(), rd.data_ptr(), O, y2.data_ptr() + 4, O + 3, M, I, O, act,
+                      scratch.data_ptr(), scratch.numel()), stream())
+    sync_or_die()
+    assert rel_err(y2[:, 1:O + 1].cpu().numpy(), y[:, 1:O + 1].cpu().numpy()) < 1e-5
+    assert y2[:, 0].abs().sum() == 0 and y2[:, O + 1:].abs().sum() == 0
     ref = x.double() @ w.double().t() + b.double()
     ref = torch.sigmoid(ref) if act == 1 else (F.softplus(ref) if act == 2 else ref)
     ref = ref + r.double()
