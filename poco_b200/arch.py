@@ -184,7 +184,7 @@ def chain_policy(channels):
     return channels >= int(os.environ.get('POCO_B200_CHAIN_MIN_C', '100000'))
 
 
-def hr_module(b, xs, name, chans):
+def hr_module(b, xs, name, chans, out0=None):
     """HighResolutionModule: 4 BasicBlocks per branch, then the multi-resolution fuse
     (hrnet.py:188-266).  Inputs are consumed (freed).  The branches, and afterwards the per-output
     fuse chains, are independent: they are emitted as concurrent plan lanes, each with a share of the
@@ -231,7 +231,7 @@ def hr_module(b, xs, name, chans):
                           chans[j], chans[i], 1, relu=False)
             ups.append((z, j - i))
         if i == 0:
-            o = b.fuse_sum([(xs[0], 0)] + ups, relu=True)
+            o = b.fuse_sum([(xs[0], 0)] + ups, relu=True, out=out0)        # (out0: the caller's buffer slice)
         else:
             acc = b.fuse_sum([(xs[i], 0)] + ups, relu=False) if ups else xs[i]
             for j in range(i):          # stride-2 conv chains; the running sum rides on the residual input
@@ -258,7 +258,9 @@ def hr_module(b, xs, name, chans):
     return outs
 
 
-def hrnet_trunk(b, img, widths, H=224, W=224, prefix='backbone.'):
+def hrnet_trunk(b, img, widths, H=224, W=224, prefix='backbone.', final_out0=None):
+    """final_out0(H, W) -> activation slice the LAST module writes its branch-0 output into (hrnet_pose: the
+    first 32 channels of the 480-channel feature buffer, which saves a copy kernel)"""
     p = prefix
     y = b.stem_conv(img, H, W, p + 'conv1', p + 'bn1', 64)
     x = b.conv_bn(y, p + 'conv2', p + 'bn2', 64, 64, 3, 2)
@@ -277,7 +279,9 @@ def hrnet_trunk(b, img, widths, H=224, W=224, prefix='backbone.'):
                         widths[nbr - 2], widths[nbr - 1], 3, 2)
         ys = ys + [new]
         for m in range(n_modules[st]):
-            ys = hr_module(b, ys, f'{p}stage{st}.{m}', widths[:nbr])
+            last = st == 4 and m == n_modules[st] - 1 and final_out0 is not None
+            ys = hr_module(b, ys, f'{p}stage{st}.{m}', widths[:nbr],
+                           out0=final_out0(ys[0].H, ys[0].W) if last else None)
     return ys
 
 
@@ -285,12 +289,14 @@ def hrnet_pose(b, img, width=32, prefix='backbone.'):
     """PoseHighResolutionNet with use_conv=True / downsample=False -> [N, 15*width, 56, 56]
     (hrnet.py:466-528).  Each branch lands in its channel slice of one buffer, so torch.cat is free."""
     widths = [width, 2 * width, 4 * width, 8 * width]
-    ys = hrnet_trunk(b, img, widths, prefix=prefix)
-    feats = b.act(sum(widths), ys[0].H, ys[0].W)
-    c0 = 0
-    b.fuse_sum([(ys[0], 0)], relu=False, out=feats.channels(0, widths[0]))
-    b.free(ys[0])
-    c0 += widths[0]
+    holder = {}
+
+    def out0(H, W):
+        holder['feats'] = b.act(sum(widths), H, W)
+        return holder['feats'].channels(0, widths[0])
+    ys = hrnet_trunk(b, img, widths, prefix=prefix, final_out0=out0)
+    feats = holder['feats']             # branch 0 of the last module already landed in its first channels
+    c0 = widths[0]
     for br in range(1, 4):
         t = ys[br]
         for k in range(br):

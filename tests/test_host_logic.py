@@ -137,3 +137,73 @@ def test_buffer_pool_keeps_zero_halo():
     g = b.act(16, 8, 8)
     assert g.buf is a.buf                   # after the join everything is reusable again
     assert sum(b.ops[i].kind in (13, 14) for i in range(len(b.ops))) == 2
+
+
+def _chain_builder(chained, groups=1, N=4, ch=128, H=14):
+    """the plan builder's view of one HRNet branch (4 BasicBlocks) on CPU buffers"""
+    from poco_b200 import arch
+    g = torch.Generator().manual_seed(3)
+    sd = {}
+    for k in range(4):
+        for c, bn in (('conv1', 'bn1'), ('conv2', 'bn2')):
+            sd[f'br.{k}.{c}.weight'] = torch.randn(ch, ch, 3, 3, generator=g) * 0.05
+            sd[f'br.{k}.{bn}.weight'] = torch.ones(ch)
+            sd[f'br.{k}.{bn}.bias'] = torch.zeros(ch)
+            sd[f'br.{k}.{bn}.running_mean'] = torch.zeros(ch)
+            sd[f'br.{k}.{bn}.running_var'] = torch.ones(ch)
+    b = engine.PlanBuilder(sd, N, 'cpu')
+    b.use_chains = chained
+    x = engine.alloc_act(ch, N, H, H, 'cpu')
+    b.begin_chain()
+    for k in range(4):
+        x = arch.basic_block(b, x, f'br.{k}', ch, ch)
+    b.end_chain(groups=groups)
+    return b
+
+
+def test_conv_chain_descriptors_and_validation():
+    """host side of poco_conv_chain: the builder links eight same-geometry convs (segment i reads what i-1
+    wrote, residuals come from two segments back or from outside), crop ranges split the batch, and the C ABI
+    rejects malformed chains before touching the GPU"""
+    b = _chain_builder(True)
+    assert [op.kind for op in b.ops] == [_lib.OP_CONV_CHAIN]
+    ch = b.ops[0].u.conv_chain
+    assert ch.n_seg == 8 and ch.flags
+    for i in range(1, 8):
+        assert ch.seg[i].in_.data == ch.seg[i - 1].out.data
+        assert not ch.seg[i].residual or ch.seg[i].residual != ch.seg[i - 1].out.data
+    assert [bool(ch.seg[i].residual) for i in range(8)] == [False, True] * 4
+    tiles = (4 * 16 * 16 + 127) // 128
+    assert _lib.lib().poco_conv_chain_flag_count(ctypes.byref(ch)) == 7 * tiles
+    # crop ranges: 4 crops in 3 groups -> chains over 1, 1 and 2 crops with offset pointers
+    b3 = _chain_builder(True, groups=3)
+    assert [op.kind for op in b3.ops] == [_lib.OP_CONV_CHAIN] * 3
+    ns = [op.u.conv_chain.seg[0].in_.N for op in b3.ops]
+    assert ns == [1, 1, 2]
+    base = b3.ops[0].u.conv_chain.seg[0].in_.data
+    assert [op.u.conv_chain.seg[0].in_.data - base for op in b3.ops] == [0, 16 * 16 * 16, 2 * 16 * 16 * 16]
+    # without chains the same branch is eight plain conv ops
+    assert [op.kind for op in _chain_builder(False).ops] == [_lib.OP_CONV] * 8
+    # malformed chains fail in validation (no GPU needed): bad length, debug-kernel segment
+    bad = _lib.ConvChain.from_buffer_copy(ch)
+    bad.n_seg = 9
+    assert _lib.lib().poco_run_op(ctypes.byref(_lib.make_op(bad)), None) != 0
+    assert b'chain length' in _lib.lib().poco_last_error()
+    bad = _lib.ConvChain.from_buffer_copy(ch)
+    bad.seg[3].impl = 1
+    assert _lib.lib().poco_run_op(ctypes.byref(_lib.make_op(bad)), None) != 0
+    assert b'tcgen05 kernel only' in _lib.lib().poco_last_error()
+
+
+def test_weight_layouts():
+    """pack_conv_weight / pack_conv_weight_dxn index maps (include/poco_b200.h poco_conv.weight, wfmt)"""
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(32, 16, 3, 3, generator=g)
+    p = engine.pack_conv_weight(w)                      # [tap][Cin/8][Cout][8]
+    assert tuple(p.shape) == (9, 2, 32, 8)
+    assert p[5, 1, 7, 3] == w[7, 11, 1, 2].half()       # tap 5 = (r 1, s 2), channel 8 + 3
+    q = engine.pack_conv_weight_dxn(w)                  # [r][Cin/8][s*Cout + co][8]
+    assert tuple(q.shape) == (3, 2, 96, 8)
+    assert q[1, 1, 2 * 32 + 7, 3] == w[7, 11, 1, 2].half()
+    assert engine.dxn_applies(32, 32, 3, 1, 1) == (os.environ.get('POCO_B200_DXN', '0') == '1')
+    assert not engine.dxn_applies(32, 48, 3, 1, 1)
