@@ -125,11 +125,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
     const uint32_t sz = valid ? 16u : 0u;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
-// same, bypassing L1 (every byte is used once by this SM)
-__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src, bool valid) {
-    const uint32_t sz = valid ? 16u : 0u;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -30,7 +30,7 @@ CONV_CASES = [
     (3, 64, 3, 2, 224, 1, False, 1), (64, 64, 3, 2, 112, 1, False, 1), (32, 64, 3, 2, 56, 2, False, 1),
     (256, 256, 3, 2, 14, 2, True, 2), (3, 64, 7, 2, 224, 1, False, 1), (256, 512, 1, 2, 56, 1, False, 0),
     (128, 256, 3, 2, 14, 3, True, 1),
-    # stride-2 3x3 on even inputs: phase-split producer (MODE_S2) when its stages fit, else the gather
+    # more stride-2 3x3 shapes of HRNet (fuse layers, stem, transitions)
     (32, 32, 3, 2, 56, 3, False, 1), (64, 128, 3, 2, 28, 5, True, 1), (32, 128, 3, 2, 28, 2, True, 0),
     (256, 64, 3, 2, 56, 1, False, 1), (48, 96, 3, 2, 28, 2, True, 1), (32, 32, 3, 2, 28, 3, False, 1),
     (64, 256, 3, 2, 14, 2, True, 1), (16, 64, 3, 2, 224, 2, False, 1),
