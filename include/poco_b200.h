@@ -196,6 +196,28 @@ typedef struct poco_realnvp {
     int32_t direction;
 } poco_realnvp;
 
+/* Per-detection crop + normalisation, the step right before the hot path.  Replaces
+ * get_single_image_crop_demo (utils/vibe_image_utils.py:233-267: gen_trans_from_patch_cv :58-91, cv2.warpAffine
+ * INTER_LINEAR / BORDER_CONSTANT :104-105, ToTensor + Normalize :343-352) and calculate_bbox_info /
+ * calculate_focal_length (utils/image_utils.py:171-187) as used by POCOTester (core/tester.py:181-212).
+ * frame: uint8 RGB [H][W][3]; boxes: f32 [n][4] = (cx, cy, w, h) in pixels; scale: the bbox scale of the caller
+ * (1.2 in the demo).  img: f32 [n][3][crop][crop], bit-identical to the reference (cv2's fixed-point bilinear
+ * is reproduced exactly).  The five per-detection outputs may be NULL. */
+typedef struct poco_crop {
+    const uint8_t* frame;
+    int32_t frame_h, frame_w;
+    const float* boxes;
+    int32_t n, crop;
+    float scale;
+    int32_t pad_;
+    float* img;
+    float* bbox_info;    /* [n][3] */
+    float* focal_length; /* [n] */
+    float* scale_out;    /* [n] max(w, h) / 200 */
+    float* center;       /* [n][2] */
+    float* orig_shape;   /* [n][2] (h, w) */
+} poco_crop;
+
 /* fork / join of plan lanes.  HRNet's branches (and the per-output fuse chains) are independent, and the
  * low-resolution ones cannot fill 148 SMs on their own: a plan runs them concurrently on internal
  * streams (lane k of `poco_op.lane`), each conv capped to its share of the SMs (poco_conv.max_ctas). */
@@ -218,7 +240,8 @@ typedef enum poco_op_kind {
     POCO_OP_REALNVP = 12,
     POCO_OP_FORK = 13, /* lanes 1..n-1 start after everything enqueued so far on lane 0 */
     POCO_OP_JOIN = 14, /* lane 0 continues after lanes 1..n-1 have drained */
-    POCO_OP_CONV_CHAIN = 15
+    POCO_OP_CONV_CHAIN = 15,
+    POCO_OP_CROP = 16
 } poco_op_kind;
 
 typedef struct poco_op {
@@ -239,6 +262,7 @@ typedef struct poco_op {
         poco_pare_head pare_head;
         poco_realnvp realnvp;
         poco_sync sync;
+        poco_crop crop;
     } u;
 } poco_op;
 
@@ -266,6 +290,7 @@ int poco_copy2d_run(const poco_copy2d* d, void* stream);
 int poco_rot6d_run(const poco_rot6d* d, void* stream);
 int poco_pare_head_run(const poco_pare_head* d, void* stream);
 int poco_realnvp_run(const poco_realnvp* d, void* stream);
+int poco_crop_run(const poco_crop* d, void* stream);
 int64_t poco_pare_scratch_floats(int32_t N, int32_t H, int32_t W);
 
 /* a plan = the static layer schedule of one POCO.forward for one batch size (poco.py:99-129):

@@ -391,3 +391,32 @@ def test_conv_dx_in_n_tap_shift():
         w[:, :, t // 3, t % 3] = torch.eye(32)
         out = run_conv(x, w, torch.zeros(32), relu=0, dxn=True)
         assert torch.equal(out, F.conv2d(x, w, padding=1)), f'tap {t}'
+
+
+def test_crop_normalize_matches_reference_bit_for_bit():
+    """poco_crop against the reference-generated golden crops and, on fresh random detections,
+    against the oracle: integer warp arithmetic -> bit-exact"""
+    import os
+
+    from oracle import crop_oracle as C
+    from poco_b200 import crop_batch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'crop_golden.npz'))
+    frame = torch.from_numpy(g['frame']).cuda()
+    out = crop_batch(frame, torch.from_numpy(g['boxes']), scale=float(g['scale']))
+    sync_or_die()
+    assert np.array_equal(out['img'].cpu().numpy(), g['img'])
+    assert np.array_equal(out['bbox_info'].cpu().numpy(), g['bbox_info'])
+    assert np.array_equal(out['focal_length'].cpu().numpy(), g['focal_length'])
+    # fresh detections on a larger frame (1080p), several far outside it; empty crops are all (0 - mean) / std
+    fr = C.synthetic_frame(5, 1080, 1920)
+    bx = C.synthetic_boxes(7, 24, 1080, 1920)
+    bx[3] = [-500, -500, 100, 100]
+    ref = C.crop_batch(fr, bx, 1.1)
+    got = crop_batch(torch.from_numpy(fr).cuda(), torch.from_numpy(bx.astype(np.float32)), scale=1.1)
+    sync_or_die()
+    for k in ('img', 'bbox_info', 'focal_length', 'scale', 'center', 'orig_shape'):
+        assert np.array_equal(got[k].cpu().numpy(), ref[k]), k
+    assert np.unique(ref['img'][3][0]).size == 1
+    # the product path has no CPU route
+    with pytest.raises(Exception):
+        crop_batch(torch.from_numpy(fr), torch.from_numpy(bx.astype(np.float32)))

@@ -68,3 +68,23 @@ def test_golden_is_not_degenerate():
     for p in PRESETS:
         _, gold, _ = load_preset(p)
         assert float(gold['crop_diff_pose']) > 0.1 and float(gold['crop_diff_var']) > 5e-3
+
+
+def test_crop_oracle_matches_reference_golden():
+    """the numpy restatement of get_single_image_crop_demo / calculate_bbox_info equals the
+    outputs of the reference functions (tests/golden/crop_golden.npz, oracle/make_golden_crop.py) bit for bit"""
+    import os
+
+    import numpy as np
+
+    from oracle import crop_oracle as C
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'crop_golden.npz'))
+    assert np.array_equal(g['frame'], C.synthetic_frame(0))
+    assert np.array_equal(g['boxes'], C.synthetic_boxes(0).astype(np.float32))
+    o = C.crop_batch(g['frame'], g['boxes'].astype(np.float64), float(g['scale']))
+    assert np.array_equal(o['img'], g['img'])
+    assert np.array_equal(o['bbox_info'], g['bbox_info'])
+    assert np.array_equal(o['focal_length'], g['focal_length'])
+    # sanity of the fixture: crops differ from each other and include zero-filled borders
+    assert np.abs(g['img'][0] - g['img'][1]).max() > 1.0
+    assert (g['img'][1][0] == g['img'][1][0, 0, 0]).mean() > 0.05       # box 1 hangs over the frame corner
