@@ -218,6 +218,25 @@ typedef struct poco_crop {
     float* orig_shape;   /* [n][2] (h, w) */
 } poco_crop;
 
+/* Uncertainty post-processing, the step right after the hot path: POCOUtils.prepare_uncert
+ * (utils/poco_utils.py:63-94, with get_kinematic_uncert :21-25 and the `1 - var` confidence option) followed by
+ * POCOUtils.get_global_uncert (:50-61), as core/tester.py:243-245 / :418-421 call them.  var: f32 [n][24]
+ * (`var_pose` of POCO.forward).  Outputs (each may be NULL): prepared [n][24], thresholded [n][24] (the copy
+ * get_global_uncert modifies in place), global_var [n].  cliff != 0: threshold 2 * sensitivity_threshold and
+ * global = first entry; else threshold sensitivity_threshold and global = mean of the row. */
+typedef struct poco_uncert_post {
+    const float* var;
+    int32_t n;
+    int32_t cliff;
+    int32_t kinematic;
+    int32_t return_conf;
+    float sensitivity_threshold; /* 0.40 in the reference */
+    int32_t pad_;
+    float* prepared;
+    float* thresholded;
+    float* global_var;
+} poco_uncert_post;
+
 /* fork / join of plan lanes.  HRNet's branches (and the per-output fuse chains) are independent, and the
  * low-resolution ones cannot fill 148 SMs on their own: a plan runs them concurrently on internal
  * streams (lane k of `poco_op.lane`), each conv capped to its share of the SMs (poco_conv.max_ctas). */
@@ -241,7 +260,8 @@ typedef enum poco_op_kind {
     POCO_OP_FORK = 13, /* lanes 1..n-1 start after everything enqueued so far on lane 0 */
     POCO_OP_JOIN = 14, /* lane 0 continues after lanes 1..n-1 have drained */
     POCO_OP_CONV_CHAIN = 15,
-    POCO_OP_CROP = 16
+    POCO_OP_CROP = 16,
+    POCO_OP_UNCERT_POST = 17
 } poco_op_kind;
 
 typedef struct poco_op {
@@ -263,6 +283,7 @@ typedef struct poco_op {
         poco_realnvp realnvp;
         poco_sync sync;
         poco_crop crop;
+        poco_uncert_post uncert_post;
     } u;
 } poco_op;
 
@@ -291,6 +312,7 @@ int poco_rot6d_run(const poco_rot6d* d, void* stream);
 int poco_pare_head_run(const poco_pare_head* d, void* stream);
 int poco_realnvp_run(const poco_realnvp* d, void* stream);
 int poco_crop_run(const poco_crop* d, void* stream);
+int poco_uncert_post_run(const poco_uncert_post* d, void* stream);
 int64_t poco_pare_scratch_floats(int32_t N, int32_t H, int32_t W);
 
 /* a plan = the static layer schedule of one POCO.forward for one batch size (poco.py:99-129):

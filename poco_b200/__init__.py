@@ -4,6 +4,6 @@
 """
 from ._lib import PocoError, kernel_launches  # noqa: F401
 from .poco import POCO  # noqa: F401
-from .preprocess import crop_batch  # noqa: F401
+from .preprocess import crop_batch, uncert_post  # noqa: F401
 
-__all__ = ['POCO', 'PocoError', 'kernel_launches', 'crop_batch']
+__all__ = ['POCO', 'PocoError', 'kernel_launches', 'crop_batch', 'uncert_post']

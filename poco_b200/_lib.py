@@ -13,7 +13,7 @@ MAX_FUSE_INPUTS = 4
 ACT_GUARD_BYTES = 8192
 
 OP_PACK_IMAGE, OP_CONV, OP_FUSE_SUM, OP_UPSAMPLE2X, OP_MAXPOOL, OP_AVGPOOL, OP_UNPACK, OP_LINEAR, \
-    OP_COPY2D, OP_ROT6D, OP_PARE_HEAD, OP_REALNVP, OP_FORK, OP_JOIN, OP_CONV_CHAIN, OP_CROP = range(1, 17)
+    OP_COPY2D, OP_ROT6D, OP_PARE_HEAD, OP_REALNVP, OP_FORK, OP_JOIN, OP_CONV_CHAIN, OP_CROP, OP_UNCERT_POST = range(1, 18)
 MAX_CHAIN = 8
 
 
@@ -98,6 +98,12 @@ class Crop(C.Structure):
                 ('center', C.c_void_p), ('orig_shape', C.c_void_p)]
 
 
+class UncertPost(C.Structure):
+    _fields_ = [('var', C.c_void_p), ('n', C.c_int32), ('cliff', C.c_int32), ('kinematic', C.c_int32),
+                ('return_conf', C.c_int32), ('sensitivity_threshold', C.c_float), ('pad_', C.c_int32),
+                ('prepared', C.c_void_p), ('thresholded', C.c_void_p), ('global_var', C.c_void_p)]
+
+
 class Sync(C.Structure):
     _fields_ = [('n_lanes', C.c_int32)]
 
@@ -106,7 +112,7 @@ class _OpU(C.Union):
     _fields_ = [('pack_image', PackImage), ('conv', Conv), ('conv_chain', ConvChain), ('fuse_sum', FuseSum), ('upsample2x', Upsample2x),
                 ('maxpool', MaxPool), ('avgpool', AvgPool), ('unpack', Unpack), ('linear', Linear),
                 ('copy2d', Copy2d), ('rot6d', Rot6d), ('pare_head', PareHead), ('realnvp', RealNVP), ('sync', Sync),
-                ('crop', Crop)]
+                ('crop', Crop), ('uncert_post', UncertPost)]
 
 
 class Op(C.Structure):
@@ -117,18 +123,18 @@ _FIELD_OF_KIND = {OP_PACK_IMAGE: 'pack_image', OP_CONV: 'conv', OP_FUSE_SUM: 'fu
                   OP_UPSAMPLE2X: 'upsample2x', OP_MAXPOOL: 'maxpool', OP_AVGPOOL: 'avgpool',
                   OP_UNPACK: 'unpack', OP_LINEAR: 'linear', OP_COPY2D: 'copy2d', OP_ROT6D: 'rot6d',
                   OP_PARE_HEAD: 'pare_head', OP_REALNVP: 'realnvp', OP_FORK: 'sync', OP_JOIN: 'sync',
-                  OP_CONV_CHAIN: 'conv_chain', OP_CROP: 'crop'}
+                  OP_CONV_CHAIN: 'conv_chain', OP_CROP: 'crop', OP_UNCERT_POST: 'uncert_post'}
 _KIND_OF_TYPE = {PackImage: OP_PACK_IMAGE, Conv: OP_CONV, FuseSum: OP_FUSE_SUM, Upsample2x: OP_UPSAMPLE2X,
                  MaxPool: OP_MAXPOOL, AvgPool: OP_AVGPOOL, Unpack: OP_UNPACK, Linear: OP_LINEAR,
                  Copy2d: OP_COPY2D, Rot6d: OP_ROT6D, PareHead: OP_PARE_HEAD, RealNVP: OP_REALNVP,
-                 ConvChain: OP_CONV_CHAIN, Crop: OP_CROP}
+                 ConvChain: OP_CONV_CHAIN, Crop: OP_CROP, UncertPost: OP_UNCERT_POST}
 
 # every symbol include/poco_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     'poco_version', 'poco_last_error', 'poco_device_check', 'poco_kernel_launches', 'poco_run_op',
     'poco_conv_run', 'poco_conv_chain_run', 'poco_conv_chain_flag_count', 'poco_pack_image_run', 'poco_fuse_sum_run', 'poco_upsample2x_run', 'poco_maxpool_run',
     'poco_avgpool_run', 'poco_unpack_run', 'poco_linear_run', 'poco_copy2d_run', 'poco_rot6d_run',
-    'poco_pare_head_run', 'poco_realnvp_run', 'poco_crop_run', 'poco_pare_scratch_floats',
+    'poco_pare_head_run', 'poco_realnvp_run', 'poco_crop_run', 'poco_uncert_post_run', 'poco_pare_scratch_floats',
     'poco_plan_create', 'poco_plan_run', 'poco_plan_num_ops', 'poco_plan_flops', 'poco_plan_destroy',
 ]
 

@@ -136,3 +136,69 @@ extern "C" int poco_crop_run(const poco_crop* d, void* stream) {
     POCO_LAUNCHED();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Uncertainty post-processing, the step right after the hot path: POCOUtils.prepare_uncert
+// (pocolib/utils/poco_utils.py:63-94; optional get_kinematic_uncert :21-25 and 1 - var) followed by
+// get_global_uncert (:50-61) as pocolib/core/tester.py:243-245 / :418-421 call them -- on the device, so the
+// per-batch device -> host synchronisation of the reference loop disappears.  One thread per crop (24 floats).
+// ------------------------------------------------------------------------------------------------------------
+namespace poco {
+namespace {
+
+__constant__ int kSmplParent[24] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+
+__global__ void uncert_post_kernel(poco_uncert_post d) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= d.n) return;
+    float v[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) v[i] = d.var[(long long)n * 24 + i];
+    if (d.kinematic) {                  // children accumulate the (already updated) value of their parent
+#pragma unroll
+        for (int i = 1; i < 24; ++i) v[i] = __fadd_rn(v[i], v[kSmplParent[i]]);
+    }
+    if (d.return_conf) {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) v[i] = __fsub_rn(1.f, v[i]);
+    }
+    if (d.prepared) {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) d.prepared[(long long)n * 24 + i] = v[i];
+    }
+    // get_global_uncert works on a copy: rows whose first entry exceeds the threshold become all ones
+    const float thr = d.cliff ? 2.f * d.sensitivity_threshold : d.sensitivity_threshold;
+    if (v[0] > thr) {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) v[i] = 1.f;
+    }
+    if (d.thresholded) {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) d.thresholded[(long long)n * 24 + i] = v[i];
+    }
+    if (d.global_var) {
+        if (d.cliff) {
+            d.global_var[n] = v[0];
+        } else {                        // numpy float32 mean of 24 values: pairwise sum in 8 lanes, then / 24
+            float r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = v[i];
+#pragma unroll
+            for (int i = 8; i < 24; ++i) r[i & 7] = __fadd_rn(r[i & 7], v[i]);
+            const float s = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                                      __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+            d.global_var[n] = __fdiv_rn(s, 24.f);
+        }
+    }
+}
+
+}  // namespace
+}  // namespace poco
+
+extern "C" int poco_uncert_post_run(const poco_uncert_post* d, void* stream) {
+    POCO_CHECK(d->var != nullptr && d->n > 0, "bad arguments");
+    POCO_CHECK(d->prepared || d->thresholded || d->global_var, "no output requested");
+    poco::uncert_post_kernel<<<(d->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*d);
+    POCO_LAUNCHED();
+    return 0;
+}

@@ -35,3 +35,21 @@ def crop_batch(frame, boxes, scale=1.2, crop=224, stream=None):
     with torch.cuda.device(dev):
         L.run_op(d, stream if stream is not None else torch.cuda.current_stream().cuda_stream)
     return out
+
+
+def uncert_post(var_pose, backbone, kinematic=False, return_conf=False, sensitivity_threshold=0.40, stream=None):
+    """POCOUtils.prepare_uncert + get_global_uncert (pocolib/utils/poco_utils.py:50-94, tester.py:243-245) on the
+    device.  var_pose: f32 CUDA [n, 24] from POCO.forward; backbone: the model's '<backbone>-<head>' string.
+    -> (prepared [n,24], thresholded [n,24], global_var [n]), all on the device: no host synchronisation."""
+    if not (isinstance(var_pose, torch.Tensor) and var_pose.is_cuda and var_pose.dtype == torch.float32
+            and var_pose.dim() == 2 and var_pose.shape[1] == 24):
+        raise L.PocoError('uncert_post needs an f32 CUDA tensor of shape [n, 24] (poco_b200 has no CPU path)')
+    v = var_pose.contiguous()
+    n = v.shape[0]
+    prepared, thr = torch.empty_like(v), torch.empty_like(v)
+    glob = torch.empty(n, dtype=torch.float32, device=v.device)
+    d = L.UncertPost(v.data_ptr(), n, 1 if 'cliff' in backbone else 0, int(bool(kinematic)), int(bool(return_conf)),
+                     float(sensitivity_threshold), 0, prepared.data_ptr(), thr.data_ptr(), glob.data_ptr())
+    with torch.cuda.device(v.device):
+        L.run_op(d, stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+    return prepared, thr, glob

@@ -420,3 +420,24 @@ def test_crop_normalize_matches_reference_bit_for_bit():
     # the product path has no CPU route
     with pytest.raises(Exception):
         crop_batch(torch.from_numpy(fr), torch.from_numpy(bx.astype(np.float32)))
+
+
+def test_uncert_post_matches_reference():
+    """poco_uncert_post against the reference-generated golden: the element-wise parts bit for bit,
+    the PARE row mean to one fp32 rounding"""
+    import os
+
+    from poco_b200 import uncert_post
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'uncert_golden.npz'))
+    var = torch.from_numpy(g['var']).cuda()
+    for bb, name in (('cliff', 'hrnet_w48_cls-cliff'), ('pare', 'hrnet_w32-pare')):
+        for kin in (0, 1):
+            tag = f'{bb}_{kin}'
+            p, t, gl = uncert_post(var, name, kinematic=bool(kin))
+            sync_or_die()
+            assert np.array_equal(p.cpu().numpy(), g['prepared_' + tag])
+            assert np.array_equal(t.cpu().numpy(), g['thresholded_' + tag])
+            assert np.allclose(gl.cpu().numpy(), g['global_' + tag], rtol=2e-7, atol=0)
+    conf, _, _ = uncert_post(var, 'hrnet_w32-pare', return_conf=True)
+    assert np.array_equal(conf.cpu().numpy(), 1 - g['var'])
+    assert np.array_equal(var.cpu().numpy(), g['var'])              # the input is never modified

@@ -88,3 +88,21 @@ def test_crop_oracle_matches_reference_golden():
     # sanity of the fixture: crops differ from each other and include zero-filled borders
     assert np.abs(g['img'][0] - g['img'][1]).max() > 1.0
     assert (g['img'][1][0] == g['img'][1][0, 0, 0]).mean() > 0.05       # box 1 hangs over the frame corner
+
+
+def test_uncert_oracle_matches_reference_golden():
+    """prepare_uncert / get_global_uncert restatement == the reference functions' outputs"""
+    import os
+
+    import numpy as np
+
+    from oracle import uncert_oracle as U
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'uncert_golden.npz'))
+    for bb in ('cliff', 'pare'):
+        for kin in (0, 1):
+            tag = f'{bb}_{kin}'
+            p = U.prepare_uncert(g['var'], bool(kin))
+            t, gl = U.global_uncert(p, bb)
+            assert np.array_equal(p, g['prepared_' + tag]) and np.array_equal(t, g['thresholded_' + tag])
+            assert np.array_equal(gl, g['global_' + tag])
+    assert (g['thresholded_cliff_0'] == 1.0).all(1).sum() < (g['thresholded_pare_0'] == 1.0).all(1).sum()
