@@ -159,3 +159,27 @@ def test_empty_batch_and_bad_inputs_raise():
     m.train()
     with pytest.raises(Exception):
         m({'img': torch.zeros(1, 3, 224, 224, device='cuda')})
+
+
+def test_stream_runner_equals_the_separate_steps():
+    """f2: StreamRunner.step == oracle crop -> POCO.forward -> oracle uncertainty post-processing"""
+    from common import build_model
+    from oracle import crop_oracle as C
+    from oracle import uncert_oracle as U
+    from poco_b200 import StreamRunner
+    m = build_model('cliff_w32', 'cuda')
+    frame = C.synthetic_frame(2, 720, 1280)
+    boxes = C.synthetic_boxes(2, 5, 720, 1280)
+    run = StreamRunner(m, bbox_scale=1.1)
+    out = run.step(torch.from_numpy(frame).cuda(), torch.from_numpy(boxes.astype(np.float32)))
+    torch.cuda.synchronize()
+    ref_batch = {k: torch.from_numpy(v).cuda() for k, v in C.crop_batch(frame, boxes, 1.1).items()}
+    with torch.no_grad():
+        ref = m(ref_batch)
+    for k in ('pred_pose', 'pred_shape', 'pred_cam', 'var_pose'):
+        assert torch.equal(out[k], ref[k]), k                   # identical crops -> identical forward
+    p = U.prepare_uncert(ref['var_pose'].cpu().numpy())
+    _, gl = U.global_uncert(p, 'hrnet_w32-cliff')
+    assert np.array_equal(out['variance'].cpu().numpy(), p)
+    assert np.array_equal(out['variance_global'].cpu().numpy(), gl)
+    assert out['orig_cam'].shape == (5, 4) and torch.isfinite(out['orig_cam']).all()

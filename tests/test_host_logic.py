@@ -207,3 +207,18 @@ def test_weight_layouts():
     assert q[1, 1, 2 * 32 + 7, 3] == w[7, 11, 1, 2].half()
     assert engine.dxn_applies(32, 32, 3, 1, 1) == (os.environ.get('POCO_B200_DXN', '0') == '1')
     assert not engine.dxn_applies(32, 48, 3, 1, 1)
+
+
+def test_convert_crop_cam_matches_reference_formula():
+    """stream.convert_crop_cam_to_orig_img == the numpy formula of pocolib/utils/demo_utils.py:249-266"""
+    from poco_b200 import convert_crop_cam_to_orig_img
+    g = torch.Generator().manual_seed(9)
+    cam = torch.rand(7, 3, generator=g) + 0.5
+    bbox = torch.rand(7, 4, generator=g) * 300 + 50
+    W, H = 1920, 1080
+    got = convert_crop_cam_to_orig_img(cam, bbox, W, H).numpy()
+    c, b = cam.numpy(), bbox.numpy()
+    sx = c[:, 0] * (1. / (W / b[:, 2]))
+    sy = c[:, 0] * (1. / (H / b[:, 2]))
+    ref = np.stack([sx, sy, ((b[:, 0] - W / 2.) / (W / 2.) / sx) + c[:, 1], ((b[:, 1] - H / 2.) / (H / 2.) / sy) + c[:, 2]]).T
+    assert np.allclose(got, ref, rtol=1e-6, atol=1e-6) and got.shape == (7, 4)
