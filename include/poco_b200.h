@@ -237,6 +237,56 @@ typedef struct poco_uncert_post {
     float* global_var;
 } poco_uncert_post;
 
+/* SMPL mesh stage, the last step of POCO.forward: smplx.SMPL linear blend skinning with
+ * pose2rot=False (smplx==0.1.28 lbs.py, called at models/head/smpl_head.py:53-58 / smplcam_head.py:48-53), the
+ * wrapper's vertex joints + J_regressor_extra joints + joint_map (smpl_head.py:12-34), the camera conversions
+ * (utils/geometry.py:447-463, smplcam_head.py:123-139) and the 2-D projection (geometry.py:480-508,
+ * smplcam_head.py:99-120).  smplx and the licensed model files are absent from the reference tree: the LBS part
+ * restates the published algorithm and its parity is unpinned.
+ * The model is device data prepared once by the host (poco_b200/smpl.py prepare_smpl_model): vertex arrays are
+ * coordinate-major and padded to vp = nv rounded up to 128 (padding holds zeros). */
+#define POCO_SMPL_JOINTS 24
+#define POCO_SMPL_BETAS 10
+#define POCO_SMPL_SCRATCH_FLOATS 580 /* per crop: 220 blend coefficients, 24x12 transforms, 24x3 posed joints */
+typedef struct poco_smpl_model {
+    const float* v_template;         /* [3][vp] */
+    const float* dirs;               /* [217][3][vp]: rows 0..9 shapedirs, rows 10..216 posedirs */
+    const float* weights;            /* [24][vp] skinning weights */
+    const float* j_template;         /* [24][3]      J_regressor . v_template */
+    const float* j_dirs;             /* [24][3][10]  J_regressor . shapedirs  */
+    const int32_t* parents;          /* [24] kinematic tree, parents[0] = -1, parents[i] < i */
+    const int32_t* extra_vertex_ids; /* [n_extra_vertex] smplx VertexJointSelector */
+    const int32_t* reg_row_ptr;      /* CSR of J_regressor_extra: [n_extra_reg + 1] */
+    const int32_t* reg_col;
+    const float* reg_val;
+    const int32_t* joint_map;        /* [n_joints_out] into the 24 + n_extra_vertex + n_extra_reg joints (<= 64) */
+    int32_t nv, vp, n_extra_vertex, n_extra_reg, n_joints_out, pad_;
+} poco_smpl_model;
+
+typedef struct poco_smpl {
+    poco_smpl_model model;
+    const float* rotmat; /* [n][24][3][3] pred_pose */
+    const float* betas;  /* [n][10] pred_shape */
+    const float* cam;    /* [n][3] pred_cam (s, tx, ty) */
+    const float* focal_length; /* cliff only: [n] */
+    const float* bbox_scale;   /* [n] bbox height / 200 */
+    const float* bbox_center;  /* [n][2] */
+    const float* img_w;        /* [n] */
+    const float* img_h;        /* [n] */
+    int32_t n;
+    int32_t cliff;              /* 0: smpl_head (crop camera, focal_default, centre 0); 1: smplcam_head */
+    int32_t normalize_joints2d; /* joints2d / (img_res / 2) (smpl_head.py:77-79) */
+    int32_t img_res;
+    float focal_default; /* 5000 */
+    int32_t pad_;
+    float* scratch;       /* n * POCO_SMPL_SCRATCH_FLOATS floats */
+    float* vertices;      /* [n][nv][3] */
+    float* joints3d;      /* [n][n_joints_out][3] */
+    float* joints2d;      /* [n][n_joints_out][2] or NULL */
+    float* cam_t;         /* [n][3] or NULL */
+    float* fullimg_cam_t; /* [n][3] or NULL (cliff) */
+} poco_smpl;
+
 /* fork / join of plan lanes.  HRNet's branches (and the per-output fuse chains) are independent, and the
  * low-resolution ones cannot fill 148 SMs on their own: a plan runs them concurrently on internal
  * streams (lane k of `poco_op.lane`), each conv capped to its share of the SMs (poco_conv.max_ctas). */
@@ -261,7 +311,8 @@ typedef enum poco_op_kind {
     POCO_OP_JOIN = 14, /* lane 0 continues after lanes 1..n-1 have drained */
     POCO_OP_CONV_CHAIN = 15,
     POCO_OP_CROP = 16,
-    POCO_OP_UNCERT_POST = 17
+    POCO_OP_UNCERT_POST = 17,
+    POCO_OP_SMPL = 18
 } poco_op_kind;
 
 typedef struct poco_op {
@@ -284,6 +335,7 @@ typedef struct poco_op {
         poco_sync sync;
         poco_crop crop;
         poco_uncert_post uncert_post;
+        poco_smpl smpl;
     } u;
 } poco_op;
 
@@ -313,6 +365,7 @@ int poco_pare_head_run(const poco_pare_head* d, void* stream);
 int poco_realnvp_run(const poco_realnvp* d, void* stream);
 int poco_crop_run(const poco_crop* d, void* stream);
 int poco_uncert_post_run(const poco_uncert_post* d, void* stream);
+int poco_smpl_run(const poco_smpl* d, void* stream);
 int64_t poco_pare_scratch_floats(int32_t N, int32_t H, int32_t W);
 
 /* a plan = the static layer schedule of one POCO.forward for one batch size (poco.py:99-129):

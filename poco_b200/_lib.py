@@ -13,8 +13,9 @@ MAX_FUSE_INPUTS = 4
 ACT_GUARD_BYTES = 8192
 
 OP_PACK_IMAGE, OP_CONV, OP_FUSE_SUM, OP_UPSAMPLE2X, OP_MAXPOOL, OP_AVGPOOL, OP_UNPACK, OP_LINEAR, \
-    OP_COPY2D, OP_ROT6D, OP_PARE_HEAD, OP_REALNVP, OP_FORK, OP_JOIN, OP_CONV_CHAIN, OP_CROP, OP_UNCERT_POST = range(1, 18)
+    OP_COPY2D, OP_ROT6D, OP_PARE_HEAD, OP_REALNVP, OP_FORK, OP_JOIN, OP_CONV_CHAIN, OP_CROP, OP_UNCERT_POST, OP_SMPL = range(1, 19)
 MAX_CHAIN = 8
+SMPL_JOINTS, SMPL_BETAS, SMPL_SCRATCH_FLOATS = 24, 10, 580
 
 
 class Act(C.Structure):
@@ -104,6 +105,24 @@ class UncertPost(C.Structure):
                 ('prepared', C.c_void_p), ('thresholded', C.c_void_p), ('global_var', C.c_void_p)]
 
 
+class SmplModel(C.Structure):
+    _fields_ = [('v_template', C.c_void_p), ('dirs', C.c_void_p), ('weights', C.c_void_p), ('j_template', C.c_void_p),
+                ('j_dirs', C.c_void_p), ('parents', C.c_void_p), ('extra_vertex_ids', C.c_void_p),
+                ('reg_row_ptr', C.c_void_p), ('reg_col', C.c_void_p), ('reg_val', C.c_void_p), ('joint_map', C.c_void_p),
+                ('nv', C.c_int32), ('vp', C.c_int32), ('n_extra_vertex', C.c_int32), ('n_extra_reg', C.c_int32),
+                ('n_joints_out', C.c_int32), ('pad_', C.c_int32)]
+
+
+class Smpl(C.Structure):
+    _fields_ = [('model', SmplModel), ('rotmat', C.c_void_p), ('betas', C.c_void_p), ('cam', C.c_void_p),
+                ('focal_length', C.c_void_p), ('bbox_scale', C.c_void_p), ('bbox_center', C.c_void_p),
+                ('img_w', C.c_void_p), ('img_h', C.c_void_p),
+                ('n', C.c_int32), ('cliff', C.c_int32), ('normalize_joints2d', C.c_int32), ('img_res', C.c_int32),
+                ('focal_default', C.c_float), ('pad_', C.c_int32),
+                ('scratch', C.c_void_p), ('vertices', C.c_void_p), ('joints3d', C.c_void_p), ('joints2d', C.c_void_p),
+                ('cam_t', C.c_void_p), ('fullimg_cam_t', C.c_void_p)]
+
+
 class Sync(C.Structure):
     _fields_ = [('n_lanes', C.c_int32)]
 
@@ -112,7 +131,7 @@ class _OpU(C.Union):
     _fields_ = [('pack_image', PackImage), ('conv', Conv), ('conv_chain', ConvChain), ('fuse_sum', FuseSum), ('upsample2x', Upsample2x),
                 ('maxpool', MaxPool), ('avgpool', AvgPool), ('unpack', Unpack), ('linear', Linear),
                 ('copy2d', Copy2d), ('rot6d', Rot6d), ('pare_head', PareHead), ('realnvp', RealNVP), ('sync', Sync),
-                ('crop', Crop), ('uncert_post', UncertPost)]
+                ('crop', Crop), ('uncert_post', UncertPost), ('smpl', Smpl)]
 
 
 class Op(C.Structure):
@@ -123,18 +142,18 @@ _FIELD_OF_KIND = {OP_PACK_IMAGE: 'pack_image', OP_CONV: 'conv', OP_FUSE_SUM: 'fu
                   OP_UPSAMPLE2X: 'upsample2x', OP_MAXPOOL: 'maxpool', OP_AVGPOOL: 'avgpool',
                   OP_UNPACK: 'unpack', OP_LINEAR: 'linear', OP_COPY2D: 'copy2d', OP_ROT6D: 'rot6d',
                   OP_PARE_HEAD: 'pare_head', OP_REALNVP: 'realnvp', OP_FORK: 'sync', OP_JOIN: 'sync',
-                  OP_CONV_CHAIN: 'conv_chain', OP_CROP: 'crop', OP_UNCERT_POST: 'uncert_post'}
+                  OP_CONV_CHAIN: 'conv_chain', OP_CROP: 'crop', OP_UNCERT_POST: 'uncert_post', OP_SMPL: 'smpl'}
 _KIND_OF_TYPE = {PackImage: OP_PACK_IMAGE, Conv: OP_CONV, FuseSum: OP_FUSE_SUM, Upsample2x: OP_UPSAMPLE2X,
                  MaxPool: OP_MAXPOOL, AvgPool: OP_AVGPOOL, Unpack: OP_UNPACK, Linear: OP_LINEAR,
                  Copy2d: OP_COPY2D, Rot6d: OP_ROT6D, PareHead: OP_PARE_HEAD, RealNVP: OP_REALNVP,
-                 ConvChain: OP_CONV_CHAIN, Crop: OP_CROP, UncertPost: OP_UNCERT_POST}
+                 ConvChain: OP_CONV_CHAIN, Crop: OP_CROP, UncertPost: OP_UNCERT_POST, Smpl: OP_SMPL}
 
 # every symbol include/poco_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     'poco_version', 'poco_last_error', 'poco_device_check', 'poco_kernel_launches', 'poco_run_op',
     'poco_conv_run', 'poco_conv_chain_run', 'poco_conv_chain_flag_count', 'poco_pack_image_run', 'poco_fuse_sum_run', 'poco_upsample2x_run', 'poco_maxpool_run',
     'poco_avgpool_run', 'poco_unpack_run', 'poco_linear_run', 'poco_copy2d_run', 'poco_rot6d_run',
-    'poco_pare_head_run', 'poco_realnvp_run', 'poco_crop_run', 'poco_uncert_post_run', 'poco_pare_scratch_floats',
+    'poco_pare_head_run', 'poco_realnvp_run', 'poco_crop_run', 'poco_uncert_post_run', 'poco_smpl_run', 'poco_pare_scratch_floats',
     'poco_plan_create', 'poco_plan_run', 'poco_plan_num_ops', 'poco_plan_flops', 'poco_plan_destroy',
 ]
 

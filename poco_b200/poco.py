@@ -95,6 +95,7 @@ class POCO(nn.Module):
             # extensions (keyword-only in practice; defaults reproduce the reference behaviour)
             smpl_mean_params=None,
             smpl=None,
+            smpl_model=None,
             use_cuda_graph=None,
     ):
         super().__init__()
@@ -168,7 +169,7 @@ class POCO(nn.Module):
         for name, (shape, kind) in spec.spec.items():
             top, _, rest = name.partition('.')
             getattr(self, top).register(rest, self._init_tensor(name, shape, kind, mp, g), 'param' if kind == 'param' else 'buffer')
-        self.smpl = smpl if smpl is not None else make_smpl_stage(self.head_name, img_res)
+        self.smpl = smpl if smpl is not None else make_smpl_stage(self.head_name, img_res, smpl_model)
 
         self.use_cuda_graph = (os.environ.get('POCO_B200_GRAPH', '1') != '0') if use_cuda_graph is None else use_cuda_graph
         self.conv_impl = int(os.environ.get('POCO_B200_CONV_IMPL', '0'))
