@@ -249,6 +249,10 @@ def run_gpu_arm(args):
     peaks = load_peaks()
 
     model, sd, meta = load_model_and_sd(preset)
+    if args.with_smpl:      # mesh stage on the device inside the e2e leg (seeded stand-in for the licensed model)
+        from oracle import smpl_oracle
+        from poco_b200.smpl import DeviceSmplStage
+        model.smpl = DeviceSmplStage(model.head_name, smpl_oracle.synthetic_model(0))
     model = model.to(dev).eval()
     batch = build_inputs(preset, B, dev)
     clocks = ClockSampler(local)
@@ -295,6 +299,8 @@ def run_gpu_arm(args):
     h2d = sum(host[k].numel() * host[k].element_size() for k in host)
     rec_host = torch.empty(B, pdist.RECORD_WIDTH, dtype=torch.float32).pin_memory()
     d2h = rec_host.numel() * 4
+    verts_host = torch.empty(B, 6890, 3, dtype=torch.float32).pin_memory() if args.with_smpl else None
+    d2h += verts_host.numel() * 4 if args.with_smpl else 0
 
     # The caller-side pipeline a serving loop uses (the reference's DataLoader does the same with
     # pin_memory + non_blocking, tester.py:394-405): a copy stream uploads step i+1's crops from pinned host
@@ -323,6 +329,8 @@ def run_gpu_arm(args):
             o = model(dev_bufs[i % 2])
             consumed[i % 2].record()
             rec_host.copy_(pdist.pack_record(o), non_blocking=True)
+            if verts_host is not None:
+                verts_host.copy_(o['smpl_vertices'], non_blocking=True)
         torch.cuda.synchronize()
 
     with torch.no_grad():
@@ -381,7 +389,9 @@ def run_gpu_arm(args):
             'ms_per_step': round(ms / K, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'fp16', 'data': 'synthetic',
             'config': {'workload': WORKLOAD[preset], 'preset': preset, 'crops_per_gpu': B, 'global_batch': B * world,
-                       'parallelism': f'dp{world}', 'smpl_mesh_stage': 'excluded (host-side, SURVEY 8d)',
+                       'parallelism': f'dp{world}',
+                       'smpl_mesh_stage': ('in the e2e leg: poco_smpl_run on a seeded synthetic SMPL model, vertices read back '
+                                           '(SURVEY 8 f4); not in `value`') if args.with_smpl else 'excluded (SURVEY 8d)',
                        'l2': 'inputs (154 MB f32 at B=256) and activations exceed the 126 MB L2 every step',
                        'cuda_graph': True, 'weights': 'calibrated synthetic checkpoint seed 0'},
             'tensor_peak_frac_end_to_end': round(value / world * gf / 1e3 / peaks['tflops_burst'], 4),
@@ -407,6 +417,7 @@ def main():
     ap.add_argument('--batch', type=int, default=256, help='crops per GPU (weak scaling)')
     ap.add_argument('--cpu-sample', type=int, default=16, help='crops per CPU-arm forward (bounded sample)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--with-smpl', action='store_true', help='run the device SMPL mesh stage (f4) inside the e2e leg')
     ap.add_argument('--dump-ops', default=None, help='write the per-op timing table (eager, CUDA events) to this CSV')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -247,10 +247,11 @@ typedef struct poco_uncert_post {
  * coordinate-major and padded to vp = nv rounded up to 128 (padding holds zeros). */
 #define POCO_SMPL_JOINTS 24
 #define POCO_SMPL_BETAS 10
+#define POCO_SMPL_DIR_ROWS 224 /* blend table rows: 10 shape + 207 pose directions + 7 zero rows */
 #define POCO_SMPL_SCRATCH_FLOATS 580 /* per crop: 220 blend coefficients, 24x12 transforms, 24x3 posed joints */
 typedef struct poco_smpl_model {
     const float* v_template;         /* [3][vp] */
-    const float* dirs;               /* [217][3][vp]: rows 0..9 shapedirs, rows 10..216 posedirs */
+    const float* dirs;               /* [224][3][vp]: rows 0..9 shapedirs, 10..216 posedirs, 217..223 zero */
     const float* weights;            /* [24][vp] skinning weights */
     const float* j_template;         /* [24][3]      J_regressor . v_template */
     const float* j_dirs;             /* [24][3][10]  J_regressor . shapedirs  */

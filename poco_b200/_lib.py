@@ -15,7 +15,7 @@ ACT_GUARD_BYTES = 8192
 OP_PACK_IMAGE, OP_CONV, OP_FUSE_SUM, OP_UPSAMPLE2X, OP_MAXPOOL, OP_AVGPOOL, OP_UNPACK, OP_LINEAR, \
     OP_COPY2D, OP_ROT6D, OP_PARE_HEAD, OP_REALNVP, OP_FORK, OP_JOIN, OP_CONV_CHAIN, OP_CROP, OP_UNCERT_POST, OP_SMPL = range(1, 19)
 MAX_CHAIN = 8
-SMPL_JOINTS, SMPL_BETAS, SMPL_SCRATCH_FLOATS = 24, 10, 580
+SMPL_JOINTS, SMPL_BETAS, SMPL_SCRATCH_FLOATS, SMPL_DIR_ROWS = 24, 10, 580, 224
 
 
 class Act(C.Structure):

@@ -26,6 +26,11 @@ constexpr int kOffJ = kOffA + kJ * 12;          // [24][3] posed joints
 static_assert(kOffJ + kJ * 3 == POCO_SMPL_SCRATCH_FLOATS, "scratch layout");
 constexpr int kMaxJointsAll = 64;
 constexpr int kCB = 8;                          // crops per CTA in the skinning kernel
+constexpr int kKU = 8;                          // blend rows per register-prefetch group
+constexpr int kRows = POCO_SMPL_DIR_ROWS;       // 224: the 217 blend rows + zero rows, a whole number of group pairs
+constexpr int kGroups = kRows / kKU;
+constexpr int kSmplVP = 6912;                   // 6890 vertices of the published model, padded to 128
+static_assert(kRows >= kCoef && kRows % (2 * kKU) == 0, "blend table rows");
 
 __global__ void __launch_bounds__(128) smpl_pose_kernel(poco_smpl d) {
     __shared__ float sG[4][kJ][12];
@@ -95,21 +100,24 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(poco_smpl d) {
     }
 }
 
+// VP != 0: the padded vertex count is a compile-time constant (6912 for the published 6890-vertex model), so the 24
+// loads of a group are one base register + immediate offsets; VP == 0: any model, strides from poco_smpl_model.vp.
+template <int VP>
 __global__ void __launch_bounds__(128) smpl_skin_kernel(poco_smpl d) {
-    __shared__ __align__(16) float sCoef[kCoef][kCB];
+    __shared__ __align__(16) float sCoef[kRows][kCB];
     __shared__ __align__(16) float sA[kCB][kJ * 12];
     const int b0 = blockIdx.y * kCB;
     const int nb = min(kCB, d.n - b0);
-    for (int i = threadIdx.x; i < kCB * kCoefPad; i += 128) {
-        const int cb = i / kCoefPad, k = i - cb * kCoefPad;
-        if (k < kCoef) sCoef[k][cb] = cb < nb ? d.scratch[(size_t)(b0 + cb) * POCO_SMPL_SCRATCH_FLOATS + k] : 0.f;
+    for (int i = threadIdx.x; i < kCB * kRows; i += 128) {
+        const int cb = i / kRows, k = i - cb * kRows;
+        sCoef[k][cb] = (cb < nb && k < kCoef) ? d.scratch[(size_t)(b0 + cb) * POCO_SMPL_SCRATCH_FLOATS + k] : 0.f;
     }
     for (int i = threadIdx.x; i < kCB * kJ * 12; i += 128) {
         const int cb = i / (kJ * 12), e = i - cb * (kJ * 12);
         sA[cb][e] = cb < nb ? d.scratch[(size_t)(b0 + cb) * POCO_SMPL_SCRATCH_FLOATS + kOffA + e] : 0.f;
     }
     __syncthreads();
-    const int vp = d.model.vp;
+    const int vp = VP ? VP : d.model.vp;
     const int v = blockIdx.x * 128 + threadIdx.x;       // (vp is a multiple of 128; padded vertices hold zeros)
     float acc[kCB][3];
     {
@@ -117,20 +125,41 @@ __global__ void __launch_bounds__(128) smpl_skin_kernel(poco_smpl d) {
 #pragma unroll
         for (int cb = 0; cb < kCB; ++cb) { acc[cb][0] = t0; acc[cb][1] = t1; acc[cb][2] = t2; }
     }
+    // blend: acc += coef[k] * dirs[k] over the rows of the table (217 + zero rows up to kRows).  The rows come from L2
+    // (every CTA of the launch reads the same table), ~700 cycles away: two register buffers of kKU rows alternate,
+    // group g+1 is in flight while the FMAs of group g issue, so no load is waited on inside a group.
     const float* dp = d.model.dirs + v;
-#pragma unroll 4
-    for (int k = 0; k < kCoef; ++k) {
-        const float d0 = __ldg(dp), d1 = __ldg(dp + vp), d2 = __ldg(dp + 2 * vp);
-        dp += 3 * (size_t)vp;
-        const float4 c0 = *reinterpret_cast<const float4*>(&sCoef[k][0]);
-        const float4 c1 = *reinterpret_cast<const float4*>(&sCoef[k][4]);
-        const float c[kCB] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const size_t row = VP ? size_t(VP) : size_t(vp);
+    float ba[kKU][3], bb[kKU][3];
+    auto fetch = [&](float (&buf)[kKU][3], int g) {
+        const float* p = dp + (size_t)g * (kKU * 3) * row;
 #pragma unroll
-        for (int cb = 0; cb < kCB; ++cb) {
-            acc[cb][0] = fmaf(c[cb], d0, acc[cb][0]);
-            acc[cb][1] = fmaf(c[cb], d1, acc[cb][1]);
-            acc[cb][2] = fmaf(c[cb], d2, acc[cb][2]);
+        for (int u = 0; u < kKU; ++u) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) buf[u][c] = __ldg(p + (u * 3 + c) * row);
         }
+    };
+    auto blend = [&](const float (&buf)[kKU][3], int g) {
+#pragma unroll
+        for (int u = 0; u < kKU; ++u) {
+            const float4 c0 = *reinterpret_cast<const float4*>(&sCoef[g * kKU + u][0]);
+            const float4 c1 = *reinterpret_cast<const float4*>(&sCoef[g * kKU + u][4]);
+            const float c[kCB] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+            for (int cb = 0; cb < kCB; ++cb) {
+                acc[cb][0] = fmaf(c[cb], buf[u][0], acc[cb][0]);
+                acc[cb][1] = fmaf(c[cb], buf[u][1], acc[cb][1]);
+                acc[cb][2] = fmaf(c[cb], buf[u][2], acc[cb][2]);
+            }
+        }
+    };
+    fetch(ba, 0);
+#pragma unroll 1
+    for (int g = 0; g < kGroups; g += 2) {
+        fetch(bb, g + 1);
+        blend(ba, g);
+        if (g + 2 < kGroups) fetch(ba, g + 2);
+        blend(bb, g + 1);
     }
     float w[kJ];
 #pragma unroll
@@ -250,7 +279,11 @@ extern "C" int poco_smpl_run(const poco_smpl* d, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     smpl_pose_kernel<<<(d->n + 3) / 4, 128, 0, s>>>(*d);
     POCO_LAUNCHED();
-    smpl_skin_kernel<<<dim3(m.vp / 128, (d->n + kCB - 1) / kCB), 128, 0, s>>>(*d);
+    const dim3 grid(m.vp / 128, (d->n + kCB - 1) / kCB);
+    if (m.vp == kSmplVP)
+        smpl_skin_kernel<kSmplVP><<<grid, 128, 0, s>>>(*d);
+    else
+        smpl_skin_kernel<0><<<grid, 128, 0, s>>>(*d);
     POCO_LAUNCHED();
     smpl_joints_kernel<<<d->n, 128, 0, s>>>(*d);
     POCO_LAUNCHED();

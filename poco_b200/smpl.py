@@ -143,7 +143,7 @@ def prepare_smpl_model(model):
     """model arrays (smplx naming: v_template [V,3], shapedirs [V,3,>=10], posedirs [207,3V] or the .pkl's [V,3,207],
     J_regressor [24,V], weights [V,24], optional parents / extra_vertex_ids / J_regressor_extra [E,V] / joint_map)
     -> dict of numpy arrays in the layout poco_smpl_model wants (include/poco_b200.h): coordinate-major vertex arrays
-    padded to a multiple of 128, shape and pose directions stacked into one [217,3,vp] table, the joint regressor
+    padded to a multiple of 128, shape and pose directions stacked into one [224,3,vp] table (217 rows + zero rows), the joint regressor
     folded through the shape blend (vertices2joints is linear), the extra regressor as CSR."""
     f8 = np.float64
     vt = np.asarray(model['v_template'], f8)
@@ -169,7 +169,8 @@ def prepare_smpl_model(model):
         out = np.zeros(a.shape[:-1] + (vp,), np.float32)
         out[..., :nv] = a
         return out
-    dirs = np.concatenate([sd.transpose(2, 1, 0), pd.reshape(n_pose, nv, 3).transpose(0, 2, 1)], axis=0)
+    dirs = np.concatenate([sd.transpose(2, 1, 0), pd.reshape(n_pose, nv, 3).transpose(0, 2, 1),
+                           np.zeros((L.SMPL_DIR_ROWS - L.SMPL_BETAS - n_pose, 3, nv))], axis=0)
     ev = np.asarray(model['extra_vertex_ids'] if 'extra_vertex_ids' in model else SMPL_EXTRA_VERTEX_IDS, np.int64)
     if ev.size and (ev.min() < 0 or ev.max() >= nv):
         raise ValueError('extra_vertex_ids out of range')

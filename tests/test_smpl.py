@@ -129,7 +129,7 @@ def emulate_kernels(p, rotmat, betas):
     R = rotmat.astype(f).reshape(n, 216)
     verts = np.zeros((n, nv, 3))
     allj = []
-    dirs, vt, W = p['dirs'].astype(f).reshape(217 * 3 * vp), p['v_template'].astype(f).reshape(3 * vp), p['weights'].astype(f).reshape(24 * vp)
+    dirs, vt, W = p['dirs'].astype(f).reshape(224 * 3 * vp), p['v_template'].astype(f).reshape(3 * vp), p['weights'].astype(f).reshape(24 * vp)
     for b in range(n):
         coef = np.zeros(220)
         coef[:10] = betas[b]
@@ -177,7 +177,7 @@ def emulate_kernels(p, rotmat, betas):
 def test_prepared_layout_reproduces_the_oracle():
     m = model(3, nv=300)                    # (small mesh: the emulation is a python loop)
     p = S.prepare_smpl_model(m)
-    assert p['vp'] == 384 and p['dirs'].shape == (217, 3, 384) and p['weights'].shape == (24, 384)
+    assert p['vp'] == 384 and p['dirs'].shape == (224, 3, 384) and not p['dirs'][217:].any() and p['weights'].shape == (24, 384)
     assert not p['dirs'][:, :, 300:].any() and not p['weights'][:, 300:].any()
     d = inputs(2, seed=8)
     v, j = emulate_kernels(p, d['rotmat'], d['shape'])
