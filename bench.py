@@ -81,13 +81,13 @@ class ClockSampler:
 
 
 def build_inputs(preset, B, device):
-    from oracle import synth_ckpt as S
+    from synth import ckpt as S
     return S.synthetic_batch(B, 1, device)
 
 
 def load_model_and_sd(preset):
     import numpy as np
-    from oracle import synth_ckpt as S
+    from synth import ckpt as S
     from poco_b200 import POCO
     gd = os.path.join(ROOT, 'tests', 'golden')
     meta = json.load(open(os.path.join(gd, f'spec_{preset}.json')))
@@ -107,7 +107,7 @@ def cpu_forward_fn(preset):
     import torch
     from oracle import poco_oracle as O
     from oracle import ref_loader as R
-    from oracle import synth_ckpt as S
+    from synth import ckpt as S
     gd = os.path.join(ROOT, 'tests', 'golden')
     meta = json.load(open(os.path.join(gd, f'spec_{preset}.json')))
     sd = S.synth_state_dict(S.template_from_spec(meta, 0), 0, np.load(os.path.join(gd, f'calib_{preset}.npz')))
@@ -250,9 +250,9 @@ def run_gpu_arm(args):
 
     model, sd, meta = load_model_and_sd(preset)
     if args.with_smpl:      # mesh stage on the device inside the e2e leg (seeded stand-in for the licensed model)
-        from oracle import smpl_oracle
+        from synth import smpl_model
         from poco_b200.smpl import DeviceSmplStage
-        model.smpl = DeviceSmplStage(model.head_name, smpl_oracle.synthetic_model(0))
+        model.smpl = DeviceSmplStage(model.head_name, smpl_model.synthetic_model(0))
     model = model.to(dev).eval()
     batch = build_inputs(preset, B, dev)
     clocks = ClockSampler(local)

@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from oracle import crop_oracle as C  # noqa: E402  (synthetic frame / boxes only)
+from synth import frames as C  # noqa: E402
 from poco_b200 import crop_batch  # noqa: E402
 
 fr = torch.from_numpy(C.synthetic_frame(5, 1080, 1920)).cuda()

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from oracle import smpl_oracle as O  # noqa: E402  (synthetic model only)
+from synth import smpl_model as O  # noqa: E402
 from poco_b200 import smpl as S  # noqa: E402
 from test_smpl import inputs  # noqa: E402
 

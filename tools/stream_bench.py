@@ -12,7 +12,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from common import build_model  # noqa: E402
-from oracle import crop_oracle as C  # noqa: E402  (synthetic frames / boxes only)
+from synth import frames as C  # noqa: E402
 from poco_b200 import StreamRunner  # noqa: E402
 
 D = int(sys.argv[1]) if len(sys.argv) > 1 else 8

@@ -14,7 +14,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from oracle import poco_oracle as O  # noqa: E402
-from oracle import synth_ckpt as S  # noqa: E402
+from synth import ckpt as S  # noqa: E402
 
 preset = sys.argv[1] if len(sys.argv) > 1 else 'cliff_w32'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
