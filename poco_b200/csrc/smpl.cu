@@ -100,6 +100,42 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(poco_smpl d) {
     }
 }
 
+// Stages the blend coefficients and relative transforms of a CTA's 8 crops in shared memory.  All global loads of a
+// thread are issued before its first shared-memory store (two L2 round trips instead of one per element: the
+// element-wise loop spent a third of the kernel here, profiles/r01d_ncu_full_smpl_summary.csv).  Kept out of line so
+// its temporaries do not weigh on the register allocation of the blend loop.
+static __device__ __noinline__ void smpl_stage_crops(const float* __restrict__ scratch, int b0, int nb,
+                                                     float (*sCoef)[kCB], float (*sA)[kJ * 12]) {
+    constexpr int kItC = kCB * kRows / 128, kItA = kCB * kJ * 12 / 128;
+    static_assert(kCB * kRows % 128 == 0 && kCB * kJ * 12 % 128 == 0, "staging loops are whole");
+    {
+        float tc[kItC];
+#pragma unroll
+        for (int it = 0; it < kItC; ++it) {
+            const int i = threadIdx.x + it * 128, cb = i / kRows, k = i - cb * kRows;
+            tc[it] = (cb < nb && k < kCoef) ? scratch[(size_t)(b0 + cb) * POCO_SMPL_SCRATCH_FLOATS + k] : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < kItC; ++it) {
+            const int i = threadIdx.x + it * 128, cb = i / kRows, k = i - cb * kRows;
+            sCoef[k][cb] = tc[it];
+        }
+    }
+    {
+        float ta[kItA];
+#pragma unroll
+        for (int it = 0; it < kItA; ++it) {
+            const int i = threadIdx.x + it * 128, cb = i / (kJ * 12), e = i - cb * (kJ * 12);
+            ta[it] = cb < nb ? scratch[(size_t)(b0 + cb) * POCO_SMPL_SCRATCH_FLOATS + kOffA + e] : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < kItA; ++it) {
+            const int i = threadIdx.x + it * 128, cb = i / (kJ * 12), e = i - cb * (kJ * 12);
+            sA[cb][e] = ta[it];
+        }
+    }
+}
+
 // VP != 0: the padded vertex count is a compile-time constant (6912 for the published 6890-vertex model), so the 24
 // loads of a group are one base register + immediate offsets; VP == 0: any model, strides from poco_smpl_model.vp.
 template <int VP>
@@ -108,14 +144,7 @@ __global__ void __launch_bounds__(128) smpl_skin_kernel(poco_smpl d) {
     __shared__ __align__(16) float sA[kCB][kJ * 12];
     const int b0 = blockIdx.y * kCB;
     const int nb = min(kCB, d.n - b0);
-    for (int i = threadIdx.x; i < kCB * kRows; i += 128) {
-        const int cb = i / kRows, k = i - cb * kRows;
-        sCoef[k][cb] = (cb < nb && k < kCoef) ? d.scratch[(size_t)(b0 + cb) * POCO_SMPL_SCRATCH_FLOATS + k] : 0.f;
-    }
-    for (int i = threadIdx.x; i < kCB * kJ * 12; i += 128) {
-        const int cb = i / (kJ * 12), e = i - cb * (kJ * 12);
-        sA[cb][e] = cb < nb ? d.scratch[(size_t)(b0 + cb) * POCO_SMPL_SCRATCH_FLOATS + kOffA + e] : 0.f;
-    }
+    smpl_stage_crops(d.scratch, b0, nb, sCoef, sA);
     __syncthreads();
     const int vp = VP ? VP : d.model.vp;
     const int v = blockIdx.x * 128 + threadIdx.x;       // (vp is a multiple of 128; padded vertices hold zeros)
