@@ -34,6 +34,86 @@ def test_ctypes_structs_match_header_sizes():
     assert _lib.Op.u.offset == 8
 
 
+def test_ctypes_layout_matches_header_field_by_field(tmp_path):
+    """include/poco_b200.h is compiled as plain C99 (the ABI must not need a C++ compiler) and every struct's size and
+    every field's offset is compared with the ctypes mirror in poco_b200/_lib.py"""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    pairs = [('poco_act', _lib.Act), ('poco_conv', _lib.Conv), ('poco_conv_chain', _lib.ConvChain),
+             ('poco_pack_image', _lib.PackImage), ('poco_fuse_sum', _lib.FuseSum), ('poco_upsample2x', _lib.Upsample2x),
+             ('poco_maxpool', _lib.MaxPool), ('poco_avgpool', _lib.AvgPool), ('poco_unpack', _lib.Unpack),
+             ('poco_linear', _lib.Linear), ('poco_copy2d', _lib.Copy2d), ('poco_rot6d', _lib.Rot6d),
+             ('poco_pare_head', _lib.PareHead), ('poco_realnvp', _lib.RealNVP), ('poco_crop', _lib.Crop),
+             ('poco_uncert_post', _lib.UncertPost), ('poco_smpl_model', _lib.SmplModel), ('poco_smpl', _lib.Smpl),
+             ('poco_sync', _lib.Sync), ('poco_op', _lib.Op)]
+    cname = lambda f: {'in_': 'in'}.get(f, f)      # noqa: E731  (`in` is a Python keyword)
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "poco_b200.h"', 'int main(void) {']
+    expect = []
+    for c, t in pairs:
+        lines.append(f'printf("%zu\\n", sizeof({c}));')
+        expect.append((f'sizeof({c})', ctypes.sizeof(t)))
+        for f, _ in t._fields_:
+            lines.append(f'printf("%zu\\n", offsetof({c}, {cname(f)}));')
+            expect.append((f'offsetof({c}, {cname(f)})', getattr(t, f).offset))
+    for m, v in (('POCO_MAX_FUSE_INPUTS', _lib.MAX_FUSE_INPUTS), ('POCO_MAX_CHAIN', _lib.MAX_CHAIN),
+                 ('POCO_ACT_GUARD_BYTES', _lib.ACT_GUARD_BYTES), ('POCO_SMPL_SCRATCH_FLOATS', _lib.SMPL_SCRATCH_FLOATS),
+                 ('POCO_SMPL_DIR_ROWS', _lib.SMPL_DIR_ROWS), ('POCO_OP_SMPL', _lib.OP_SMPL), ('POCO_OP_CONV_CHAIN', _lib.OP_CONV_CHAIN)):
+        lines.append(f'printf("%zu\\n", (size_t){m});')
+        expect.append((m, v))
+    lines += ['return 0; }']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)],
+                   check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert len(got) == len(expect)
+    bad = [(name, want, g) for (name, want), g in zip(expect, got) if want != g]
+    assert not bad, bad
+
+
+def test_every_op_rejects_malformed_descriptors_before_touching_the_gpu():
+    """error behaviour of the C ABI (include/poco_b200.h): non-zero return + poco_last_error(), never a throw or a
+    launch.  Zeroed descriptors for every op kind, then a few op-specific violations."""
+    lib = _lib.lib()
+    kinds = [_lib.PackImage, _lib.Conv, _lib.ConvChain, _lib.FuseSum, _lib.Upsample2x, _lib.MaxPool, _lib.AvgPool,
+             _lib.Unpack, _lib.Linear, _lib.Copy2d, _lib.Rot6d, _lib.PareHead, _lib.RealNVP, _lib.Crop, _lib.UncertPost,
+             _lib.Smpl]
+    assert {_lib._KIND_OF_TYPE[t] for t in kinds} == set(_lib._KIND_OF_TYPE.values())
+    n0 = _lib.kernel_launches()
+    for t in kinds:
+        assert lib.poco_run_op(ctypes.byref(_lib.make_op(t())), None) == 1, t.__name__
+        assert lib.poco_last_error(), t.__name__
+    op = _lib.Op()
+    op.kind = 99
+    assert lib.poco_run_op(ctypes.byref(op), None) == 1 and b'unknown op kind' in lib.poco_last_error()
+    with pytest.raises(_lib.PocoError, match='unknown op kind'):
+        _lib.run_op(op, 0)
+    plan = ctypes.c_void_p()
+    assert lib.poco_plan_create(ctypes.byref(op), 1, ctypes.byref(plan)) == 1
+    assert lib.poco_plan_create(None, 0, ctypes.byref(plan)) == 1
+    # SMPL stage: the padded vertex count must be a multiple of 128 and the joint table must fit
+    buf = ctypes.create_string_buffer(64)
+    a = ctypes.addressof(buf)
+    m = _lib.SmplModel(a, a, a, a, a, a, a, a, a, a, a, 6890, 6890, 21, 9, 49, 0)
+    d = _lib.Smpl(m, a, a, a, 0, 0, 0, 0, 0, 4, 0, 0, 224, 5000.0, 0, a, a, a, a, a, 0)
+    assert lib.poco_run_op(ctypes.byref(_lib.make_op(d)), None) == 1 and b'multiple of 128' in lib.poco_last_error()
+    d.model.vp = 6912
+    d.model.n_extra_vertex = 40
+    assert lib.poco_run_op(ctypes.byref(_lib.make_op(d)), None) == 1 and b'too many joints' in lib.poco_last_error()
+    d.model.n_extra_vertex = 21
+    d.cliff = 1                                 # CLIFF cameras without the box metadata
+    assert lib.poco_run_op(ctypes.byref(_lib.make_op(d)), None) == 1 and b'cliff' in lib.poco_last_error()
+    # crop: non-positive bbox scale, oversized crop
+    c = _lib.Crop(a, 1080, 1920, a, 4, 224, 0.0, 0, a, 0, 0, 0, 0, 0)
+    assert lib.poco_run_op(ctypes.byref(_lib.make_op(c)), None) == 1 and b'scale' in lib.poco_last_error()
+    c.scale, c.crop = 1.2, 4096
+    assert lib.poco_run_op(ctypes.byref(_lib.make_op(c)), None) == 1 and b'geometry' in lib.poco_last_error()
+    assert _lib.kernel_launches() == n0, 'a rejected descriptor must not launch anything'
+
+
 @pytest.mark.parametrize('preset', PRESETS)
 def test_state_dict_contract(preset):
     """same names / shapes as the reference (spec_<preset>.json was dumped from pocolib.models.POCO)"""
