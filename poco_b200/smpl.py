@@ -1,20 +1,20 @@
-"""Host-side SMPL mesh stage of POCO.forward (reference smpl_head.py:36-83, smplcam_head.py:27-96).
+"""SMPL mesh stage of POCO.forward (reference smpl_head.py:36-83, smplcam_head.py:27-96).
 
-Per the north star this stage stays host-side PyTorch.  Its arithmetic lives in the un-vendored
-`smplx==0.1.28` package plus licence-gated model files (data/smpl, data/J_regressor_extra.npy), none
-of which are available here, so the stage is *injectable*:
+The stage's LBS arithmetic lives in the un-vendored `smplx==0.1.28` package plus licence-gated model files
+(data/smpl, data/J_regressor_extra.npy); neither ships with the reference tree.  The stage is therefore *injectable*
+and `make_smpl_stage` picks, in this order:
 
-  * when `smplx` and the model files are present, `SmplStage` runs the real LBS (same calls as the
-    reference) and the camera conversions below;
-  * otherwise `StubSmplStage` returns zero meshes with the right keys / shapes so POCO.forward keeps
-    its dict contract (parity for smpl_* keys is unpinned and excluded from the 1e-3 gate).
+  * `DeviceSmplStage` -- the whole stage (LBS with pose2rot=False, the wrapper's 49 joints, both camera conversions,
+    projection) as three CUDA kernels behind one C-ABI call (poco_smpl_run, poco_b200/csrc/smpl.cu), from model arrays
+    handed in as data (`POCO(..., smpl_model=...)`; `load_smpl_model` reads an .npz or the official .pkl without
+    chumpy).  Needs no smplx and has no CPU path;
+  * `SmplStage` -- smplx's own LBS (same calls as the reference) + the torch camera conversions below, when smplx
+    and its files are installed but no arrays were given;
+  * `StubSmplStage` -- zero meshes with the reference's keys / shapes so POCO.forward keeps its dict contract.
 
-The camera conversions are in-tree reference math and are implemented here in plain torch.
-
-`DeviceSmplStage` runs the whole stage -- LBS, the wrapper's 49 joints, cameras, projection -- as
-three CUDA kernels (poco_b200/csrc/smpl.cu) from model arrays handed in as data (`load_smpl_model` reads an .npz or
-the official .pkl); it is what `make_smpl_stage` picks whenever model arrays are available, needs no smplx, and has
-no CPU path.
+Parity: the camera conversions and the projection are in-tree reference math (pinned by tests/test_smpl.py to
+outputs of the reference functions); the LBS restates smplx's published algorithm -- unpinned, excluded from the
+1e-3 gate.
 """
 import os
 
