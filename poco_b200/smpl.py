@@ -271,11 +271,14 @@ class DeviceSmplStage(nn.Module):
 
 def make_smpl_stage(head_name, img_res=224, model=None):
     """model arrays given (or data/smpl/SMPL_NEUTRAL.pkl readable) -> DeviceSmplStage (CUDA); else smplx's LBS when
-    that package and its files exist; else the stub."""
-    if model is None and os.path.exists(os.path.join(SMPL_MODEL_DIR, 'SMPL_NEUTRAL.pkl')):
+    that package and its files exist; else the stub (with a warning: its meshes are zeros)."""
+    import warnings
+    pkl = os.path.join(SMPL_MODEL_DIR, 'SMPL_NEUTRAL.pkl')
+    if model is None and os.path.exists(pkl):
         try:
             model = load_smpl_model()
-        except Exception:                               # noqa: BLE001  (unreadable pickle: fall through to smplx)
+        except Exception as e:                          # noqa: BLE001  (unreadable pickle: say so, then try smplx)
+            warnings.warn(f'poco_b200: could not read {pkl} ({type(e).__name__}: {e}); trying smplx', stacklevel=2)
             model = None
     if model is not None:
         return DeviceSmplStage(head_name, model, img_res)
@@ -283,6 +286,9 @@ def make_smpl_stage(head_name, img_res=224, model=None):
         import smplx  # noqa: F401
         if os.path.isdir(SMPL_MODEL_DIR) and os.path.exists(JOINT_REGRESSOR_TRAIN_EXTRA):
             return SmplStage(head_name, img_res)
-    except Exception:
+    except Exception:                                   # noqa: BLE001  (smplx absent or its files unreadable)
         pass
+    warnings.warn('poco_b200: no SMPL model (pass smpl_model=..., or provide data/smpl + data/J_regressor_extra.npy): '
+                  'smpl_vertices / smpl_joints3d / smpl_joints2d are zeros; pose, shape, camera and confidence outputs '
+                  'are unaffected', stacklevel=2)
     return StubSmplStage(head_name, img_res)
