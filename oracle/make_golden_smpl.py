@@ -56,6 +56,8 @@ def main():
     out.update(img_w=img_w.numpy(), img_h=img_h.numpy(), center=center.numpy(), scale=scale.numpy(), focal=focal.numpy(),
                cliff_full_t=full_t.numpy(), cliff_joints2d=j2d.numpy(),
                cliff_cam_t=G.convert_weak_perspective_to_perspective(cam).numpy())
+    import pocolib.core.constants as K
+    out['joint_map'] = np.array([K.JOINT_MAP[n] for n in K.JOINT_NAMES], np.int32)      # smpl_head.py:17 (constants.py:15-93)
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, os.path.getsize(OUT), 'bytes')
 

@@ -98,7 +98,8 @@ class SmplStage(nn.Module):
         self.smpl = smplx.SMPL(SMPL_MODEL_DIR, create_transl=False)
         self.register_buffer('J_regressor_extra',
                              torch.tensor(np.load(JOINT_REGRESSOR_TRAIN_EXTRA), dtype=torch.float32))
-        self.joint_map = joint_map      # constants.JOINT_MAP order of the reference (49 joints)
+        # [constants.JOINT_MAP[n] for n in constants.JOINT_NAMES] (smpl_head.py:17-20): 49 of the 54 joints
+        self.joint_map = list(joint_map) if joint_map is not None else SMPL_JOINT_MAP
 
     def _joints(self, out):
         extra = torch.einsum('bik,ji->bjk', out.vertices, self.J_regressor_extra)

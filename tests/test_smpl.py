@@ -95,6 +95,12 @@ def test_oracle_joints_selection():
     np.testing.assert_allclose(J[:, 27], np.einsum('bik,i->bk', v, m['J_regressor_extra'][0].astype(np.float64)))  # 45
 
 
+def test_joint_map_is_the_reference_one():
+    ref = np.load(GOLD)['joint_map']
+    np.testing.assert_array_equal(ref, O.JOINT_MAP)
+    np.testing.assert_array_equal(ref, S.SMPL_JOINT_MAP)
+
+
 def test_oracle_cameras_match_the_reference_functions():
     g = np.load(GOLD)
     cam, joints = g['cam'], g['joints'].astype(np.float64)
