@@ -111,3 +111,9 @@ for a, b in zip(edges[:-1], edges[1:]):
     e = run(lambda i, a=a, b=b: (h16, h16) if a <= i < b else (split, split))
     sh = (cum[b - 1] - (cum[a - 1] if a else 0)) * 100
     print(f'| {a}..{b - 1} | {sh:.1f} % | ' + ' | '.join(f'{e[k]:.1e}' for k in KEYS) + ' |', flush=True)
+
+print('\n| parity-mode candidates: split on layers [0, k), fp16 from k on | share of FLOPs split | pred_pose | pred_shape | pred_cam | var_pose | MMA work |')
+print('|---|---|---|---|---|---|---|')
+for k in (15, 40, 183, 250, 280, 307):
+    e = run(lambda i, k=k: (split, split) if i < k else (h16, h16))
+    print(f'| k = {k} | {cum[k - 1] * 100:.1f} % | ' + ' | '.join(f'{e[x]:.1e}' for x in KEYS) + f' | {1 + 2 * cum[k - 1]:.2f}x |', flush=True)
