@@ -98,7 +98,7 @@ for frac in (0.25, 0.5, 0.75):
 # finer sweep: where along the depth is the error injected?  (split on layers [a, b), fp16 elsewhere)
 print('\n| split-precision window (layers) | share of FLOPs | pred_pose | pred_shape | pred_cam | var_pose |')
 print('|---|---|---|---|---|---|')
-edges = [0, 2, 15, 40, 72, 120, 183, 250, 307, n]
+edges = sorted({0, 2, n} | {max(2, int(round(n * q))) for q in (0.05, 0.13, 0.23, 0.39, 0.59, 0.80, 0.987)})
 for a, b in zip(edges[:-1], edges[1:]):
     e = run(lambda i, a=a, b=b: (split, split) if a <= i < b else (h16, h16))
     sh = (cum[b - 1] - (cum[a - 1] if a else 0)) * 100
@@ -114,6 +114,6 @@ for a, b in zip(edges[:-1], edges[1:]):
 
 print('\n| parity-mode candidates: split on layers [0, k), fp16 from k on | share of FLOPs split | pred_pose | pred_shape | pred_cam | var_pose | MMA work |')
 print('|---|---|---|---|---|---|---|')
-for k in (15, 40, 183, 250, 280, 307):
+for k in sorted({max(2, int(round(n * q))) for q in (0.05, 0.13, 0.59, 0.80, 0.90, 0.987)}):
     e = run(lambda i, k=k: (split, split) if i < k else (h16, h16))
     print(f'| k = {k} | {cum[k - 1] * 100:.1f} % | ' + ' | '.join(f'{e[x]:.1e}' for x in KEYS) + f' | {1 + 2 * cum[k - 1]:.2f}x |', flush=True)
