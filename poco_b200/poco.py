@@ -356,6 +356,11 @@ class POCO(nn.Module):
         return out
 
     def forward(self, batch):
+        if 'is_train' in batch:
+            # the reference switches the uncertainty / flow heads to their training behaviour on this key
+            # (poco_head.py:102, nf_head.py:85: gt-pose conditioning, log_phi from the flow); not built here
+            raise L.PocoError("poco_b200 implements the inference path only: batch carries 'is_train' "
+                              "(use flow_context / flow_log_prob for the RealNVP terms)")
         head_output = self.hot_path(batch)
         if self.head_name == 'cliff':
             smpl_output = self.smpl(

@@ -145,6 +145,8 @@ def test_constructor_errors_and_no_cpu_path():
         m({'img': torch.zeros(1, 3, 224, 224)})            # CPU tensors: there is no fallback
     with pytest.raises(KeyError):
         m({})
+    with pytest.raises(PocoError, match='is_train'):       # training branches (poco_head.py:102, nf_head.py:85) are not built
+        m({'img': torch.zeros(1, 3, 224, 224), 'is_train': True})
 
 
 def test_fold_and_pack_weights():
