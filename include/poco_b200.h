@@ -28,6 +28,10 @@ typedef struct poco_act {
     void* data;           /* fp16, plane 0 / padded pixel 0 */
     int64_t plane_stride; /* pixels per plane: N*(H+2)*(W+2) */
     int32_t C, N, H, W;   /* channels (multiple of 8), crops, unpadded height / width */
+    void* lo;             /* NULL: fp16 mode.  Split-precision ("parity") mode: a second fp16 tensor of the same
+                           * geometry (same plane_stride, zero halo, guards) holding the rounding residual, so that
+                           * the value of an element is  float(data[i]) + float(lo[i])  (~22 significant bits).
+                           * Every op that reads / writes a poco_act honours it; all tensors of one op must agree. */
 } poco_act;
 
 /* conv + folded BatchNorm + optional residual add + optional ReLU.
@@ -35,7 +39,11 @@ typedef struct poco_act {
  * BasicBlock/Bottleneck (backbone/hrnet.py:42-58, :79-99; resnet.py:100-121), transition and fuse
  * convs (hrnet.py:198-240, :345-384), output-stage convs (hrnet.py:437-450), the PARE conv branches
  * (head/pare_head.py:468-491).  weight: fp16 [kh*kw][Cin/8][Cout][8] with the BN scale folded in,
- * bias: fp32 [Cout] (BN shift + conv bias).  Cin, Cout multiples of 16. */
+ * bias: fp32 [Cout] (BN shift + conv bias).  Cin, Cout multiples of 16.
+ * Split-precision mode (in.lo != NULL; the reference computes in fp32, pocolib/core/config.py:154 PRECISION=32):
+ * weight holds TWO such tensors back to back, W_hi = fp16(W) then W_lo = fp16(W - W_hi), and the kernel accumulates
+ * x_hi W_hi + x_lo W_hi + x_hi W_lo in one fp32 MMA chain (3x the tensor work, operands good to ~2^-22), adds
+ * residual + residual_lo in fp32 and stores out = fp16(y), out.lo = fp16(y - out). */
 typedef struct poco_conv {
     poco_act in, out;
     const void* weight;
@@ -49,6 +57,7 @@ typedef struct poco_conv {
     int32_t wfmt; /* weight layout: 0 = [kh*kw][Cin/8][Cout][8]; 1 = "dx in N" for 3x3 / stride 1 / pad 1 with
                    * Cout in {32, 64}: [kh][Cin/8][kw*Cout][8] (column s*Cout + co of filter row r) -- the three
                    * horizontal taps share one MMA, a third of the shared-memory operand reads */
+    const void* residual_lo; /* split-precision mode: rounding residual of `residual` (same plane stride), else NULL */
 } poco_conv;
 
 /* A chain of convolutions of ONE geometry (3x3/s1/p1 or 1x1/s1, Cin == Cout) executed by one persistent

@@ -20,14 +20,16 @@ SMPL_JOINTS, SMPL_BETAS, SMPL_SCRATCH_FLOATS, SMPL_DIR_ROWS = 24, 10, 580, 224
 
 class Act(C.Structure):
     _fields_ = [('data', C.c_void_p), ('plane_stride', C.c_int64),
-                ('C', C.c_int32), ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32)]
+                ('C', C.c_int32), ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('lo', C.c_void_p)]
 
 
 class Conv(C.Structure):
     _fields_ = [('in_', Act), ('out', Act), ('weight', C.c_void_p), ('bias', C.c_void_p),
                 ('residual', C.c_void_p), ('res_plane_stride', C.c_int64),
                 ('kh', C.c_int32), ('kw', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
-                ('relu', C.c_int32), ('impl', C.c_int32), ('max_ctas', C.c_int32), ('wfmt', C.c_int32)]
+                ('relu', C.c_int32), ('impl', C.c_int32), ('max_ctas', C.c_int32), ('wfmt', C.c_int32),
+                ('residual_lo', C.c_void_p)]
 
 
 class ConvChain(C.Structure):

@@ -411,8 +411,8 @@ def poco_head_layers(nfeat, num_neurons, uncert_inp_type, n_out=24):
     return pre, layers
 
 
-def poco_head_spec(b, nfeat, num_neurons, uncert_inp_type, prefix='uncert_head.'):
-    pre, layers = poco_head_layers(nfeat, num_neurons, uncert_inp_type)
+def poco_head_spec(b, nfeat, num_neurons, uncert_inp_type, prefix='uncert_head.', n_out=24):
+    pre, layers = poco_head_layers(nfeat, num_neurons, uncert_inp_type, n_out)
     for name, i, o in pre + layers:
         b.param_only_linear(prefix + name, i, o)
 

@@ -59,7 +59,7 @@ static int res_ring_base(bool half) {
     static const int v = [] { const char* e = getenv("POCO_B200_RES_RING"); return e ? std::max(1, atoi(e)) : kResRing; }();
     return half ? std::min(v, 2) : v;
 }
-static int ring_bytes_for(int item_planes, bool half) { return 2 * (kOutRing + res_ring_base(half)) * item_planes * kPlaneTile; }
+static int ring_bytes_for(int item_planes, bool half, int sp = 1) { return 2 * (kOutRing + res_ring_base(half)) * item_planes * kPlaneTile * sp; }
 
 enum { MODE_LINEAR = 0, MODE_GATHER = 1 };
 
@@ -74,6 +74,10 @@ struct ChainSeg {
     const float* bias;
     int relu;
     int pad_;
+    // split-precision mode (SPLIT instantiations, single segment): the rounding-residual tensors
+    const __half* in_lo;
+    __half* out_lo;
+    const __half* res_lo;
 };
 
 struct ConvTcParams {
@@ -195,13 +199,18 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // of a tile); tiles advance by 126 pixels so that rows 0 and 127 of a tile are never outputs.
 // MINB = 2: the "half" configuration (two CTAs per SM), which needs the register cap of __launch_bounds__(.., 2);
 // the one-CTA instantiations keep their registers (capping them cost the wide-N epilogue 20 %).
-template <int MODE, int IPL, bool DXN, int MINB = 1>
+// SPLIT: split-precision ("parity") mode.  Every activation is a pair of fp16 tensors (hi, lo = x - hi) and the weights
+// are [W_hi][W_lo]; a K chunk lands as kc/8 hi planes followed by kc/8 lo planes, the issuer runs the same straight-line
+// MMA sequence three times into one accumulator -- (x_hi, W_hi), (x_lo, W_hi), (x_hi, W_lo) -- and the epilogue adds
+// residual hi + lo in fp32 and stores hi = fp16(y), lo = fp16(y - hi).  Everything else (roles, barriers, rings) is shared.
+template <int MODE, int IPL, bool DXN, int MINB = 1, bool SPLIT = false>
 __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
     const int res_ring_n = p.res_ring;
     constexpr int ipl = IPL;                            // output planes (8 columns each) per epilogue work item
-    const int warp_ring_bytes = (kOutRing + res_ring_n) * ipl * 512;      // per epilogue warp: out ring + residual ring
+    constexpr int SP = SPLIT ? 2 : 1;
+    const int warp_ring_bytes = (kOutRing + res_ring_n) * ipl * 512 * SP;      // per epilogue warp: out ring + residual ring
     uint8_t* w_res = smem + kHeaderBytes + 8 * warp_ring_bytes;
     uint8_t* stage0 = w_res + p.w_res_bytes * p.w_bufs;
     const int stage_bytes = p.a_stage_bytes + p.w_stage_bytes;
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         const uint32_t dst = smem_u32(w_res) + uint32_t(b) * uint32_t(p.w_res_bytes);
         const uint32_t bar = smem_u32(&hdr->w_ready[b]);
         mbar_arrive_expect_tx(bar, uint32_t(p.w_res_bytes));
-        const int total = taps * cin8;
+        const int total = taps * cin8 * SP;                      // (split mode: the W_lo tensor follows W_hi, slab for slab)
         const int group = whole_n ? min(total, 64) : 1;          // <= 64 slabs (<= 256 KB) per copy
         for (int i = 0; i < total; i += group) {
             const int g = min(group, total - i);
@@ -294,6 +303,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
     };
     // Resident weights of a chain: segment s uses buffer s % w_bufs.  w_ready[b] completes once per
     // segment that uses buffer b; w_free[b] completes when the MMAs of such a segment have retired.
+    const size_t w_lo_off = size_t(taps) * cin8 * w_n * 8;        // split mode: elements from W_hi to W_lo
     auto wbuf_of = [&](int s) { return p.w_bufs == 2 ? (s & 1) : 0; };
     auto wuse_of = [&](int s) { return p.w_bufs == 2 ? (s >> 1) : s; };      // how many earlier segments used that buffer
 
@@ -348,14 +358,23 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                     if (elect_one()) {
                         const uint32_t bar = smem_u32(&hdr->full[slot]);
                         const bool skip_a = (p.debug & 4) != 0;
-                        const uint32_t tx = (skip_a ? 0u : uint32_t(planes_per_chunk) * copy_bytes) +
+                        const uint32_t tx = (skip_a ? 0u : uint32_t(planes_per_chunk * SP) * copy_bytes) +
                                             (p.w_resident ? 0u : uint32_t(p.w_stage_bytes));
                         mbar_arrive_expect_tx(bar, tx);
                         const uint32_t st = smem_u32(stage0 + size_t(slot) * stage_bytes);
-                        const __half* src = sg.in + ((long long)(c * planes_per_chunk) * p.in_plane + q0) * 8;
+                        const long long src_off = ((long long)(c * planes_per_chunk) * p.in_plane + q0) * 8;
+                        const __half* src = sg.in + src_off;
                         for (int jj = 0; jj < planes_per_chunk && !skip_a; ++jj, src += p.in_plane * 8)
                             bulk_g2s(st + uint32_t(jj) * p.a_plane_bytes, src, copy_bytes, bar);
-                        if (!p.w_resident) load_stage_weights(wg, st + p.a_stage_bytes, bar, 0, taps, c);
+                        if (SPLIT) {        // the lo planes of the chunk land behind its hi planes
+                            const __half* srl = sg.in_lo + src_off;
+                            for (int jj = 0; jj < planes_per_chunk && !skip_a; ++jj, srl += p.in_plane * 8)
+                                bulk_g2s(st + uint32_t(planes_per_chunk + jj) * p.a_plane_bytes, srl, copy_bytes, bar);
+                        }
+                        if (!p.w_resident) {
+                            load_stage_weights(wg, st + p.a_stage_bytes, bar, 0, taps, c);
+                            if (SPLIT) load_stage_weights(wg + w_lo_off, st + p.a_stage_bytes + (p.w_stage_bytes >> 1), bar, 0, taps, c);
+                        }
                     }
                     __syncwarp();
                 }
@@ -379,6 +398,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         // (zero-fill outside the image), so up to (kGatherLag+1) x 18 loads are in flight per thread.
         pdl_wait();
         const __half* in0 = p.seg[0].in;
+        const __half* in0_lo = p.seg[0].in_lo;
         const int r = threadIdx.x;                 // row of the tile
         const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
         const int Wp_i = p.Win + 2, HpWp_i = (p.Hin + 2) * Wp_i;
@@ -418,6 +438,19 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                             cp_async16(st + uint32_t(tt) * 4096u + 2048u, src + p.in_plane * 8, ok);
                         }
                     }
+                    if (SPLIT) {            // the lo planes of all taps of the group land behind the hi block
+                        const __half* srl0 = in0_lo + (long long)(c * 2) * p.in_plane * 8;
+                        const uint32_t stl = st + uint32_t(TG) * 4096u;
+#pragma unroll
+                        for (int tt = 0; tt < 9; ++tt) {
+                            if (tt < TG) {
+                                const bool ok = (okmask >> tt) & 1u;
+                                const __half* src = srl0 + pix[tt];
+                                cp_async16(stl + uint32_t(tt) * 4096u, src, ok);
+                                cp_async16(stl + uint32_t(tt) * 4096u + 2048u, src + p.in_plane * 8, ok);
+                            }
+                        }
+                    }
                     cp_async_commit();
                     if (it >= uint32_t(kGatherLag)) {
                         cp_async_wait<kGatherLag>();
@@ -448,8 +481,9 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                         if (elect_one()) {
                             const uint32_t bar = smem_u32(&hdr->full[slot]);
                             mbar_arrive_expect_tx(bar, uint32_t(p.w_stage_bytes));
-                            load_stage_weights(wg, smem_u32(stage0 + size_t(slot) * stage_bytes) + p.a_stage_bytes, bar,
-                                               tg * TG, tg * TG + TG, c);
+                            const uint32_t ws = smem_u32(stage0 + size_t(slot) * stage_bytes) + p.a_stage_bytes;
+                            load_stage_weights(wg, ws, bar, tg * TG, tg * TG + TG, c);
+                            if (SPLIT) load_stage_weights(wg + w_lo_off, ws + (p.w_stage_bytes >> 1), bar, tg * TG, tg * TG + TG, c);
                         }
                         __syncwarp();
                     }
@@ -514,7 +548,17 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                             const uint32_t a_lo = ((a_base + uint32_t(p.halo) * 16u) >> 4) | a_lbo;
                             const uint32_t b_lo = (w0 >> 4) | b_lbo;
                             if (!(p.debug & 2)) {
-#define POCO_ISSUE(T, K) issue_linear<T, K>(d_tmem, a_lo, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, acc)
+#define POCO_ISSUE(T, K)                                                                                                    \
+    do {                                                                                                                    \
+        if (SPLIT) {        /* x_lo W_hi + x_hi W_lo first: the tensor core truncates every accumulation to the magnitude */ \
+                            /* of the running sum, so the 2^-11-sized correction terms go in while it is still small     */ \
+            issue_linear<T, K>(d_tmem, a_lo2, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, acc);               \
+            issue_linear<T, K>(d_tmem, a_lo, b_lo2, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, 1u);                \
+        }                                                                                                                   \
+        issue_linear<T, K>(d_tmem, a_lo, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, SPLIT ? 1u : acc);       \
+    } while (0)
+                                const uint32_t a_lo2 = a_lo + ((uint32_t(planes_per_chunk) * uint32_t(p.a_plane_bytes)) >> 4);
+                                const uint32_t b_lo2 = b_lo + ((p.w_resident ? uint32_t(p.w_res_bytes) : uint32_t(p.w_stage_bytes)) >> 5);
                                 if (taps == 9) {
                                     switch (ksteps) {
                                         case 1: POCO_ISSUE(9, 1); break;
@@ -544,12 +588,23 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                             const uint32_t w0 = p.w_resident ? w_res_u32 + uint32_t(tg * TG * cin8 + c * 2) * slab_bytes : w_stage;
                             const uint32_t a_lo = (a_base >> 4) | a_lbo;
                             const uint32_t b_lo = (w0 >> 4) | b_lbo;
+                            const uint32_t a_lo2 = a_lo + uint32_t(TG) * 256u;       // lo block: TG taps x 4 KB behind the hi block
+                            const uint32_t b_lo2 = b_lo + ((p.w_resident ? uint32_t(p.w_res_bytes) : uint32_t(p.w_stage_bytes)) >> 5);
+#define POCO_ISSUE_G(T)                                                                     \
+    do {                                                                                    \
+        if (SPLIT) {                                                                        \
+            issue_gather<T>(d_tmem, a_lo2, b_lo, w_tap_stride, desc_hi, idesc, acc);        \
+            issue_gather<T>(d_tmem, a_lo, b_lo2, w_tap_stride, desc_hi, idesc, 1u);         \
+        }                                                                                   \
+        issue_gather<T>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, SPLIT ? 1u : acc); \
+    } while (0)
                             switch (TG) {
-                                case 9: issue_gather<9>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
-                                case 7: issue_gather<7>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
-                                case 3: issue_gather<3>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
-                                default: issue_gather<1>(d_tmem, a_lo, b_lo, w_tap_stride, desc_hi, idesc, acc); break;
+                                case 9: POCO_ISSUE_G(9); break;
+                                case 7: POCO_ISSUE_G(7); break;
+                                case 3: POCO_ISSUE_G(3); break;
+                                default: POCO_ISSUE_G(1); break;
                             }
+#undef POCO_ISSUE_G
                         }
                         }
                         umma_commit(smem_u32(&hdr->empty[slot]));      // smem slot free once these MMAs retire
@@ -593,7 +648,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         const int odd = items & 1;
         auto k_first = [&](uint32_t tl_) { return (half + (odd ? int(tl_ & 1u) : 0)) & 1; };
         const bool skip_store = (p.debug & 8) != 0;
-        constexpr uint32_t kSlot = IPL * 512;           // one item slice of this warp: IPL planes x 32 rows x 16 B
+        constexpr uint32_t kSlot = IPL * 512 * SP;      // one item slice of this warp: IPL planes x 32 rows x 16 B (split: hi planes, then lo planes)
         uint8_t* res_ring = smem + kHeaderBytes + ew * warp_ring_bytes;
         unsigned long long* res_full = hdr->res_full + ew * kMaxResRing;
         const uint32_t rr_n = uint32_t(res_ring_n);
@@ -607,6 +662,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         int pf_j = 0, pf_k = k_first(uint32_t(pf_s * my_tiles));
         uint32_t pf_tl = uint32_t(pf_s * my_tiles);
         const __half* pf_res = pf_s < n_segs ? p.seg[pf_s].res : nullptr;
+        const __half* pf_res_lo = SPLIT ? p.seg[0].res_lo : nullptr;
         uint32_t pf_issued = 0;
         auto prefetch_residual = [&](int cur_seg, uint32_t upto) {      // elected lane: top the ring up to `upto` items
             while (pf_issued < upto) {
@@ -637,11 +693,17 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                 }
                 const uint32_t rows = uint32_t(left < 32 ? left : 32);
                 const int planes = min(ipl, (n_out >> 3) - item * ipl);
-                mbar_arrive_expect_tx(bar, uint32_t(planes) * rows * 16u);
-                const __half* src = pf_res + ((long long)(plane0 + item * ipl) * p.res_plane + qw) * 8;
+                mbar_arrive_expect_tx(bar, uint32_t(planes * SP) * rows * 16u);
+                const long long res_off = ((long long)(plane0 + item * ipl) * p.res_plane + qw) * 8;
+                const __half* src = pf_res + res_off;
                 const uint32_t dst = smem_u32(res_ring) + slot * kSlot;
                 for (int pl = 0; pl < planes; ++pl, src += p.res_plane * 8)
                     bulk_g2s(dst + uint32_t(pl) * 512u, src, rows * 16u, bar);
+                if (SPLIT) {
+                    const __half* srl = pf_res_lo + res_off;
+                    for (int pl = 0; pl < planes; ++pl, srl += p.res_plane * 8)
+                        bulk_g2s(dst + uint32_t(IPL + pl) * 512u, srl, rows * 16u, bar);
+                }
             }
         };
         // position of a row inside its crop, advanced incrementally: tile -> next tile of the unit, and last
@@ -775,7 +837,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                     }
                     const uint32_t rslot = g % rr_n;
                     if (has_res) MBAR_WAIT(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
-                    __half* outp = sg.out + ((long long)(plane0 + item * ipl) * p.out_plane + qw + lane) * 8;
+                    const long long out_off = ((long long)(plane0 + item * ipl) * p.out_plane + qw + lane) * 8;
+                    __half* outp = sg.out + out_off;
                     const uint8_t* rb = res_ring + rslot * kSlot + lane * 16;
 #pragma unroll
                     for (int pl = 0; pl < IPL; ++pl) {
@@ -799,6 +862,16 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                                 f[2 * i] += t2.x;
                                 f[2 * i + 1] += t2.y;
                             }
+                            if (SPLIT) {
+                                const uint4 l4 = *reinterpret_cast<const uint4*>(rb + (IPL + pl) * 512);
+                                const uint32_t rl[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 t2 = unpack_half2(rl[i]);
+                                    f[2 * i] += t2.x;
+                                    f[2 * i + 1] += t2.y;
+                                }
+                            }
                         }
                         if (relu == 1) {
 #pragma unroll
@@ -809,6 +882,17 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                             o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
                             o4.z = pack_half2(f[4], f[5]); o4.w = pack_half2(f[6], f[7]);
                             *reinterpret_cast<uint4*>(outp + (long long)pl * p.out_plane * 8) = o4;
+                            if (SPLIT) {        // lo = fp16(y - hi)
+                                const uint32_t oh[4] = {o4.x, o4.y, o4.z, o4.w};
+                                uint32_t ol[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 h2 = unpack_half2(oh[i]);
+                                    ol[i] = pack_half2(f[2 * i] - h2.x, f[2 * i + 1] - h2.y);
+                                }
+                                *reinterpret_cast<uint4*>(sg.out_lo + out_off + (long long)pl * p.out_plane * 8) =
+                                    make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                            }
                         }
                     }
                     if (has_res) {
@@ -866,6 +950,11 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
                "output geometry does not match the convolution");
     POCO_CHECK((kTileM + out.W + 3) * 16 <= POCO_ACT_GUARD_BYTES, "tile halo exceeds the activation guard");
 
+    const bool split = in.lo != nullptr;          // split-precision ("parity") mode: see the SPLIT template parameter
+    const int sp = split ? 2 : 1;
+    POCO_CHECK(!split || (out.lo != nullptr && n_segs == 1 && d->wfmt == 0), "split precision: out.lo missing, or a chain / dx-in-N conv");
+    POCO_CHECK(split || out.lo == nullptr, "out.lo given but in.lo is null");
+    POCO_CHECK(!split || !d->residual || d->residual_lo, "split precision: residual_lo missing");
     ConvTcParams p{};
     p.n_segs = n_segs;
     p.flags = flags;
@@ -883,6 +972,9 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         p.seg[i].w = static_cast<const __half*>(c.weight);
         p.seg[i].bias = c.bias;
         p.seg[i].relu = c.relu;
+        p.seg[i].in_lo = static_cast<const __half*>(c.in.lo);
+        p.seg[i].out_lo = static_cast<__half*>(c.out.lo);
+        p.seg[i].res_lo = static_cast<const __half*>(c.residual_lo);
         if (c.residual) {
             POCO_CHECK(!any_res || p.res_plane == c.res_plane_stride, "chain: residual plane strides differ");
             p.res_plane = c.res_plane_stride;
@@ -918,7 +1010,8 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
 
     // N blocking: largest multiple-of-16 divisor of Cout that is <= 256 (dx-in-N: the three column groups)
     int n_tile = 0;
-    for (int t = std::min(256, out.C); t >= 16; t -= 16)
+    // (split mode: N <= 128, so that a K chunk of [hi | lo] activations plus [W_hi | W_lo] still leaves two stages)
+    for (int t = std::min(split ? 128 : 256, out.C); t >= 16; t -= 16)
         if (out.C % t == 0) { n_tile = t; break; }
     if (dxn) n_tile = 3 * out.C;
     POCO_CHECK(n_tile > 0 && n_tile <= 256, "no valid N tile");
@@ -935,7 +1028,7 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     // other lanes' full-size CTAs no empty SM (A/B inside the HR modules: 19.5 k vs 19.8 k crops/s).
     static const int half_mode = [] { const char* e = getenv("POCO_B200_HALF"); return e ? atoi(e) : 1; }();   // 0 off, 1 outside lanes, 2 always
     const bool half_stride1 = d->stride == 1 && in.H == out.H && in.W == out.W && d->kh == 3 && d->pad == 1;
-    bool half = half_mode > 0 && (half_mode == 2 || d->max_ctas == 0) && !dxn && n_segs == 1 && n_tile <= 64 && half_stride1;
+    bool half = half_mode > 0 && (half_mode == 2 || d->max_ctas == 0) && !dxn && !split && n_segs == 1 && n_tile <= 64 && half_stride1;
     int smem_budget = kSmemBudget;
     auto set_half = [&](bool h) {
         half = h;
@@ -955,7 +1048,8 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     for (int i = 1; i < n_segs; ++i) POCO_CHECK(segs[i].wfmt == 0, "chain: dx-in-N weights are not supported");
     POCO_CHECK(n_segs == 1 || (linear && out.W + 3 <= kTileM), "chain: only 3x3/s1/p1 and 1x1/s1 convolutions chain");
     int budget = 0;         // set per attempt below
-    const int w_total = taps * in.C * n_tile * 2;
+    const int w_total = taps * in.C * n_tile * 2 * sp;
+    const int w_res_cap = split ? 160 * 1024 : 112 * 1024;      // largest weight block kept resident
 
     // M grouping: G adjacent tiles of a 3x3 conv are fetched as ONE run per plane, so the (W+3)-pixel halo is
     // paid once per G tiles (a 128-pixel tile of a 56-wide image reads 246 pixels: 1.9x the data it owns;
@@ -998,7 +1092,7 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     for (int want4 = (mode == MODE_LINEAR && (dxn || (n_tile >= 64 && taps == 1) || n_tile == 32) ? 1 : 0); want4 >= (dxn ? 1 : 0) && !found; --want4) {
         p.item_planes = want4 ? 4 : 2;
         const int items_here = ((dxn ? out.C : n_tile) + p.item_planes * 8 - 1) / (p.item_planes * 8);
-        budget = smem_budget - kHeaderBytes - ring_bytes_for(p.item_planes, half);
+        budget = smem_budget - kHeaderBytes - ring_bytes_for(p.item_planes, half || split, sp);
         (void)items_here;
         if (mode == MODE_LINEAR) {
             const int kcs[4] = {64, 48, 32, 16};
@@ -1006,12 +1100,12 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
             static const int max_wbufs = [] { const char* e = getenv("POCO_CHAIN_WBUFS"); return e ? atoi(e) : 2; }();
             for (int wb = (n_segs > 1 ? std::min(2, max_wbufs) : 1); wb >= 0 && !found; --wb) {
                 const int resident = wb > 0;
-                if (resident && w_total > 112 * 1024) continue;
+                if (resident && w_total > w_res_cap) continue;
                 for (int ki = 0; ki < 4 && !found; ++ki) {
                     const int kc = kcs[ki];
                     if (in.C % kc != 0) continue;
-                    const int a_stage = (kc / 8) * p.a_plane_bytes;
-                    const int w_stage = resident ? 0 : taps * kc * n_tile * 2;
+                    const int a_stage = (kc / 8) * p.a_plane_bytes * sp;
+                    const int w_stage = resident ? 0 : taps * kc * n_tile * 2 * sp;
                     const int avail = budget - wb * w_total;
                     const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
                     if (stages < (want4 ? 4 : 2)) continue;
@@ -1029,12 +1123,12 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
             // gather: K chunk = 16 channels (2 planes); a stage holds `tap_group` taps (all / one row / one)
             const int groups[3] = {taps <= 9 ? taps : d->kw, d->kw, 1};
             for (int resident = 1; resident >= 0 && !found; --resident) {
-                if (resident && w_total > 112 * 1024) continue;
+                if (resident && w_total > w_res_cap) continue;
                 for (int gi = 0; gi < 3 && !found; ++gi) {
                     const int tg = groups[gi];
                     if (taps % tg != 0) continue;
-                    const int a_stage = tg * 4096;
-                    const int w_stage = resident ? 0 : tg * 16 * n_tile * 2;
+                    const int a_stage = tg * 4096 * sp;
+                    const int w_stage = resident ? 0 : tg * 16 * n_tile * 2 * sp;
                     const int avail = budget - (resident ? w_total : 0);
                     const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
                     if (stages < (want4 ? 4 : kGatherLag + 1)) continue;
@@ -1059,10 +1153,10 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     p.flag_expect = (p.epi_items >= 2 ? 8 : 4) * n_blocks;
     // slabs are n_tile*16 bytes (a multiple of 256): the resident region needs no padding and
     // w_res_bytes is both the region size and the mbarrier transaction count
-    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes, half) + size_t(p.w_res_bytes) * p.w_bufs + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
-    p.res_ring = res_ring_base(half);
+    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes, half || split, sp) + size_t(p.w_res_bytes) * p.w_bufs + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
+    p.res_ring = res_ring_base(half || split);
     if (any_res && p.res_ring > 0) {       // spend spare shared memory on a deeper residual prefetch ring
-        const int item_bytes = p.item_planes * kPlaneTile;
+        const int item_bytes = p.item_planes * kPlaneTile * sp;
         const int extra = int((size_t(smem_budget) - smem) / (2 * item_bytes));
         const int base = p.res_ring;
         p.res_ring = std::min(kMaxResRing, base + std::max(0, extra));
@@ -1090,8 +1184,16 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         cfg.blockDim = dim3(threads);
         return cudaLaunchKernelEx(&cfg, kernel, pk);
     };
-    static std::once_flag once4[7];
-    if (half && p.item_planes == 2)
+    static std::once_flag once4[11];
+    if (split && mode == MODE_LINEAR && p.item_planes == 2)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 1, true>, once4[7], Roles<MODE_LINEAR>::kThreads));
+    else if (split && mode == MODE_LINEAR)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false, 1, true>, once4[8], Roles<MODE_LINEAR>::kThreads));
+    else if (split && p.item_planes == 2)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 2, false, 1, true>, once4[9], Roles<MODE_GATHER>::kThreads));
+    else if (split)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 4, false, 1, true>, once4[10], Roles<MODE_GATHER>::kThreads));
+    else if (half && p.item_planes == 2)
         POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 2>, once4[5], Roles<MODE_LINEAR>::kThreads));
     else if (half)
         POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false, 2>, once4[6], Roles<MODE_LINEAR>::kThreads));

@@ -3,6 +3,8 @@
 // forward pass; they are written for correctness-first fp32 parity and few launches.
 #include <algorithm>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -151,10 +153,20 @@ __global__ void __launch_bounds__(128) pare_logits_kernel(poco_pare_head d) {
     const int x = int(idx % W), y = int((idx / W) % H), n = int(idx / ((long long)W * H));
     const long long pix = (long long)n * (H + 2) * (W + 2) + (long long)(y + 1) * (W + 2) + (x + 1);
     const __half* base = static_cast<const __half*>(d.part_feats.data);
+    const __half* base_lo = static_cast<const __half*>(d.part_feats.lo);       // split-precision mode: value = hi + lo
     float f[PC];
 #pragma unroll
     for (int pl = 0; pl < PC / 8; ++pl)
         unpack8h(*reinterpret_cast<const uint4*>(base + ((long long)pl * d.part_feats.plane_stride + pix) * 8), f + pl * 8);
+    if (base_lo != nullptr) {
+#pragma unroll
+        for (int pl = 0; pl < PC / 8; ++pl) {
+            float l[8];
+            unpack8h(*reinterpret_cast<const uint4*>(base_lo + ((long long)pl * d.part_feats.plane_stride + pix) * 8), l);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[pl * 8 + i] += l[i];
+        }
+    }
     const long long hw = (long long)H * W;
     for (int j = 0; j < 25; ++j) {
         float acc = b[j];
@@ -177,9 +189,13 @@ __host__ __device__ inline int pare_num_chunks(int H, int W) { const int r = par
 constexpr int kPartial = PJ + PJ + PJ * PC;
 
 // K2: flash-style partial softmax pooling over one chunk of rows of one crop
+// SPLIT (split-precision mode): the features are hi + lo fp16 pairs and are staged as fp32 in dynamic shared memory
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) pare_pool_kernel(poco_pare_head d) {
     __shared__ float a[PCHUNK][PJ];
-    __shared__ __align__(16) __half fs[PCHUNK][PC + 8];
+    __shared__ __align__(16) __half fs[SPLIT ? 1 : PCHUNK][PC + 8];
+    extern __shared__ __align__(16) float fsf_raw[];
+    float(*fsf)[PC + 4] = reinterpret_cast<float(*)[PC + 4]>(fsf_raw);      // [PCHUNK][PC + 4], SPLIT only
     __shared__ float mloc[PJ];
     const int H = d.smpl_feats.H, W = d.smpl_feats.W;
     const int rows = pare_chunk_rows(H, W), nch = pare_num_chunks(H, W);
@@ -199,8 +215,18 @@ __global__ void __launch_bounds__(256) pare_pool_kernel(poco_pare_head d) {
         const int pl = e / npx, px = e % npx;
         const int y = y0 + px / W, x = px % W;
         const long long pix = (long long)n * (H + 2) * (W + 2) + (long long)(y + 1) * (W + 2) + (x + 1);
-        *reinterpret_cast<uint4*>(&fs[px][pl * 8]) =
-            *reinterpret_cast<const uint4*>(base + ((long long)pl * d.smpl_feats.plane_stride + pix) * 8);
+        const uint4 hv = *reinterpret_cast<const uint4*>(base + ((long long)pl * d.smpl_feats.plane_stride + pix) * 8);
+        if (SPLIT) {
+            const uint4 lv = *reinterpret_cast<const uint4*>(static_cast<const __half*>(d.smpl_feats.lo) +
+                                                             ((long long)pl * d.smpl_feats.plane_stride + pix) * 8);
+            float h[8], l[8];
+            unpack8h(hv, h);
+            unpack8h(lv, l);
+            *reinterpret_cast<float4*>(&fsf[px][pl * 8]) = make_float4(h[0] + l[0], h[1] + l[1], h[2] + l[2], h[3] + l[3]);
+            *reinterpret_cast<float4*>(&fsf[px][pl * 8 + 4]) = make_float4(h[4] + l[4], h[5] + l[5], h[6] + l[6], h[7] + l[7]);
+        } else {
+            *reinterpret_cast<uint4*>(&fs[px][pl * 8]) = hv;
+        }
     }
     __syncthreads();
     float* part = d.scratch + (long long)blockIdx.x * kPartial;
@@ -226,8 +252,16 @@ __global__ void __launch_bounds__(256) pare_pool_kernel(poco_pare_head d) {
     const int cg = threadIdx.x & 31, jg = threadIdx.x >> 5;
     float acc[3][4] = {};
     for (int px = 0; px < npx; ++px) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(&fs[px][cg * 4]);
-        const float2 f01 = unpack_half2(raw.x), f23 = unpack_half2(raw.y);
+        float2 f01, f23;
+        if (SPLIT) {
+            const float4 v4 = *reinterpret_cast<const float4*>(&fsf[px][cg * 4]);
+            f01 = make_float2(v4.x, v4.y);
+            f23 = make_float2(v4.z, v4.w);
+        } else {
+            const uint2 raw = *reinterpret_cast<const uint2*>(&fs[px][cg * 4]);
+            f01 = unpack_half2(raw.x);
+            f23 = unpack_half2(raw.y);
+        }
 #pragma unroll
         for (int jj = 0; jj < 3; ++jj) {
             const float w = a[px][jg * 3 + jj];
@@ -481,7 +515,15 @@ extern "C" int poco_pare_head_run(const poco_pare_head* d, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     pare_logits_kernel<<<blocks_for((long long)N * H * W, 128), 128, 0, s>>>(*d);
     POCO_LAUNCHED();
-    pare_pool_kernel<<<N * pare_num_chunks(H, W), 256, 0, s>>>(*d);
+    POCO_CHECK((d->part_feats.lo != nullptr) == (d->smpl_feats.lo != nullptr), "pare_head: both feature tensors must share one precision mode");
+    if (d->smpl_feats.lo != nullptr) {
+        constexpr int kDyn = PCHUNK * (PC + 4) * int(sizeof(float));
+        static std::once_flag once;
+        std::call_once(once, [] { cudaFuncSetAttribute(pare_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDyn); });
+        pare_pool_kernel<true><<<N * pare_num_chunks(H, W), 256, kDyn, s>>>(*d);
+    } else {
+        pare_pool_kernel<false><<<N * pare_num_chunks(H, W), 256, 0, s>>>(*d);
+    }
     POCO_LAUNCHED();
     pare_final_kernel<<<N, 256, 0, s>>>(*d);
     POCO_LAUNCHED();

@@ -15,8 +15,9 @@ struct Act {
     __half* data;
     long long plane;
     int C, N, H, W;
+    __half* lo;         // split-precision mode: rounding residual tensor (value = data + lo), else nullptr
 };
-inline Act mk(const poco_act& a) { return Act{static_cast<__half*>(a.data), a.plane_stride, a.C, a.N, a.H, a.W}; }
+inline Act mk(const poco_act& a) { return Act{static_cast<__half*>(a.data), a.plane_stride, a.C, a.N, a.H, a.W, static_cast<__half*>(a.lo)}; }
 
 __device__ __forceinline__ long long pix_index(const Act& a, int n, int y, int x) {
     return (long long)n * (a.H + 2) * (a.W + 2) + (long long)(y + 1) * (a.W + 2) + (x + 1);
@@ -40,13 +41,35 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     v.z = pack_half2(f[4], f[5]); v.w = pack_half2(f[6], f[7]);
     return v;
 }
+// value of 8 channels of one pixel: hi (+ lo in split-precision mode; the branch is uniform per launch)
+__device__ __forceinline__ void ld8f(const Act& a, int plane, long long pix, float* f) {
+    unpack8(ld16(a, plane, pix), f);
+    if (a.lo != nullptr) {
+        float l[8];
+        unpack8(*reinterpret_cast<const uint4*>(a.lo + ((long long)plane * a.plane + pix) * 8), l);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += l[i];
+    }
+}
+// store fp32 values as hi = fp16(v) (+ lo = fp16(v - hi))
+__device__ __forceinline__ void st8f(const Act& a, int plane, long long pix, const float* f) {
+    const uint4 h = pack8(f);
+    st16(a, plane, pix, h);
+    if (a.lo != nullptr) {
+        float hf[8], l[8];
+        unpack8(h, hf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) l[i] = f[i] - hf[i];
+        *reinterpret_cast<uint4*>(a.lo + ((long long)plane * a.plane + pix) * 8) = pack8(l);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // debug convolution (CUDA cores, fp32 accumulate): one thread = one output pixel x 8 output channels
 // ------------------------------------------------------------------------------------------------
 __global__ void conv_ref_kernel(Act in, Act out, const __half* __restrict__ w, const float* __restrict__ bias,
-                                const __half* __restrict__ res, long long res_plane, int kh, int kw, int stride,
-                                int pad, int relu) {
+                                const __half* __restrict__ res, const __half* __restrict__ res_lo, long long res_plane,
+                                int kh, int kw, int stride, int pad, int relu) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long npix = (long long)out.N * out.H * out.W;
     if (idx >= npix) return;
@@ -62,12 +85,19 @@ __global__ void conv_ref_kernel(Act in, Act out, const __half* __restrict__ w, c
         const long long ip = pix_index(in, n, yi, xi);
         for (int c8 = 0; c8 < cin8; ++c8) {
             float a[8];
-            unpack8(ld16(in, c8, ip), a);
+            ld8f(in, c8, ip, a);
             const uint4* wp = reinterpret_cast<const uint4*>(w + ((long long)(t * cin8 + c8) * out.C + co8 * 8) * 8);
+            const uint4* wl = wp + (long long)kh * kw * cin8 * out.C;      // split mode: W_lo follows W_hi
 #pragma unroll
             for (int o = 0; o < 8; ++o) {
                 float wf[8];
                 unpack8(__ldg(wp + o), wf);
+                if (in.lo != nullptr) {
+                    float wlo[8];
+                    unpack8(__ldg(wl + o), wlo);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) wf[i] += wlo[i];
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[o] = fmaf(a[i], wf[i], acc[o]);
             }
@@ -83,12 +113,17 @@ __global__ void conv_ref_kernel(Act in, Act out, const __half* __restrict__ w, c
         unpack8(*reinterpret_cast<const uint4*>(res + ((long long)co8 * res_plane + op) * 8), r);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += r[i];
+        if (res_lo != nullptr) {
+            unpack8(*reinterpret_cast<const uint4*>(res_lo + ((long long)co8 * res_plane + op) * 8), r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += r[i];
+        }
     }
     if (relu == 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
     }
-    st16(out, co8, op, pack8(acc));
+    st8f(out, co8, op, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -124,8 +159,9 @@ __global__ void pack_image_kernel(const float* __restrict__ img, Act out) {
     const float* src = img + (long long)n * 3 * hw + (long long)y * out.W + x;
     float f[8] = {src[0], src[hw], src[2 * hw], 0.f, 0.f, 0.f, 0.f, 0.f};
     const long long op = pix_index(out, n, y, x);
-    st16(out, 0, op, pack8(f));
-    for (int pl = 1; pl < (out.C >> 3); ++pl) st16(out, pl, op, make_uint4(0, 0, 0, 0));
+    st8f(out, 0, op, f);
+    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int pl = 1; pl < (out.C >> 3); ++pl) st8f(out, pl, op, z);
 }
 
 // im2col of the 3x3 / stride-2 / pad-1 stem window: 27 taps x channels -> 32 fp16 channels per output pixel
@@ -152,7 +188,7 @@ __global__ void __launch_bounds__(256) pack_stem_kernel(const float* __restrict_
     for (int k = 27; k < 32; ++k) f[k] = 0.f;
     const long long op = pix_index(out, n, y, x);
 #pragma unroll
-    for (int pl = 0; pl < 4; ++pl) st16(out, pl, op, pack8(f + pl * 8));
+    for (int pl = 0; pl < 4; ++pl) st8f(out, pl, op, f + pl * 8);
 }
 
 struct FuseArgs {
@@ -169,10 +205,14 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseArgs a, RowMap m, int
     const long long po = pix_index(a.out, n, y, x);
     const int pl0 = blockIdx.y * planes_per_thread;
     for (int pl = pl0; pl < pl0 + planes_per_thread; ++pl) {
-        uint4 v[POCO_MAX_FUSE_INPUTS];
+        uint4 v[POCO_MAX_FUSE_INPUTS], vl[POCO_MAX_FUSE_INPUTS];
+        const bool split = a.out.lo != nullptr;
 #pragma unroll
         for (int k = 0; k < POCO_MAX_FUSE_INPUTS; ++k)
-            if (k < a.n_in) v[k] = ld16(a.in[k], pl, pin[k]);
+            if (k < a.n_in) {
+                v[k] = ld16(a.in[k], pl, pin[k]);
+                if (split) vl[k] = *reinterpret_cast<const uint4*>(a.in[k].lo + ((long long)pl * a.in[k].plane + pin[k]) * 8);
+            }
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int k = 0; k < POCO_MAX_FUSE_INPUTS; ++k)
@@ -181,12 +221,17 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseArgs a, RowMap m, int
                 unpack8(v[k], f);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] += f[i];
+                if (split) {
+                    unpack8(vl[k], f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+                }
             }
         if (a.relu) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
         }
-        st16(a.out, pl, po, pack8(acc));
+        st8f(a.out, pl, po, acc);
     }
 }
 
@@ -203,6 +248,17 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(Act in, Act out, float 
     const long long po = pix_index(out, n, y, x);
     const int pl0 = blockIdx.y * planes_per_thread;
     for (int pl = pl0; pl < pl0 + planes_per_thread; pl += 2) {       // two planes = eight 16-byte loads in flight
+        if (in.lo != nullptr) {         // split-precision mode: interpolate hi + lo in fp32
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float a[8], b[8], c[8], d[8], o[8];
+                ld8f(in, pl + q, p00, a); ld8f(in, pl + q, p01, b); ld8f(in, pl + q, p10, c); ld8f(in, pl + q, p11, d);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+                st8f(out, pl + q, po, o);
+            }
+            continue;
+        }
         uint4 v[2][4];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -234,11 +290,11 @@ __global__ void maxpool_kernel(Act in, Act out) {
             const int yi = 2 * y + dy, xi = 2 * x + dx;
             if (yi < 0 || yi >= in.H || xi < 0 || xi >= in.W) continue;
             float f[8];
-            unpack8(ld16(in, pl, pix_index(in, n, yi, xi)), f);
+            ld8f(in, pl, pix_index(in, n, yi, xi), f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
         }
-    st16(out, pl, pix_index(out, n, y, x), pack8(m));
+    st8f(out, pl, pix_index(out, n, y, x), m);
 }
 
 // one warp per (crop, plane): mean over H*W of 8 channels
@@ -251,7 +307,7 @@ __global__ void avgpool_kernel(Act in, float* __restrict__ out, long long ld) {
     const int hw = in.H * in.W;
     for (int i = lane; i < hw; i += 32) {
         float f[8];
-        unpack8(ld16(in, pl, pix_index(in, n, i / in.W, i % in.W)), f);
+        ld8f(in, pl, pix_index(in, n, i / in.W, i % in.W), f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] += f[k];
     }
@@ -271,7 +327,7 @@ __global__ void unpack_kernel(Act in, float* __restrict__ out, int c_valid) {
     const int pl = blockIdx.y;
     const int x = int(idx % in.W), y = int((idx / in.W) % in.H), n = int(idx / ((long long)in.W * in.H));
     float f[8];
-    unpack8(ld16(in, pl, pix_index(in, n, y, x)), f);
+    ld8f(in, pl, pix_index(in, n, y, x), f);
     const long long hw = (long long)in.H * in.W;
     for (int i = 0; i < 8; ++i) {
         const int c = pl * 8 + i;
@@ -289,19 +345,22 @@ int check_act(const poco_act& a, const char* what) {
     POCO_CHECK(a.N > 0 && a.H > 0 && a.W > 0, std::string(what) + ": empty tensor");
     POCO_CHECK(a.plane_stride >= int64_t(a.N) * (a.H + 2) * (a.W + 2), std::string(what) + ": plane stride too small");
     POCO_CHECK((reinterpret_cast<uintptr_t>(a.data) & 15) == 0, std::string(what) + ": data must be 16-byte aligned");
+    POCO_CHECK((reinterpret_cast<uintptr_t>(a.lo) & 15) == 0, std::string(what) + ": lo must be 16-byte aligned");
     return 0;
 }
 
 int conv_ref_launch(const poco_conv* d, cudaStream_t s) {
     POCO_CHECK(d->in.N == d->out.N, "batch mismatch");
+    POCO_CHECK((d->in.lo != nullptr) == (d->out.lo != nullptr) && (!d->in.lo || !d->residual || d->residual_lo),
+               "split precision: in.lo, out.lo and residual_lo must be given together");
     POCO_CHECK((d->in.H + 2 * d->pad - d->kh) / d->stride + 1 == d->out.H &&
                    (d->in.W + 2 * d->pad - d->kw) / d->stride + 1 == d->out.W,
                "output geometry does not match the convolution");
     const long long npix = (long long)d->out.N * d->out.H * d->out.W;
     dim3 grid(blocks_for(npix, 128), d->out.C / 8);
     conv_ref_kernel<<<grid, 128, 0, s>>>(mk(d->in), mk(d->out), static_cast<const __half*>(d->weight), d->bias,
-                                        static_cast<const __half*>(d->residual), d->res_plane_stride, d->kh, d->kw,
-                                        d->stride, d->pad, d->relu);
+                                        static_cast<const __half*>(d->residual), static_cast<const __half*>(d->residual_lo),
+                                        d->res_plane_stride, d->kh, d->kw, d->stride, d->pad, d->relu);
     POCO_LAUNCHED();
     return 0;
 }
@@ -337,6 +396,7 @@ extern "C" int poco_fuse_sum_run(const poco_fuse_sum* d, void* stream) {
     for (int k = 0; k < d->n_in; ++k) {
         if (check_act(d->in[k], "in")) return 1;
         POCO_CHECK(d->in[k].C == d->out.C && d->in[k].N == d->out.N, "fuse input channel/batch mismatch");
+        POCO_CHECK((d->in[k].lo != nullptr) == (d->out.lo != nullptr), "fuse_sum: inputs and output must share one precision mode");
         POCO_CHECK(d->shift[k] >= 0 && (d->in[k].H << d->shift[k]) == d->out.H && (d->in[k].W << d->shift[k]) == d->out.W,
                    "fuse input resolution mismatch");
         a.in[k] = mk(d->in[k]);
@@ -358,6 +418,7 @@ extern "C" int poco_upsample2x_run(const poco_upsample2x* d, void* stream) {
     const float sy = d->out.H > 1 ? float(d->in.H - 1) / float(d->out.H - 1) : 0.f;
     const float sx = d->out.W > 1 ? float(d->in.W - 1) / float(d->out.W - 1) : 0.f;
     POCO_CHECK(d->out.C % 16 == 0 && d->out.W <= 256, "upsample2x: channels must be a multiple of 16 and W <= 256");
+    POCO_CHECK((d->in.lo != nullptr) == (d->out.lo != nullptr), "upsample2x: input and output must share one precision mode");
     const RowMap m = row_map(d->out.N, d->out.H, d->out.W);
     const int planes = d->out.C / 8;
     const int ppt = planes % 4 == 0 ? 4 : 2;
@@ -371,6 +432,7 @@ extern "C" int poco_maxpool_run(const poco_maxpool* d, void* stream) {
     if (check_act(d->in, "in") || check_act(d->out, "out")) return 1;
     POCO_CHECK(d->out.H == (d->in.H + 2 - 3) / 2 + 1 && d->out.W == (d->in.W + 2 - 3) / 2 + 1 && d->out.C == d->in.C,
                "maxpool geometry mismatch");
+    POCO_CHECK((d->in.lo != nullptr) == (d->out.lo != nullptr), "maxpool: input and output must share one precision mode");
     const long long npix = (long long)d->out.N * d->out.H * d->out.W;
     dim3 grid(blocks_for(npix, 256), d->out.C / 8);
     maxpool_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(d->in), mk(d->out));

@@ -20,53 +20,64 @@ BN_EPS = 1e-5
 class ActT:
     """[C/8][N][H+2][W+2][8] fp16 view into a torch buffer (see include/poco_b200.h)."""
 
-    def __init__(self, buf, ptr, C_, N, H, W, plane_stride, cap_planes, root=None):
+    def __init__(self, buf, ptr, C_, N, H, W, plane_stride, cap_planes, root=None, lo_off=0):
         self.buf, self.ptr = buf, ptr
         self.C, self.N, self.H, self.W = C_, N, H, W
         self.plane_stride = plane_stride
         self.cap_planes = cap_planes
         self.root = root or self
+        self.lo_off = lo_off        # split-precision mode: byte offset from the hi tensor to its lo twin (0 = fp16 mode)
+
+    @property
+    def ptr_lo(self):
+        return self.ptr + self.lo_off if self.lo_off else None
 
     def desc(self):
-        return L.Act(self.ptr, self.plane_stride, self.C, self.N, self.H, self.W)
+        return L.Act(self.ptr, self.plane_stride, self.C, self.N, self.H, self.W, self.ptr_lo)
 
     def channels(self, c0, c1):
         """channel-slice view (free torch.cat / torch.split: planes are contiguous)"""
         assert c0 % 8 == 0 and c1 % 8 == 0 and 0 <= c0 < c1 <= self.C
         return ActT(self.buf, self.ptr + (c0 // 8) * self.plane_stride * 16, c1 - c0, self.N, self.H, self.W,
-                    self.plane_stride, 0, self.root)
+                    self.plane_stride, 0, self.root, self.lo_off)
 
     def retype(self, C_):
         """same buffer, fewer channels (pool reuse)"""
         assert C_ % 8 == 0 and C_ // 8 <= self.cap_planes
-        return ActT(self.buf, self.ptr, C_, self.N, self.H, self.W, self.plane_stride, self.cap_planes, None)
+        return ActT(self.buf, self.ptr, C_, self.N, self.H, self.W, self.plane_stride, self.cap_planes, None, self.lo_off)
 
 
-def alloc_act(C_, N, H, W, device):
+def alloc_act(C_, N, H, W, device, split=False):
+    """split=True (split-precision mode): one buffer holds the hi tensor and, behind its own guard, the lo tensor"""
     assert C_ % 8 == 0
     plane = N * (H + 2) * (W + 2)
     guard = L.ACT_GUARD_BYTES // 2
-    buf = torch.zeros(guard + (C_ // 8) * plane * 8 + guard, dtype=torch.float16, device=device)
-    return ActT(buf, buf.data_ptr() + L.ACT_GUARD_BYTES, C_, N, H, W, plane, C_ // 8)
+    one = guard + (C_ // 8) * plane * 8 + guard
+    one = (one + 63) // 64 * 64                 # keep the lo tensor 128-byte aligned like the hi one
+    buf = torch.zeros(one * (2 if split else 1), dtype=torch.float16, device=device)
+    return ActT(buf, buf.data_ptr() + L.ACT_GUARD_BYTES, C_, N, H, W, plane, C_ // 8, None, one * 2 if split else 0)
 
 
-def to_planar(x, c_pad=None):
+def to_planar(x, c_pad=None, split=False):
     """torch reference of the layout (tests / debugging): NCHW float -> ActT on x.device"""
     N, C_, H, W = x.shape
     Cp = c_pad or ((C_ + 7) // 8 * 8)
-    a = alloc_act(Cp, N, H, W, x.device)
-    v = act_view(a)
-    xp = torch.zeros(N, Cp, H, W, dtype=torch.float16, device=x.device)
-    xp[:, :C_] = x.to(torch.float16)
-    v[:, :, 1:H + 1, 1:W + 1, :] = xp.view(N, Cp // 8, 8, H, W).permute(1, 0, 3, 4, 2)
+    a = alloc_act(Cp, N, H, W, x.device, split)
+    hi = x.to(torch.float16)
+    parts = [(hi, False)] + ([((x.float() - hi.float()).to(torch.float16), True)] if split else [])
+    for t, lo in parts:
+        v = act_view(a, lo)
+        xp = torch.zeros(N, Cp, H, W, dtype=torch.float16, device=x.device)
+        xp[:, :C_] = t
+        v[:, :, 1:H + 1, 1:W + 1, :] = xp.view(N, Cp // 8, 8, H, W).permute(1, 0, 3, 4, 2)
     return a
 
 
-def act_view(a):
-    """[C/8, N, H+2, W+2, 8] torch view of an (unsliced) ActT"""
+def act_view(a, lo=False):
+    """[C/8, N, H+2, W+2, 8] torch view of an (unsliced) ActT (lo=True: its rounding-residual twin)"""
     guard = L.ACT_GUARD_BYTES // 2
-    off = (a.ptr - a.buf.data_ptr()) // 2
-    assert off >= guard
+    off = (a.ptr + (a.lo_off if lo else 0) - a.buf.data_ptr()) // 2
+    assert off >= guard and (a.lo_off or not lo)
     n = (a.C // 8) * a.plane_stride * 8
     flat = a.buf[off:off + n]
     return flat.view(a.C // 8, a.plane_stride, 8)[:, :a.N * (a.H + 2) * (a.W + 2)].reshape(
@@ -74,9 +85,11 @@ def act_view(a):
 
 
 def from_planar(a):
-    """ActT -> NCHW float32 torch tensor (tests / debugging)"""
-    v = act_view(a)[:, :, 1:a.H + 1, 1:a.W + 1, :]
-    return v.permute(1, 0, 4, 2, 3).reshape(a.N, a.C, a.H, a.W).float()
+    """ActT -> NCHW float32 torch tensor (tests / debugging); split-precision tensors return hi + lo"""
+    def one(lo):
+        v = act_view(a, lo)[:, :, 1:a.H + 1, 1:a.W + 1, :]
+        return v.permute(1, 0, 4, 2, 3).reshape(a.N, a.C, a.H, a.W).float()
+    return one(False) + one(True) if a.lo_off else one(False)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -95,15 +108,19 @@ def fold_bn(w, conv_bias, bn):
     return w, b
 
 
-def pack_conv_weight(w, cin_pad=None):
-    """[Cout, Cin, kh, kw] f32 -> fp16 [kh*kw][Cin/8][Cout][8] (UMMA no-swizzle K-major B slabs)"""
+def pack_conv_weight(w, cin_pad=None, split=False):
+    """[Cout, Cin, kh, kw] f32 -> fp16 [kh*kw][Cin/8][Cout][8] (UMMA no-swizzle K-major B slabs).
+    split=True (split-precision mode): [2][kh*kw][Cin/8][Cout][8] = W_hi = fp16(W), then W_lo = fp16(W - W_hi)."""
     cout, cin, kh, kw = w.shape
     cp = cin_pad or cin
     if cp != cin:
         w = torch.cat([w, w.new_zeros(cout, cp - cin, kh, kw)], 1)
     assert cp % 16 == 0 and cout % 16 == 0, (cin, cout)
-    p = w.permute(2, 3, 1, 0).reshape(kh * kw, cp // 8, 8, cout).permute(0, 1, 3, 2)
-    return p.contiguous().to(torch.float16)
+    p = w.permute(2, 3, 1, 0).reshape(kh * kw, cp // 8, 8, cout).permute(0, 1, 3, 2).contiguous()
+    hi = p.to(torch.float16)
+    if not split:
+        return hi
+    return torch.stack([hi, (p.float() - hi.float()).to(torch.float16)]).contiguous()
 
 
 def pack_conv_weight_dxn(w):
@@ -146,8 +163,9 @@ class PlanBuilder:
 
     mode = 'plan'
 
-    def __init__(self, sd, N, device, conv_impl=0):
+    def __init__(self, sd, N, device, conv_impl=0, split=False):
         self.sd = sd
+        self.split = bool(split)    # split-precision ("parity") mode: hi + lo fp16 activations and weights everywhere
         self.N = N
         self.device = torch.device(device)
         self.ops = []
@@ -159,7 +177,7 @@ class PlanBuilder:
         self.shares = None      # SM budget per lane inside a fork
         self.num_sms = 148
         self.use_lanes = os.environ.get('POCO_B200_LANES', '1') != '0'
-        self.use_chains = os.environ.get('POCO_B200_CHAINS', '1') != '0'
+        self.use_chains = os.environ.get('POCO_B200_CHAINS', '1') != '0' and not self.split
         self.chain = None       # pending conv descriptors of an open chain
 
     # -- buffers
@@ -174,7 +192,7 @@ class PlanBuilder:
             if best is not None:
                 pool.remove(best)
                 return best.retype(C_) if best.C != C_ else best
-        a = alloc_act(C_, self.N, H, W, self.device)
+        a = alloc_act(C_, self.N, H, W, self.device, self.split)
         self.keep.append(a.buf)
         return a
 
@@ -183,7 +201,8 @@ class PlanBuilder:
         root = a.root
         if root is not a and a.ptr != root.ptr:
             return
-        full = ActT(root.buf, root.ptr, root.cap_planes * 8, root.N, root.H, root.W, root.plane_stride, root.cap_planes)
+        full = ActT(root.buf, root.ptr, root.cap_planes * 8, root.N, root.H, root.W, root.plane_stride, root.cap_planes,
+                    None, root.lo_off)
         lst = self.free_pool.setdefault((self.lane, root.H, root.W), [])
         if all(x.buf is not full.buf for x in lst):
             lst.append(full)
@@ -257,7 +276,7 @@ class PlanBuilder:
         wf, bf = fold_bn(w, None, bnp)
         w1 = wf.permute(0, 2, 3, 1).reshape(cout, 27)               # k = (r*3+s)*3 + c
         w1 = torch.cat([w1, w1.new_zeros(cout, 5)], 1).reshape(cout, 32, 1, 1)
-        wp = pack_conv_weight(w1)
+        wp = pack_conv_weight(w1, split=self.split)
         bf = bf.contiguous()
         self.keep += [wp, bf]
         out = self.act(cout, H // 2, W // 2)
@@ -287,8 +306,9 @@ class PlanBuilder:
             ws.append(wf)
             bs.append(bf)
         pad = k // 2 if pad is None else pad
-        wfmt = 1 if (self.conv_impl == 0 and self.chain is None and x.C == cin and dxn_applies(cin, cout, k, stride, pad)) else 0
-        wp = pack_conv_weight_dxn(torch.cat(ws, 0)) if wfmt else pack_conv_weight(torch.cat(ws, 0), cin_pad=x.C)
+        wfmt = 1 if (self.conv_impl == 0 and self.chain is None and x.C == cin and not self.split and
+                     dxn_applies(cin, cout, k, stride, pad)) else 0
+        wp = pack_conv_weight_dxn(torch.cat(ws, 0)) if wfmt else pack_conv_weight(torch.cat(ws, 0), cin_pad=x.C, split=self.split)
         bf = torch.cat(bs, 0).contiguous()
         self.keep += [wp, bf]
         Ho = (x.H + 2 * pad - k) // stride + 1
@@ -302,7 +322,8 @@ class PlanBuilder:
                    residual.ptr if residual is not None else None,
                    residual.plane_stride if residual is not None else 0,
                    k, k, stride, pad, int(relu), self.conv_impl,
-                   self.shares[self.lane] if self.shares is not None else 0, wfmt)
+                   self.shares[self.lane] if self.shares is not None else 0, wfmt,
+                   residual.ptr_lo if residual is not None else None)
         if self.chain is not None:
             self.chain.append(d)
         else:

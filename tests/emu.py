@@ -32,18 +32,24 @@ class Emu:
         es = torch.empty(0, dtype=dtype).element_size()
         return rem[:rem.numel() // es * es].view(dtype)
 
-    def act(self, a):
-        f = self.flat(a.data, torch.float16)
+    def act(self, a, lo=False):
+        f = self.flat(a.lo if lo else a.data, torch.float16)
         Hp, Wp = a.H + 2, a.W + 2
         return torch.as_strided(f, (a.C // 8, a.N, Hp, Wp, 8), (a.plane_stride * 8, Hp * Wp * 8, Wp * 8, 8, 1))
 
     def act_get(self, a):
-        v = self.act(a)[:, :, 1:a.H + 1, 1:a.W + 1, :]
-        return v.permute(1, 0, 4, 2, 3).reshape(a.N, a.C, a.H, a.W).float()
+        """value of a tensor: hi (+ lo in split-precision mode)"""
+        def one(lo):
+            v = self.act(a, lo)[:, :, 1:a.H + 1, 1:a.W + 1, :]
+            return v.permute(1, 0, 4, 2, 3).reshape(a.N, a.C, a.H, a.W).float()
+        return one(False) + one(True) if a.lo else one(False)
 
     def act_set(self, a, x):
-        v = self.act(a)
-        v[:, :, 1:a.H + 1, 1:a.W + 1, :] = x.to(torch.float16).view(a.N, a.C // 8, 8, a.H, a.W).permute(1, 0, 3, 4, 2)
+        hi = x.to(torch.float16)
+        parts = [(hi, False)] + ([((x.float() - hi.float()).to(torch.float16), True)] if a.lo else [])
+        for t, lo in parts:
+            v = self.act(a, lo)
+            v[:, :, 1:a.H + 1, 1:a.W + 1, :] = t.view(a.N, a.C // 8, 8, a.H, a.W).permute(1, 0, 3, 4, 2)
 
     def mat(self, ptr, rows, cols, ld):
         return torch.as_strided(self.flat(ptr, torch.float32), (rows, cols), (ld, 1))
@@ -74,14 +80,17 @@ class Emu:
             wp = self.flat(d.weight, torch.float16)[:taps * i.C * o.C].view(3, i.C // 8, 3, o.C, 8).float()
             w = wp.permute(3, 1, 4, 0, 2).reshape(o.C, i.C, 3, 3)
         else:
-            wp = self.flat(d.weight, torch.float16)[:taps * i.C * o.C].view(taps, i.C // 8, o.C, 8).float()
+            nw = taps * i.C * o.C
+            wp = self.flat(d.weight, torch.float16)[:nw].view(taps, i.C // 8, o.C, 8).float()
+            if i.lo:        # split-precision mode: W_lo follows W_hi
+                wp = wp + self.flat(d.weight, torch.float16)[nw:2 * nw].view(taps, i.C // 8, o.C, 8).float()
             w = wp.permute(2, 1, 3, 0).reshape(o.C, i.C, d.kh, d.kw)
         b = self.flat(d.bias, torch.float32)[:o.C]
         y = F.conv2d(self.act_get(i), w, b, stride=d.stride, padding=d.pad)
         if d.relu == 2:
             y = F.relu(y)
         if d.residual:
-            r = L.Act(d.residual, d.res_plane_stride, o.C, o.N, o.H, o.W)
+            r = L.Act(d.residual, d.res_plane_stride, o.C, o.N, o.H, o.W, d.residual_lo)
             y = y + self.act_get(r)
         if d.relu == 1:
             y = F.relu(y)

@@ -27,28 +27,30 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def run_conv(x, w, bias, stride=1, pad=None, relu=1, residual=None, impl=0, dxn=False):
+def run_conv(x, w, bias, stride=1, pad=None, relu=1, residual=None, impl=0, dxn=False, split=False):
     """x [N,Cin,H,W], w [Cout,Cin,k,k], bias [Cout] (CPU float) -> [N,Cout,Ho,Wo] float (CPU).
-    Inputs are rounded to fp16 exactly as the engine does."""
+    Inputs are rounded to fp16 exactly as the engine does (split=True: to hi + lo fp16 pairs, the parity mode)."""
     dev = 'cuda'
     N, Cin, H, W = x.shape
     Cout, _, k, _ = w.shape
     pad = k // 2 if pad is None else pad
     cin_p = (Cin + 15) // 16 * 16
-    a = engine.to_planar(x.to(dev), c_pad=cin_p)
+    a = engine.to_planar(x.to(dev), c_pad=cin_p, split=split)
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-    o = engine.alloc_act(Cout, N, Ho, Wo, dev)
-    wp = engine.pack_conv_weight_dxn(w.to(dev).float()) if dxn else engine.pack_conv_weight(w.to(dev).float(), cin_pad=cin_p)
+    o = engine.alloc_act(Cout, N, Ho, Wo, dev, split)
+    wp = engine.pack_conv_weight_dxn(w.to(dev).float()) if dxn else engine.pack_conv_weight(w.to(dev).float(), cin_pad=cin_p, split=split)
     b = bias.to(dev).float().contiguous()
-    r = engine.to_planar(residual.to(dev)) if residual is not None else None
+    r = engine.to_planar(residual.to(dev), split=split) if residual is not None else None
     d = L.Conv(a.desc(), o.desc(), wp.data_ptr(), b.data_ptr(), r.ptr if r is not None else None,
-               r.plane_stride if r is not None else 0, k, k, stride, pad, relu, impl, 0, 1 if dxn else 0)
+               r.plane_stride if r is not None else 0, k, k, stride, pad, relu, impl, 0, 1 if dxn else 0,
+               r.ptr_lo if r is not None else None)
     L.run_op(d, stream())
     sync_or_die()
     out = engine.from_planar(o).cpu()
-    halo = engine.act_view(o)
-    assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
-                 halo[:, :, :, -1].abs().sum()) == 0.0, 'kernel wrote into the zero halo'
+    for lo in ([False, True] if split else [False]):
+        halo = engine.act_view(o, lo)
+        assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
+                     halo[:, :, :, -1].abs().sum()) == 0.0, 'kernel wrote into the zero halo'
     return out
 
 
@@ -61,6 +63,27 @@ def conv_reference(x, w, bias, stride=1, pad=None, relu=1, residual=None):
         y = F.relu(y)
     if residual is not None:
         y = y + residual.half().float()
+    if relu == 1:
+        y = F.relu(y)
+    return y
+
+
+def split16(t):
+    """value a split-precision tensor holds for t: fp16(t) + fp16(t - fp16(t)), as float64"""
+    hi = t.float().half()
+    lo = (t.float() - hi.float()).half()
+    return hi.double() + lo.double()
+
+
+def conv_reference_split(x, w, bias, stride=1, pad=None, relu=1, residual=None):
+    """float64 oracle arithmetic on the hi + lo operand values of the split-precision (parity) mode"""
+    k = w.shape[-1]
+    pad = k // 2 if pad is None else pad
+    y = F.conv2d(split16(x), split16(w), bias.double(), stride=stride, padding=pad)
+    if relu == 2:
+        y = F.relu(y)
+    if residual is not None:
+        y = y + split16(residual)
     if relu == 1:
         y = F.relu(y)
     return y
