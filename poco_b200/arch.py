@@ -179,7 +179,9 @@ def chain_groups(branch, n_branches):
 
 
 def chain_policy(channels):
-    """POCO_B200_CHAIN_MIN_C=<c>: chain the BasicBlocks of branches with at least c channels (default 128)"""
+    """POCO_B200_CHAIN_MIN_C=<c>: chain the BasicBlocks of branches with at least c channels.  Default: never
+    (100000) -- at batch 256 the flag protocol's gpu-scope fences cost what the saved launches give back
+    (profiles/r01b_chain_vs_separate.csv); the chained path is exercised by tests/test_gpu_ops.py only."""
     import os
     return channels >= int(os.environ.get('POCO_B200_CHAIN_MIN_C', '100000'))
 
@@ -195,10 +197,8 @@ def hr_module(b, xs, name, chans, out0=None):
     for i in range(nb):
         b.set_lane(i)
         x = xs[i]
-        # The branch's eight convs share one geometry.  For the low-resolution branches (few tiles per SM,
-        # so the ~8 us launch + pipeline fill of a conv is most of its time) they run as ONE persistent
-        # chained launch; measured at batch 256 (tools/chain_bench.py) the chain wins from 128 channels up
-        # and loses below (the flag protocol's fences cost more than the launches they replace).
+        # The branch's eight convs share one geometry and CAN run as one persistent chained launch
+        # (POCO_B200_CHAIN_MIN_C, off by default: see chain_policy).
         chained = chain_policy(chans[i])
         if chained:
             b.begin_chain()

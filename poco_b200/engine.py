@@ -176,6 +176,8 @@ class PlanBuilder:
         self.lane = 0
         self.shares = None      # SM budget per lane inside a fork
         self.num_sms = 148
+        if self.device.type == 'cuda':      # lane shares are fractions of the real SM count
+            self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.use_lanes = os.environ.get('POCO_B200_LANES', '1') != '0'
         self.use_chains = os.environ.get('POCO_B200_CHAINS', '1') != '0' and not self.split
         self.chain = None       # pending conv descriptors of an open chain
@@ -270,14 +272,16 @@ class PlanBuilder:
         sd = self.sd
         col = self.act(32, H // 2, W // 2)
         self.add(L.PackImage(img.data_ptr(), col.desc(), 1, 0))
-        w = sd[conv + '.weight'].to(self.device)
+        # weight preparation (BN folding, repacking, fp16 cast) runs on the HOST: the only device work of a plan
+        # build is the upload, so the first kernels a fresh process launches are the forward's own
+        w = sd[conv + '.weight'].cpu()
         assert tuple(w.shape) == (cout, 3, 3, 3), (conv, tuple(w.shape))
-        bnp = tuple(sd[bn + s].to(self.device) for s in ('.weight', '.bias', '.running_mean', '.running_var'))
+        bnp = tuple(sd[bn + s].cpu() for s in ('.weight', '.bias', '.running_mean', '.running_var'))
         wf, bf = fold_bn(w, None, bnp)
         w1 = wf.permute(0, 2, 3, 1).reshape(cout, 27)               # k = (r*3+s)*3 + c
         w1 = torch.cat([w1, w1.new_zeros(cout, 5)], 1).reshape(cout, 32, 1, 1)
-        wp = pack_conv_weight(w1, split=self.split)
-        bf = bf.contiguous()
+        wp = pack_conv_weight(w1, split=self.split).to(self.device)
+        bf = bf.contiguous().to(self.device)
         self.keep += [wp, bf]
         out = self.act(cout, H // 2, W // 2)
         d = L.Conv(col.desc(), out.desc(), wp.data_ptr(), bf.data_ptr(), None, 0, 1, 1, 1, 0, 1, self.conv_impl,
@@ -295,21 +299,22 @@ class PlanBuilder:
         bns = bn if isinstance(bn, (list, tuple)) else [bn] * len(convs)
         ws, bs = [], []
         for cv, b_ in zip(convs, bns):
-            w = sd[cv + '.weight'].to(self.device)
+            w = sd[cv + '.weight'].cpu()            # (host-side weight preparation, see stem_conv)
             assert tuple(w.shape) == (cout // len(convs), cin, k, k), (cv, tuple(w.shape), (cout, cin, k, k))
             cb = sd.get(cv + '.bias')
             assert (cb is not None) == bool(bias), f'{cv}: conv bias presence mismatch'
             bnp = None
             if b_ is not None:
-                bnp = tuple(sd[b_ + s].to(self.device) for s in ('.weight', '.bias', '.running_mean', '.running_var'))
-            wf, bf = fold_bn(w, cb.to(self.device) if cb is not None else None, bnp)
+                bnp = tuple(sd[b_ + s].cpu() for s in ('.weight', '.bias', '.running_mean', '.running_var'))
+            wf, bf = fold_bn(w, cb.cpu() if cb is not None else None, bnp)
             ws.append(wf)
             bs.append(bf)
         pad = k // 2 if pad is None else pad
         wfmt = 1 if (self.conv_impl == 0 and self.chain is None and x.C == cin and not self.split and
                      dxn_applies(cin, cout, k, stride, pad)) else 0
         wp = pack_conv_weight_dxn(torch.cat(ws, 0)) if wfmt else pack_conv_weight(torch.cat(ws, 0), cin_pad=x.C, split=self.split)
-        bf = torch.cat(bs, 0).contiguous()
+        wp = wp.to(self.device)
+        bf = torch.cat(bs, 0).contiguous().to(self.device)
         self.keep += [wp, bf]
         Ho = (x.H + 2 * pad - k) // stride + 1
         Wo = (x.W + 2 * pad - k) // stride + 1
@@ -417,6 +422,7 @@ class PlanBuilder:
         w, b = self.dev(w), self.dev(b)
         O = w.shape[0]
         assert w.shape[1] == I, (tuple(w.shape), I)
+        assert 0 <= ycol and ycol + O <= y.shape[1], f'linear writes columns [{ycol}, {ycol + O}) of a {tuple(y.shape)} matrix'
         # one split-K workspace for all linear ops of the plan (they run one after the other on the main lane)
         need = 8 * x.shape[0] * O
         if getattr(self, '_lin_scratch', None) is None or self._lin_scratch.numel() < need:

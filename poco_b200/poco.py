@@ -23,6 +23,15 @@ SMPL_MEAN_PARAMS = 'data/smpl_mean_params.npz'      # reference: pocolib/core/co
 class ParamTree(nn.Module):
     """Container that holds parameters / buffers under dotted reference names."""
 
+    _owner = None       # weakref to the POCO whose prepared plans depend on these tensors
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        owner = self._owner() if self._owner is not None else None
+        if owner is not None:
+            owner._invalidate()         # plans hold folded / packed copies of the weights
+        return r
+
     def register(self, path, tensor, kind):
         parts = path.split('.')
         node = self
@@ -170,6 +179,11 @@ class POCO(nn.Module):
         for name, (shape, kind) in spec.spec.items():
             top, _, rest = name.partition('.')
             getattr(self, top).register(rest, self._init_tensor(name, shape, kind, mp, g), 'param' if kind == 'param' else 'buffer')
+        import weakref
+        for part in ('backbone', 'head', 'uncert_head', 'flow_head'):
+            if hasattr(self, part):
+                for mod in getattr(self, part).modules():
+                    object.__setattr__(mod, '_owner', weakref.ref(self))
         self.smpl = smpl if smpl is not None else make_smpl_stage(self.head_name, img_res, smpl_model)
 
         # precision: 'fp16'  -- fp16 x fp16 -> fp32 tensor-core convs (BASELINE configs[1]; ~1e-2 of the fp32 reference on
@@ -243,15 +257,22 @@ class POCO(nn.Module):
             mod = getattr(self, part)
             try:
                 mod.load_state_dict(sub, strict=True)
-            except Exception:           # reference falls back to non-strict with a warning
-                mod.load_state_dict(sub, strict=False)
+            except RuntimeError as e:   # the reference falls back to a non-strict load with a warning (train_utils.py:98-104)
+                r = mod.load_state_dict(sub, strict=False)
+                import warnings
+                warnings.warn(f'poco_b200.load_pretrained: strict load of `{part}` failed ({str(e).splitlines()[0]}); '
+                              f'loaded non-strictly -- missing keys keep their initial values: {list(r.missing_keys)[:8]}'
+                              f'{"..." if len(r.missing_keys) > 8 else ""}, unexpected: {list(r.unexpected_keys)[:8]}'
+                              f'{"..." if len(r.unexpected_keys) > 8 else ""}')
         self._invalidate()
 
     # ------------------------------------------------------------------ plan
     def _build_engine(self, B, device):
         if device.type == 'cuda':       # (a cpu device is accepted only to *build* schedules in host-logic tests)
             L.check(L.lib().poco_device_check(device.index if device.index is not None else torch.cuda.current_device()))
-        sd ={k: v.detach() for k, v in self.state_dict().items()}
+        # one device -> host copy of the parameters: all weight preparation (BN folding, repacking, the fp64 fold of
+        # fc1 / fc2) is host work, the plan build launches no torch arithmetic kernels on the GPU
+        sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
         b = PlanBuilder(sd, B, device, conv_impl=self.conv_impl, split=self.precision == 'split')
         eng = _Engine()
         eng.img = b.f32(B, 3, self.img_res, self.img_res)
@@ -333,12 +354,29 @@ class POCO(nn.Module):
         eng.builder_keep = b.keep
         return eng
 
+    # Prepared plans (activation pool + packed weights + CUDA graph) are kept per batch size.  The reference demo calls
+    # forward with B = number of detections of an image (tester.py:213), so a folder run sees many distinct B:
+    # batch sizes are rounded up to a bucket (the padding crops are zeros, their outputs are dropped -- crops are
+    # independent, so the real crops' results do not change) and at most MAX_PLANS plans are kept (LRU).
+    MAX_PLANS = int(os.environ.get('POCO_B200_MAX_PLANS', '6'))
+
+    @staticmethod
+    def bucket(B):
+        """plan batch size for a request of B crops: exact up to 8, then multiples of 8 / 32 / 64"""
+        if B <= 8:
+            return B
+        step = 8 if B <= 64 else (32 if B <= 256 else 64)
+        return (B + step - 1) // step * step
+
     def _engine(self, B, device):
         key = (B, str(device))
-        eng = self._engines.get(key)
+        eng = self._engines.pop(key, None)
         if eng is None:
+            plans = [k for k in self._engines if k[0] != 'flow']
+            while len(plans) >= self.MAX_PLANS:
+                del self._engines[plans.pop(0)]         # least recently used
             eng = self._build_engine(B, device)
-            self._engines[key] = eng
+        self._engines[key] = eng                        # (re-insert: most recently used last)
         return eng
 
     # ------------------------------------------------------------------ forward
@@ -352,13 +390,18 @@ class POCO(nn.Module):
         B = img.shape[0]
         if tuple(img.shape[1:]) != (3, self.img_res, self.img_res):
             raise ValueError(f"batch['img'] must be [B,3,{self.img_res},{self.img_res}], got {tuple(img.shape)}")
-        eng = self._engine(B, img.device)
-        eng.img.copy_(img)
+        if B == 0:
+            raise ValueError("batch['img'] is empty")
+        Bp = self.bucket(B)
+        eng = self._engine(Bp, img.device)
+        eng.img[:B].copy_(img)
         if self.head_name == 'cliff':
-            eng.bbox.copy_(batch['bbox_info'])
+            eng.bbox[:B].copy_(batch['bbox_info'])
+        # (rows [B, Bp) keep whatever an earlier request left there: every op is row-independent per crop)
         eng.run(self.use_cuda_graph)
         out = {}
         for k, v in eng.out.items():
+            v = v[:B]
             out[k] = v.clone() if v.is_contiguous() else v.contiguous()
         if self.var_sigma_dim == 9:
             out['var_pose'] = out['var_pose'].view(B, -1, 3, 3)

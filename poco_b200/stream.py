@@ -27,7 +27,11 @@ class StreamRunner:
     """one video stream on one GPU.  step(frame, boxes) returns device tensors; `frame` is the decoded RGB frame
     (uint8 [H, W, 3]) already in device memory, `boxes` the detections [n, 4] = (cx, cy, w, h)."""
 
-    def __init__(self, model, bbox_scale=1.2, crop=224, kinematic_uncert=False, sensitivity_threshold=0.40):
+    def __init__(self, model, bbox_scale=1.2, crop=224, kinematic_uncert=False, sensitivity_threshold=0.40,
+                 clip_global=True):
+        """clip_global: np.clip(variance_global, 0, 0.99) as the image-folder loop does (tester.py:245); the tracked-video
+        loop (tester.py:418-421) keeps the raw value -- pass False for that behaviour."""
+        self.clip_global = bool(clip_global)
         self.model = model.eval()
         self.bbox_scale, self.crop = float(bbox_scale), int(crop)
         self.kinematic, self.threshold = bool(kinematic_uncert), float(sensitivity_threshold)
@@ -42,6 +46,8 @@ class StreamRunner:
         var, _, var_global = uncert_post(out['var_pose'], self.backbone, kinematic=self.kinematic,
                                          sensitivity_threshold=self.threshold)
         out['variance'] = var                                   # tester.py:243
+        if self.clip_global:
+            var_global = torch.clamp(var_global, 0.0, 0.99)     # tester.py:245
         out['variance_global'] = var_global                     # tester.py:244
         out['confidence'] = 1.0 - var_global
         out['orig_cam'] = convert_crop_cam_to_orig_img(out['pred_cam'], boxes, W, H)      # tester.py:216-221

@@ -9,9 +9,14 @@ from gpu_util import sync_or_die
 
 pytestmark = pytest.mark.gpu
 
-# fp16 weights + fp16 activation storage through ~110 sequential conv layers against the fp32
-# reference, on the calibrated synthetic checkpoint (DESIGN.md "precision"): max-abs-err / max-abs-ref
+# The north-star gate (<= 1e-3 on the four gated outputs against the fp32 reference) is asserted on the parity mode,
+# precision='split', in tests/test_gpu_split.py::test_parity_mode_meets_the_north_star_gate and in the
+# benchmark-batch-size test below.  This file exercises the default precision='fp16' (BASELINE configs[1] "fp16"):
+# fp16 weights + fp16 activation storage through ~110 sequential conv layers do NOT meet 1e-3 on pred_pose /
+# pred_shape / pred_cam (measured 0.9-2.0e-2 / 2.0-3.5e-3 / 0.5-8.9e-3 on the calibrated synthetic checkpoint,
+# DESIGN.md 4); the bounds below are what fp16 operands are expected to deliver, not the parity gate.
 E2E_TOL = {'pred_pose': 6e-2, 'pred_shape': 6e-3, 'pred_cam': 1.5e-2, 'var_pose': 1e-3}
+PARITY_TOL = 1e-3
 
 
 @pytest.mark.parametrize('preset', PRESETS)
@@ -47,6 +52,41 @@ def test_forward_matches_reference_goldens(preset):
     if 'pred_segm_mask_sub' in gold:
         st = int(gold['segm_stride'])
         assert rel_err(out['pred_segm_mask'][:, :, ::st, ::st].cpu().numpy(), gold['pred_segm_mask_sub']) < 5e-2
+
+
+@pytest.mark.parametrize('preset,B,precision', [('cliff_w32', 256, 'fp16'), ('pare_w32', 128, 'fp16'),
+                                                ('cliff_w32', 256, 'split'), ('pare_w32', 128, 'split')])
+def test_benchmark_batch_sizes_equal_small_batches_and_goldens(preset, B, precision):
+    """BASELINE configs[1] (POCO-CLIFF / HRNet-W32, 256 crops) and configs[2] (POCO-PARE / HRNet-W32, 128 crops) with
+    the default schedule of that batch size (plan lanes with SM shares, m_group, half-size CTAs, 148-CTA persistent
+    grids, CUDA-graph replay): crops 0-3 are the golden crops and must match the reference outputs; EVERY crop must
+    equal the same crop run in a batch of 4 -- bitwise for everything a crop computes on its own (the whole backbone,
+    the PARE head), to fp32 re-association for what goes through the split-K linear layers (their split count depends
+    on the number of rows)."""
+    meta, gold, _ = load_preset(preset)
+    m = build_model(preset, 'cuda', precision=precision)
+    small = synthetic_batch(preset, 'cuda')                     # the 4 golden crops
+    extra = synthetic_batch(preset, 'cuda', B=B - meta['test_b'])
+    big = {k: torch.cat([small[k], extra[k] + (0.25 if k == 'img' else 0.0)], 0).contiguous() for k in small}
+    with torch.no_grad():
+        for _ in range(3):              # eager warm-up, graph capture, replay
+            out = m.hot_path(big)
+    sync_or_die(180)
+    tol = E2E_TOL if precision == 'fp16' else {k: PARITY_TOL for k in GATED}
+    errs = {k: rel_err(out[k][:meta['test_b']].cpu().numpy(), gold[k]) for k in GATED}
+    print(preset, B, precision, errs)
+    for k in GATED:
+        assert torch.isfinite(out[k]).all(), k
+        assert errs[k] < tol[k], (k, errs)
+    exact = ('uncert_feat',) if 'cliff' in preset else ('uncert_feat', 'pred_pose', 'pred_shape', 'pred_cam', 'pred_segm_mask')
+    with torch.no_grad():
+        for i0 in range(0, B, 4):
+            sub = m.hot_path({k: v[i0:i0 + 4].contiguous() for k, v in big.items()})
+            for k in exact:
+                assert torch.equal(sub[k], out[k][i0:i0 + 4]), (k, i0)
+            for k in GATED:
+                assert rel_err(sub[k].cpu().numpy(), out[k][i0:i0 + 4].cpu().numpy()) < 1e-5, (k, i0)
+    sync_or_die(180)
 
 
 @pytest.mark.parametrize('preset', ['pare_r50', 'cliff_w32'])
@@ -181,5 +221,8 @@ def test_stream_runner_equals_the_separate_steps():
     p = U.prepare_uncert(ref['var_pose'].cpu().numpy())
     _, gl = U.global_uncert(p, 'hrnet_w32-cliff')
     assert np.array_equal(out['variance'].cpu().numpy(), p)
-    assert np.array_equal(out['variance_global'].cpu().numpy(), gl)
+    assert np.array_equal(out['variance_global'].cpu().numpy(), np.clip(gl, 0, 0.99))      # tester.py:245
+    raw = StreamRunner(m, bbox_scale=1.1, clip_global=False).step(torch.from_numpy(frame).cuda(),
+                                                                  torch.from_numpy(boxes.astype(np.float32)))
+    assert np.array_equal(raw['variance_global'].cpu().numpy(), gl)                        # tester.py:418-421
     assert out['orig_cam'].shape == (5, 4) and torch.isfinite(out['orig_cam']).all()

@@ -125,6 +125,54 @@ def test_state_dict_contract(preset):
         assert len(list(getattr(m, part).parameters())) > 0        # trainer.py:598-601 per-module groups
 
 
+@pytest.mark.parametrize('kw,width,view', [
+    (dict(loss_ver='norm_flow', sigma_dim=9, nflow_mask_type='alter'), 216, (2, 24, 3, 3)),     # the reference hparams default
+    (dict(loss_ver='genG', sigma_dim=9), 48, (2, 48)),
+    (dict(loss_ver='gauss', sigma_dim=9), 72, (2, 72)),
+    (dict(loss_ver='gauss_sigma', sigma_dim=9), 24, (2, 24)),
+])
+def test_uncertainty_head_output_width_follows_loss_ver_and_sigma_dim(kw, width, view):
+    """poco_head.get_num_uncertainty_outputs (poco_head.py:84-94): the LAST uncert_fc layer is 24 * mult * sigma_dim
+    wide, and var_pose is viewed [B, -1, 3, 3] when sigma_dim == 9 (poco_head.py:147-148)"""
+    import emu
+    from oracle import synth_ckpt as S
+    m = POCO(backbone='resnet50-pare', uncert_type=['pose'], smpl_mean_params=S.smpl_mean_params(0), **kw).eval()
+    sd = m.state_dict()
+    last = sorted(k for k in sd if k.startswith('uncert_head.uncert_fc') and k.endswith('.weight'))[-1]
+    assert sd[last].shape[0] == width == m.n_uncert_out
+    # the plan writes every column of var_pose (a narrower last layer used to leave zeros behind)
+    eng = m._build_engine(2, torch.device('cpu'))
+    eng.img.copy_(torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(0)))
+    emu.run_plan_ops(eng.plan.ops, eng.plan.keep)
+    vp = eng.out['var_pose']
+    assert vp.shape == (2, width) and (vp != 0).all()
+    assert vp.view(2, -1, 3, 3).shape == view if m.var_sigma_dim == 9 else vp.shape == view
+
+
+def test_submodule_load_state_dict_invalidates_prepared_plans():
+    """plans hold folded / packed weight copies: loading into model.backbone must drop them"""
+    m = build_model('pare_r50')
+    m._engines[(1, 'cpu')] = object()
+    m.backbone.load_state_dict(m.backbone.state_dict())
+    assert not m._engines
+    m._engines[(1, 'cpu')] = object()
+    m.head.load_state_dict(m.head.state_dict(), strict=False)
+    assert not m._engines
+
+
+def test_plan_cache_is_bucketed_and_bounded():
+    """tester.py:213 calls forward with B = #detections: batch sizes round up to buckets, plans are LRU-evicted"""
+    assert [POCO.bucket(b) for b in (1, 5, 8, 9, 16, 17, 64, 65, 100, 256, 257, 2048)] == \
+        [1, 5, 8, 16, 16, 24, 64, 96, 128, 256, 320, 2048]
+    m = build_model('pare_r50')
+    m.MAX_PLANS = 2
+    built = []
+    m._build_engine = lambda B, dev: built.append(B) or ('plan', B)
+    for B in (4, 16, 4, 24, 16):
+        m._engine(B, torch.device('cpu'))
+    assert built == [4, 16, 24, 16] and [k[0] for k in m._engines] == [24, 16]
+
+
 def test_load_pretrained_variants(tmp_path):
     meta, _, sd = load_preset('pare_r50')
     from oracle import synth_ckpt as S
