@@ -42,7 +42,7 @@ namespace {
 #define MBAR_WAIT(bar, parity) mbar_wait(bar, parity)
 #endif
 
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;                     // operand stages over both rings (header barrier arrays)
 constexpr int kMaxAccBufs = 8;                     // TMEM accumulator ring (512 columns / n_tile)
 constexpr int kTileM = 128;
 constexpr int kSmemBudget = 225 * 1024;   // of 227 KB usable per CTA
@@ -59,7 +59,12 @@ static int res_ring_base(bool half) {
     static const int v = [] { const char* e = getenv("POCO_B200_RES_RING"); return e ? std::max(1, atoi(e)) : kResRing; }();
     return half ? std::min(v, 2) : v;
 }
-static int ring_bytes_for(int item_planes, bool half, int sp = 1) { return 2 * (kOutRing + res_ring_base(half)) * item_planes * kPlaneTile * sp; }
+// a conv without a residual input has no ring at all: its shared memory goes to operand stages (bytes in flight)
+static bool ring_always() { static const bool v = [] { const char* e = getenv("POCO_B200_RING_ALWAYS"); return e && e[0] == '1'; }(); return v; }
+static int max_stages() { static const int v = [] { const char* e = getenv("POCO_B200_MAX_STAGES"); return e ? std::max(2, std::min(kMaxStages, atoi(e))) : kMaxStages; }(); return v; }
+static int ring_bytes_for(int item_planes, bool half, int sp, bool any_res) {
+    return (any_res || ring_always()) ? 2 * (kOutRing + res_ring_base(half)) * item_planes * kPlaneTile * sp : 0;
+}
 
 enum { MODE_LINEAR = 0, MODE_GATHER = 1 };
 
@@ -113,7 +118,9 @@ struct ConvTcParams {
     int item_planes;      // epilogue work item = item_planes x 8 accumulator columns (2 or 4)
     int tap_group;        // gather mode: filter taps per stage
     int debug;            // POCO_CONV_DEBUG bits (bring-up only): 1 skip epilogue work, 2 skip MMAs, 4 skip A loads,
-                          // 8 skip output stores, 16 ignore the residual
+                          // 8 skip output stores, 16 ignore the residual, 32 cycle accounting of the MMA issuers
+    int stagger;          // cycles the second MMA issuer waits before its first unit (keeps the two issuers out of phase)
+    unsigned long long* prof;   // debug & 32: [2 issuers][8] cycle sums (POCO_CONV_PROF points the launcher at a buffer)
 };
 
 struct SmemHeader {
@@ -128,6 +135,7 @@ struct SmemHeader {
     uint32_t pad_[3];
     float bias[2][256];                                // double buffered across chain segments
     float xch[2][2][4][2][32];                         // dx-in-N: [half][buffer][warp][D0 of row 31 | D2 of row 0][channel]
+    unsigned long long stamps[8];                      // debug & 64: globaltimer of CTA 0's phases
 };
 static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
 
@@ -151,10 +159,42 @@ struct Roles {
 // registers: ~3 uniform ALU ops per UTCHMMA.
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; }
 
+// POCO_ISSUE_BATCH (round 2): UTCHMMA reads its descriptors from uniform registers and holds them until the tensor pipe
+// dequeues the instruction; a uniform-datapath op that overwrites one of them stalls (short scoreboard) until then.  The
+// lean "3 uniform ops per MMA" chain reused a handful of registers every 2-3 MMAs, so only ~3 MMAs were ever queued and the
+// pipe ran at 60-72 cycles per MMA instead of its 40-64 (ncu source page: 80 % of the issuer's samples were short_sb on
+// UIADD3; tools/mma_bench7.cu reaches the hardware rate with the same operand geometry).  Here the descriptors of a batch
+// of MMAs are materialised in ordinary registers first; ptxas then moves each into its own uniform register pair right
+// before its UTCHMMA, so a whole batch can sit in the queue.  0 = the old uniform chain.
+#ifndef POCO_ISSUE_BATCH
+#define POCO_ISSUE_BATCH 12
+#endif
 template <int TAPS, int KS>
 __device__ __forceinline__ void issue_linear(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, int Wp, uint32_t a_kstep,
                                              uint32_t b_kstep, uint32_t b_tap, uint32_t desc_hi, uint32_t idesc,
                                              uint32_t acc0) {
+#if POCO_ISSUE_BATCH > 0
+    constexpr int TOTAL = TAPS * KS;
+    constexpr int BATCH = POCO_ISSUE_BATCH < TOTAL ? POCO_ISSUE_BATCH : TOTAL;
+#pragma unroll
+    for (int j0 = 0; j0 < TOTAL; j0 += BATCH) {
+        uint32_t al[BATCH], bl[BATCH];
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+            const int j = j0 + i, t = j / KS, k = j % KS;
+            if (j < TOTAL) {
+                al[i] = a_lo + (TAPS == 1 ? 0u : TAPS == 3 ? uint32_t((t - 1) * Wp) : uint32_t((t / 3 - 1) * Wp + (t % 3 - 1))) + uint32_t(k) * a_kstep;
+                bl[i] = b_lo + uint32_t(t) * b_tap + uint32_t(k) * b_kstep;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i)
+            if (j0 + i < TOTAL) asm volatile("" : "+r"(al[i]), "+r"(bl[i]));        // all of the batch live in registers here
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i)
+            if (j0 + i < TOTAL) umma_f16(d_tmem, desc64(desc_hi, al[i]), desc64(desc_hi, bl[i]), idesc, (j0 + i) ? 1u : acc0);
+    }
+#else
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) {
         // tap (r,s): shift of (r-1) rows and (s-1) pixels inside the landed run (16 B per pixel = 1 descriptor unit)
@@ -165,15 +205,29 @@ __device__ __forceinline__ void issue_linear(uint32_t d_tmem, uint32_t a_lo, uin
             umma_f16(d_tmem, desc64(desc_hi, at + uint32_t(k) * a_kstep), desc64(desc_hi, bt + uint32_t(k) * b_kstep), idesc,
                      (t | k) ? 1u : acc0);
     }
+#endif
 }
 
 template <int TG>
 __device__ __forceinline__ void issue_gather(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t b_tap,
                                              uint32_t desc_hi, uint32_t idesc, uint32_t acc0) {
+#if POCO_ISSUE_BATCH > 0
+    uint32_t al[TG], bl[TG];
+#pragma unroll
+    for (int tt = 0; tt < TG; ++tt) {
+        al[tt] = a_lo + uint32_t(tt) * 256u;
+        bl[tt] = b_lo + uint32_t(tt) * b_tap;
+    }
+#pragma unroll
+    for (int tt = 0; tt < TG; ++tt) asm volatile("" : "+r"(al[tt]), "+r"(bl[tt]));
+#pragma unroll
+    for (int tt = 0; tt < TG; ++tt) umma_f16(d_tmem, desc64(desc_hi, al[tt]), desc64(desc_hi, bl[tt]), idesc, tt ? 1u : acc0);
+#else
 #pragma unroll
     for (int tt = 0; tt < TG; ++tt)      // one K=16 MMA per tap of the group; A taps are 4 KB (256 units) apart
         umma_f16(d_tmem, desc64(desc_hi, a_lo + uint32_t(tt) * 256u), desc64(desc_hi, b_lo + uint32_t(tt) * b_tap), idesc,
                  tt ? 1u : acc0);
+#endif
 }
 
 // global-memory helpers of the chain protocol
@@ -207,6 +261,8 @@ template <int MODE, int IPL, bool DXN, int MINB = 1, bool SPLIT = false>
 __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
+    const bool tl_on = (p.debug & 64) && blockIdx.x == 0 && blockIdx.y == 0;     // timeline of CTA 0 (bring-up)
+    if (tl_on && threadIdx.x == 0) hdr->stamps[0] = global_timer_ns();
     const int res_ring_n = p.res_ring;
     constexpr int ipl = IPL;                            // output planes (8 columns each) per epilogue work item
     constexpr int SP = SPLIT ? 2 : 1;
@@ -260,6 +316,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
+    if (tl_on && threadIdx.x == 0) hdr->stamps[1] = global_timer_ns();
     // Programmatic dependent launch: let the next kernel of the stream start its prologue on every SM
     // this CTA leaves; roles that touch activations call pdl_wait() before their first access.
     pdl_launch_dependents();
@@ -312,7 +369,9 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         if (p.w_resident && elect_one()) load_resident_weights(0);      // weights are constants: no dependency
         __syncwarp();
         pdl_wait();
-        uint32_t its[2] = {0u, 0u}, tl = 0, ul = 0;      // ul: units so far (the two issuers take alternate units)
+        // Ring positions are kept as (slot, phase) counters: `it % stages` / `it / stages` with a run-time divisor cost
+        // ~150 cycles of dependent integer-division code per stage on every role's critical path (r02 ncu source page).
+        uint32_t r_slot[2] = {0u, 0u}, r_ph[2] = {0u, 0u}, tl = 0, ul = 0;      // ul: units so far (the two issuers take alternate units)
         // double-buffered weights: fetch the next segment's a few tiles into this one (its buffer was
         // last read two segments ago); single buffer: after this segment's last MMA has retired
         const int w_prefetch_at = min(my_tiles - 1, 2 * p.stages * p.rings);
@@ -352,8 +411,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                 const uint32_t ring = p.rings == 2 ? (ul & 1u) : 0u;
                 ++ul;
                 for (int c = 0; c < p.n_chunks; ++c) {
-                    const uint32_t it = its[ring]++;
-                    const uint32_t slot = ring * p.stages + it % p.stages, ph = (it / p.stages) & 1u;
+                    const uint32_t slot = ring * p.stages + r_slot[ring], ph = r_ph[ring];
+                    if (++r_slot[ring] == uint32_t(p.stages)) { r_slot[ring] = 0; r_ph[ring] ^= 1u; }
                     MBAR_WAIT(smem_u32(&hdr->empty[slot]), ph ^ 1u);
                     if (elect_one()) {
                         const uint32_t bar = smem_u32(&hdr->full[slot]);
@@ -403,7 +462,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         const int Wp_o = p.Wout + 2, HpWp_o = (p.Hout + 2) * Wp_o;
         const int Wp_i = p.Win + 2, HpWp_i = (p.Hin + 2) * Wp_i;
         const int TG = p.tap_group, n_groups = taps / TG;
-        uint32_t it = 0;
+        uint32_t it = 0, g_slot = 0, g_ph = 0, g_lag = 0;      // g_lag: slot of the stage kGatherLag iterations back
         for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
             const long long q = (long long)tile * kTileM + r;
             const int n = int(q / HpWp_o);
@@ -425,7 +484,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                     okmask |= ok ? (1u << tt) : 0u;
                 }
                 for (int c = 0; c < p.n_chunks; ++c, ++it) {
-                    const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+                    const uint32_t slot = g_slot, ph = g_ph;
+                    if (++g_slot == uint32_t(p.stages)) { g_slot = 0; g_ph ^= 1u; }
                     MBAR_WAIT(smem_u32(&hdr->empty[slot]), ph ^ 1u);
                     const uint32_t st = smem_u32(stage0 + size_t(slot) * stage_bytes) + uint32_t(r) * 16u;
                     const __half* src0 = in0 + (long long)(c * 2) * p.in_plane * 8;
@@ -455,15 +515,18 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                     if (it >= uint32_t(kGatherLag)) {
                         cp_async_wait<kGatherLag>();
                         fence_proxy_async_smem();
-                        mbar_arrive(smem_u32(&hdr->full[(it - kGatherLag) % p.stages]));
+                        mbar_arrive(smem_u32(&hdr->full[g_lag]));
+                        if (++g_lag == uint32_t(p.stages)) g_lag = 0;
                     }
                 }
             }
         }
         cp_async_wait<0>();
         fence_proxy_async_smem();
-        for (uint32_t d = (it > uint32_t(kGatherLag) ? it - kGatherLag : 0u); d < it; ++d)
-            mbar_arrive(smem_u32(&hdr->full[d % p.stages]));
+        for (uint32_t d = (it > uint32_t(kGatherLag) ? it - kGatherLag : 0u); d < it; ++d) {
+            mbar_arrive(smem_u32(&hdr->full[g_lag]));
+            if (++g_lag == uint32_t(p.stages)) g_lag = 0;
+        }
     } else if (MODE == MODE_GATHER && warp == R::kWWarp) {
         // ============================================================ W producer (bulk copies)
         if (p.w_resident) {
@@ -471,12 +534,13 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
             __syncwarp();
         } else {
             const __half* wg = p.seg[0].w + size_t(nb) * p.n_tile * 8;
-            uint32_t it = 0;
+            uint32_t w_slot = 0, w_ph = 0;
             const int TG = p.tap_group, n_groups = taps / TG;
             for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x)
                 for (int tg = 0; tg < n_groups; ++tg)
-                    for (int c = 0; c < p.n_chunks; ++c, ++it) {
-                        const uint32_t slot = it % p.stages, ph = (it / p.stages) & 1u;
+                    for (int c = 0; c < p.n_chunks; ++c) {
+                        const uint32_t slot = w_slot, ph = w_ph;
+                        if (++w_slot == uint32_t(p.stages)) { w_slot = 0; w_ph ^= 1u; }
                         MBAR_WAIT(smem_u32(&hdr->empty[slot]), ph ^ 1u);
                         if (elect_one()) {
                             const uint32_t bar = smem_u32(&hdr->full[slot]);
@@ -506,21 +570,33 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
             : ((p.w_resident ? uint32_t(cin8) : 2u) * slab_bytes) >> 4;
         const bool active = p.rings == 2 || mw == 0u;       // a single ring is served by warp 0
         const uint32_t tile_bytes = uint32_t(p.tile_stride) * 16u;
-        uint32_t it = 0, tl = 0, ul = 0;
+        uint32_t tl = 0, ul = 0;
+        uint32_t m_slot = 0, m_ph = 0;                  // this issuer's position in its stage ring
+        uint32_t a_buf = 0, a_par = 1u;                 // accumulator ring position of the next tile (all tiles, both issuers)
+        const bool prof = (p.debug & 32) != 0;
+        long long pt_acc = 0, pt_full = 0, pt_issue = 0, pt_units = 0, pt_t0 = prof ? clock64() : 0, pt_mark = 0;
+        if (mw == 1u && p.rings == 2 && p.stagger > 0) {
+            const long long t_end = clock64() + p.stagger;
+            while (clock64() < t_end) {
+            }
+        }
         for (int s = 0; s < n_segs; ++s) {
             const uint32_t w_res_u32 = smem_u32(w_res) + uint32_t(wbuf_of(s)) * uint32_t(p.w_res_bytes);
             if (p.w_resident && active) MBAR_WAIT(smem_u32(&hdr->w_ready[wbuf_of(s)]), uint32_t(wuse_of(s)) & 1u);
             for (int ju = 0; ju < my_units; ++ju) {
                 const int gcount = unit_tiles(unit_of(ju));
-                const uint32_t tl0 = tl;
                 tl += uint32_t(gcount);
                 const uint32_t ul0 = ul++;
+                const uint32_t b0 = a_buf, par0 = a_par;      // first accumulator of this unit; advance the ring past the unit
+                a_buf += uint32_t(gcount);
+                if (a_buf >= nacc) { a_buf -= nacc; a_par ^= 1u; }
                 if (p.rings == 2 ? (ul0 & 1u) != mw : mw != 0u) continue;   // one ring per issuer
                 // accumulator of every tile of the unit (all must have been drained); computed here, outside the
                 // elected region, so that the MMA descriptors below stay pure uniform-register arithmetic
                 uint32_t dt[4], bufg[4];
+                if (prof) { pt_mark = clock64(); ++pt_units; }
                 {
-                    uint32_t b = tl0 % nacc, par = ((tl0 / nacc) & 1u) ^ 1u;
+                    uint32_t b = b0, par = par0;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         bufg[g] = b;
@@ -530,10 +606,14 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                     }
                 }
                 tc_fence_after();
-                for (int ki = 0; ki < kiters; ++ki, ++it) {
-                    const uint32_t slot = (p.rings == 2 ? mw * p.stages : 0u) + it % p.stages, ph = (it / p.stages) & 1u;
+                if (prof) { const long long t = clock64(); pt_acc += t - pt_mark; pt_mark = t; }
+                for (int ki = 0; ki < kiters; ++ki) {
+                    const uint32_t slot = (p.rings == 2 ? mw * p.stages : 0u) + m_slot, ph = m_ph;
+                    if (++m_slot == uint32_t(p.stages)) { m_slot = 0; m_ph ^= 1u; }
                     MBAR_WAIT(smem_u32(&hdr->full[slot]), ph);
                     tc_fence_after();
+                    if (prof) { const long long t = clock64(); pt_full += t - pt_mark; pt_mark = t; }
+                    if (tl_on && mw == 0u && ul0 == 0u && ki == 0 && lane == 0) hdr->stamps[2] = global_timer_ns();
                     if (elect_one()) {
                         const uint32_t a_base0 = smem_u32(stage0) + slot * uint32_t(stage_bytes);
                         const uint32_t w_stage = a_base0 + p.a_stage_bytes;
@@ -616,12 +696,23 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                         }
                     }
                     __syncwarp();
+                    if (prof) { const long long t = clock64(); pt_issue += t - pt_mark; pt_mark = t; }
+                    if (tl_on && mw == 0u && ul0 == 0u && ki == kiters - 1 && lane == 0) hdr->stamps[3] = global_timer_ns();
                 }
             }
             if (p.w_resident && active && n_segs > 1) {     // this warp's MMAs of the segment no longer read the weight buffer
                 if (elect_one()) umma_commit(smem_u32(&hdr->w_free[wbuf_of(s)]));
                 __syncwarp();
             }
+        }
+        if (prof && lane == 0 && p.prof != nullptr) {
+            unsigned long long* o = p.prof + mw * 8;
+            atomicAdd(o + 0, (unsigned long long)(clock64() - pt_t0));
+            atomicAdd(o + 1, (unsigned long long)pt_acc);
+            atomicAdd(o + 2, (unsigned long long)pt_full);
+            atomicAdd(o + 3, (unsigned long long)pt_issue);
+            atomicAdd(o + 4, (unsigned long long)pt_units);
+            atomicAdd(o + 5, 1ull);
         }
     } else if (warp >= R::kEpiWarp0) {
         // ============================================================ epilogue (8 autonomous warps)
@@ -651,7 +742,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         constexpr uint32_t kSlot = IPL * 512 * SP;      // one item slice of this warp: IPL planes x 32 rows x 16 B (split: hi planes, then lo planes)
         uint8_t* res_ring = smem + kHeaderBytes + ew * warp_ring_bytes;
         unsigned long long* res_full = hdr->res_full + ew * kMaxResRing;
-        const uint32_t rr_n = uint32_t(res_ring_n);
+        const uint32_t rr_n = uint32_t(res_ring_n > 0 ? res_ring_n : 1);      // (0 = no ring: a conv without residual)
         // Residual prefetch cursor (used by the elected lane): the next residual-bearing (segment, tile,
         // item) of this warp.  A segment's residual may be the output of the segment two before it, so
         // the cursor never runs past segment `cur + 1` (everything up to `cur - 1` is complete on this
@@ -663,7 +754,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         uint32_t pf_tl = uint32_t(pf_s * my_tiles);
         const __half* pf_res = pf_s < n_segs ? p.seg[pf_s].res : nullptr;
         const __half* pf_res_lo = SPLIT ? p.seg[0].res_lo : nullptr;
-        uint32_t pf_issued = 0;
+        uint32_t pf_issued = 0, pf_slot = 0;
         auto prefetch_residual = [&](int cur_seg, uint32_t upto) {      // elected lane: top the ring up to `upto` items
             while (pf_issued < upto) {
                 while (pf_k >= items) {         // advance to the next tile (segment) with an item for this half
@@ -682,7 +773,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                 const long long tile_ = tile_of(pf_j);
                 const int item = pf_k;
                 pf_k += 2;
-                const uint32_t slot = pf_issued % rr_n;
+                const uint32_t slot = pf_slot;
+                if (++pf_slot == rr_n) pf_slot = 0;
                 ++pf_issued;
                 const long long qw = tile_ * p.tile_stride + p.tile_origin + lg * 32;
                 const long long left = p.P_out - qw;
@@ -712,6 +804,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         const uint32_t step_unit = uint32_t((((long long)gridDim.x * G - (G - 1)) * p.tile_stride) % HpWp_o);
         const uint32_t magic_w = 0xFFFFFFFFu / uint32_t(Wp_o) + 1u;      // exact floor(n / Wp) for n < 2^16
         uint32_t tl = 0, g = 0;                         // g counts residual items consumed
+        uint32_t e_buf = 0, e_par = 0;                  // accumulator ring position of tile `tl`
+        uint32_t rs_slot = 0, rs_par = 0;               // residual ring position of item `g`
         int xbuf = 0;                                   // dx-in-N exchange buffer of this half (alternates per item)
         for (int s = 0; s < n_segs; ++s) {
             const ChainSeg& sg = p.seg[s];
@@ -752,7 +846,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
             for (int ju = 0; ju < my_units; ++ju)
             for (int g_ = 0, tile = unit_of(ju) * G; g_ < unit_tiles(unit_of(ju)); ++g_, ++tile, ++tl) {
                 ++j;
-                const uint32_t buf = tl % nacc;
+                const uint32_t buf = e_buf, buf_par = e_par;
+                if (++e_buf == nacc) { e_buf = 0; e_par ^= 1u; }
                 const long long qw = (long long)tile * p.tile_stride + p.tile_origin + lg * 32;     // first row of this warp's slice
                 const uint32_t yy = __umulhi(rem, magic_w), xx = rem - yy * uint32_t(Wp_o);
                 const bool interior = qw + lane < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout) &&
@@ -763,8 +858,9 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                 const uint32_t rows_w = left <= 0 ? 0u : uint32_t(left < 32 ? left : 32);
                 const int k0 = k_first(tl);
                 if (k0 >= items) continue;                  // the other half drains this tile
-                MBAR_WAIT(smem_u32(&hdr->tmem_full[buf]), (tl / nacc) & 1u);
+                MBAR_WAIT(smem_u32(&hdr->tmem_full[buf]), buf_par);
                 tc_fence_after();
+                if (tl_on && ew == 0 && j == 0 && lane == 0) hdr->stamps[4] = global_timer_ns();
                 if (p.debug & 1) {
                     tc_fence_before();
                     __syncwarp();
@@ -835,8 +931,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                             if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[buf]));
                         }
                     }
-                    const uint32_t rslot = g % rr_n;
-                    if (has_res) MBAR_WAIT(smem_u32(&res_full[rslot]), (g / rr_n) & 1u);
+                    const uint32_t rslot = rs_slot;
+                    if (has_res) MBAR_WAIT(smem_u32(&res_full[rslot]), rs_par);
                     const long long out_off = ((long long)(plane0 + item * ipl) * p.out_plane + qw + lane) * 8;
                     __half* outp = sg.out + out_off;
                     const uint8_t* rb = res_ring + rslot * kSlot + lane * 16;
@@ -897,11 +993,13 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                     }
                     if (has_res) {
                         ++g;
+                        if (++rs_slot == rr_n) { rs_slot = 0; rs_par ^= 1u; }
                         __syncwarp();                       // every lane is done with the residual slot
                         if (elect_one()) prefetch_residual(s, g + rr_n);
                         __syncwarp();
                     }
                 }
+                if (tl_on && ew == 0 && lane == 0) { if (j == 0) hdr->stamps[5] = global_timer_ns(); hdr->stamps[6] = global_timer_ns(); }
                 if (flags_cur != nullptr && (++sig_owned >= kSignalEvery)) signal_tiles(j);
             }
             if (flags_cur != nullptr) signal_tiles(my_tiles - 1);
@@ -914,6 +1012,12 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
     if (warp == R::kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
+    }
+    if (tl_on && threadIdx.x == 0 && p.prof != nullptr) {
+        hdr->stamps[7] = global_timer_ns();
+        const unsigned long long slot = atomicAdd(p.prof + 127, 1ull);
+        if (slot < 12)
+            for (int i = 0; i < 8; ++i) p.prof[16 + slot * 8 + i] = hdr->stamps[i];
     }
 }
 
@@ -999,6 +1103,11 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     {
         const char* dbg = getenv("POCO_CONV_DEBUG");
         p.debug = dbg ? atoi(dbg) : 0;
+        const char* pr = getenv("POCO_CONV_PROF");         // device address (decimal) of 16 zeroed uint64 counters
+        p.prof = pr ? reinterpret_cast<unsigned long long*>(strtoull(pr, nullptr, 10)) : nullptr;
+        if (p.prof == nullptr) p.debug &= ~(32 | 64);
+        static const int stagger = [] { const char* e = getenv("POCO_B200_STAGGER"); return e ? atoi(e) : 0; }();
+        p.stagger = stagger;
     }
     p.P_out = int64_t(out.N) * (out.H + 2) * (out.W + 2);
     // weight format 1 = dx-in-N: [3 filter rows][Cin/8][3 * Cout (s-major)][8], see conv_tc_kernel
@@ -1092,7 +1201,7 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     for (int want4 = (mode == MODE_LINEAR && (dxn || (n_tile >= 64 && taps == 1) || n_tile == 32) ? 1 : 0); want4 >= (dxn ? 1 : 0) && !found; --want4) {
         p.item_planes = want4 ? 4 : 2;
         const int items_here = ((dxn ? out.C : n_tile) + p.item_planes * 8 - 1) / (p.item_planes * 8);
-        budget = smem_budget - kHeaderBytes - ring_bytes_for(p.item_planes, half || split, sp);
+        budget = smem_budget - kHeaderBytes - ring_bytes_for(p.item_planes, half || split, sp, any_res);
         (void)items_here;
         if (mode == MODE_LINEAR) {
             const int kcs[4] = {64, 48, 32, 16};
@@ -1107,14 +1216,15 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
                     const int a_stage = (kc / 8) * p.a_plane_bytes * sp;
                     const int w_stage = resident ? 0 : taps * kc * n_tile * 2 * sp;
                     const int avail = budget - wb * w_total;
-                    const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
+                    const int stages = std::min(max_stages(), avail / (a_stage + w_stage));
                     if (stages < (want4 ? 4 : 2)) continue;
                     p.kc = kc; p.n_chunks = in.C / kc;
                     p.w_resident = resident;
                     p.w_bufs = std::max(1, wb);
                     p.w_res_bytes = resident ? w_total : 0;
                     p.a_stage_bytes = a_stage; p.w_stage_bytes = w_stage;
-                    p.rings = stages >= 4 ? 2 : 1;
+                    static const int max_rings = [] { const char* e = getenv("POCO_B200_RINGS"); return e ? atoi(e) : 2; }();
+                    p.rings = (stages >= 4 && max_rings >= 2) ? 2 : 1;
                     p.stages = stages / p.rings;
                     found = true;
                 }
@@ -1130,7 +1240,7 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
                     const int a_stage = tg * 4096 * sp;
                     const int w_stage = resident ? 0 : tg * 16 * n_tile * 2 * sp;
                     const int avail = budget - (resident ? w_total : 0);
-                    const int stages = std::min(kMaxStages, avail / (a_stage + w_stage));
+                    const int stages = std::min(max_stages(), avail / (a_stage + w_stage));
                     if (stages < (want4 ? 4 : kGatherLag + 1)) continue;
                     p.kc = 16; p.n_chunks = in.C / 16;
                     p.tap_group = tg;
@@ -1153,8 +1263,8 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     p.flag_expect = (p.epi_items >= 2 ? 8 : 4) * n_blocks;
     // slabs are n_tile*16 bytes (a multiple of 256): the resident region needs no padding and
     // w_res_bytes is both the region size and the mbarrier transaction count
-    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes, half || split, sp) + size_t(p.w_res_bytes) * p.w_bufs + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
-    p.res_ring = res_ring_base(half || split);
+    size_t smem = size_t(kHeaderBytes) + ring_bytes_for(p.item_planes, half || split, sp, any_res) + size_t(p.w_res_bytes) * p.w_bufs + size_t(p.stages * p.rings) * (p.a_stage_bytes + p.w_stage_bytes);
+    p.res_ring = (any_res || ring_always()) ? res_ring_base(half || split) : 0;
     if (any_res && p.res_ring > 0) {       // spend spare shared memory on a deeper residual prefetch ring
         const int item_bytes = p.item_planes * kPlaneTile * sp;
         const int extra = int((size_t(smem_budget) - smem) / (2 * item_bytes));
@@ -1168,7 +1278,11 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     const ConvTcParams& pk = p;
     // Programmatic dependent launch is opt-in (POCO_B200_PDL=1): one-CTA-per-SM kernels leave the dependent grid no
     // room to start early, and its CTAs parked in griddepcontrol.wait cost 1.7 % end to end (A/B: 20.0 k with,
-    // 20.4 k crops/s without).
+    // 20.4 k crops/s without; round 2: 12.63 vs 12.32 ms).  Round 2 also tried the co-resident variant -- every
+    // stride-1 conv as ONE half-size CTA per SM (<= 110 KB, <= 256 TMEM columns) with PDL, so that the successor's
+    // CTAs sit set up next to the running ones: the overlap works (the successor's first data lands 2 us after the
+    // predecessor's exit instead of 7, profiles/r02b_conv_launch_timeline.csv) but half the shared memory per conv
+    // costs far more than the overlap returns (20.6 vs 12.3 ms per step, profiles/r02b_coop_pdl_experiment.csv).
     static const bool use_pdl = [] { const char* e = getenv("POCO_B200_PDL"); return e && e[0] == '1'; }();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
