@@ -1120,7 +1120,19 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     // N blocking: largest multiple-of-16 divisor of Cout that is <= 256 (dx-in-N: the three column groups)
     int n_tile = 0;
     // (split mode: N <= 128, so that a K chunk of [hi | lo] activations plus [W_hi | W_lo] still leaves two stages)
-    for (int t = std::min(split ? 128 : 256, out.C); t >= 16; t -= 16)
+    int n_cap = split ? 128 : 256;
+    // Weight-streamed stride-1 convs (the weights of one N block do not fit next to the operand stages): every tile
+    // re-reads the whole weight block from L2, and at ~42 B/clk per SM (6300 B/clk chip-wide L2 cap) that stream -- not
+    // the MMAs -- bounded 128->128 @14, 256->256 @7 / @56 (r02 cycle accounting: 103 cycles per MMA against a 64-cycle
+    // pipe).  They run with N <= 128 so that four accumulators fit in TMEM and G = 2 tiles share every streamed
+    // weight stage (half the L2 traffic; the MMA rate per output column is the same at N = 128 and N = 256).
+    static const int stream_group = [] { const char* e = getenv("POCO_B200_STREAM_GROUP"); return e ? atoi(e) : 2; }();
+    const bool linear_geom = d->stride == 1 && in.H == out.H && in.W == out.W &&
+                             ((d->kh == 3 && d->kw == 3 && d->pad == 1) || (d->kh == 1 && d->kw == 1 && d->pad == 0));
+    const bool stream_grouped = stream_group >= 2 && linear_geom && d->wfmt == 0 && n_segs == 1 &&
+                                int64_t(d->kh) * d->kw * in.C * std::min(n_cap, out.C) * 2 * sp > (split ? 160 : 112) * 1024;
+    if (stream_grouped && out.C % 128 == 0) n_cap = 128;
+    for (int t = std::min(n_cap, out.C); t >= 16; t -= 16)
         if (out.C % t == 0) { n_tile = t; break; }
     if (dxn) n_tile = 3 * out.C;
     POCO_CHECK(n_tile > 0 && n_tile <= 256, "no valid N tile");
@@ -1170,8 +1182,8 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     // only N <= 32.  POCO_B200_MGROUP=<g> forces up to g everywhere.
     static const int max_group = [] { const char* e = getenv("POCO_B200_MGROUP"); return e ? atoi(e) : 0; }();
     int g_first = 1;
-    if (mode == MODE_LINEAR && n_segs == 1 && (taps == 9 || dxn)) {
-        const int cap = max_group > 0 ? max_group : (n_tile <= 32 ? 2 : 1);
+    if (mode == MODE_LINEAR && n_segs == 1 && (taps == 9 || dxn || (taps == 1 && stream_grouped))) {
+        const int cap = max_group > 0 ? max_group : (n_tile <= 32 ? 2 : ((stream_grouped && w_total > w_res_cap) ? stream_group : 1));
         while (g_first * 2 <= cap && g_first * 4 <= p.acc_bufs) g_first *= 2;
     }
     auto set_group = [&](int G) {

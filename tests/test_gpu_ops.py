@@ -295,11 +295,10 @@ def test_conv_chain_matches_separate_launches(ch, H, N, max_ctas, groups):
                      halo[:, :, :, -1].abs().sum()) == 0.0
     for o in outs[2:]:
         assert torch.equal(o, outs[1])                  # replays of the chain are deterministic
-    if ch >= 128:
-        assert torch.equal(outs[1], outs[0])            # same tiling and K order as the separate launches
-    else:       # N <= 64: the separate launches run in the two-CTA "half" configuration (other K chunking than
-        # the chain's): the fp32 accumulation order differs, a few fp16 roundings flip per layer
-        assert rel_err(outs[1].numpy(), outs[0].numpy()) < 4e-3
+    # the separate launches may pick another configuration than the chain (two-CTA "half" mode for N <= 64, N blocks of
+    # 128 columns with two tiles per streamed weight stage for the wide layers): other K chunking, so the fp32
+    # accumulation order differs and a few fp16 roundings flip per layer
+    assert rel_err(outs[1].numpy(), outs[0].numpy()) < 4e-3
     # oracle arithmetic with the engine's roundings (fp16 activations and folded weights, fp32 accumulate)
     x = x0.half().float()
     for k in range(4):
