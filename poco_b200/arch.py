@@ -178,12 +178,21 @@ def chain_groups(branch, n_branches):
     return table[branch] if branch < len(table) else 1
 
 
-def chain_policy(channels):
-    """POCO_B200_CHAIN_MIN_C=<c>: chain the BasicBlocks of branches with at least c channels.  Default: never
-    (100000) -- at batch 256 the flag protocol's gpu-scope fences cost what the saved launches give back
-    (profiles/r01b_chain_vs_separate.csv); the chained path is exercised by tests/test_gpu_ops.py only."""
+def chain_policy(channels, N=256, latency_mode=False):
+    """Run the eight BasicBlock convs of an HRNet branch as ONE persistent chained launch?
+    Small batches (N <= 16 crops, the video-stream case: a handful of detections per frame) are launch-latency bound --
+    a conv is ~10 us of launch gap + pipeline fill around ~1 us of work -- and the chain removes that per conv
+    (1080p stream, 8 detections: 2.15 -> 1.92 ms per frame).  At batch 256 the flag protocol's gpu-scope fences cost
+    what the saved launches give back (profiles/r01b_chain_vs_separate.csv), so large batches launch conv by conv.
+    Opt-in (POCO(latency_mode=True), what the stream driver uses): a chain accumulates its K chunks in another order
+    than the separate launches, so switching it by batch size would break "a crop's result is bitwise independent of
+    the batch it travels in" across the threshold.
+    POCO_B200_CHAIN_MIN_C=<c> overrides: chain the branches with at least c channels at every batch size."""
     import os
-    return channels >= int(os.environ.get('POCO_B200_CHAIN_MIN_C', '100000'))
+    env = os.environ.get('POCO_B200_CHAIN_MIN_C')
+    if env is not None:
+        return channels >= int(env)
+    return bool(latency_mode) and N <= 16
 
 
 def hr_module(b, xs, name, chans, out0=None):
@@ -199,7 +208,7 @@ def hr_module(b, xs, name, chans, out0=None):
         x = xs[i]
         # The branch's eight convs share one geometry and CAN run as one persistent chained launch
         # (POCO_B200_CHAIN_MIN_C, off by default: see chain_policy).
-        chained = chain_policy(chans[i])
+        chained = chain_policy(chans[i], N, getattr(b, 'latency_mode', False))
         if chained:
             b.begin_chain()
         for k in range(4):

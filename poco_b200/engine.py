@@ -163,8 +163,9 @@ class PlanBuilder:
 
     mode = 'plan'
 
-    def __init__(self, sd, N, device, conv_impl=0, split=False):
+    def __init__(self, sd, N, device, conv_impl=0, split=False, latency_mode=False):
         self.sd = sd
+        self.latency_mode = bool(latency_mode)      # small batches: branch convs as persistent chains (arch.chain_policy)
         self.split = bool(split)    # split-precision ("parity") mode: hi + lo fp16 activations and weights everywhere
         self.N = N
         self.device = torch.device(device)

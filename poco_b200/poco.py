@@ -107,6 +107,7 @@ class POCO(nn.Module):
             smpl_model=None,
             use_cuda_graph=None,
             precision=None,
+            latency_mode=False,
     ):
         super().__init__()
         self.backbone_name, self.head_name = backbone.split('-')
@@ -194,6 +195,9 @@ class POCO(nn.Module):
         self.precision = precision or os.environ.get('POCO_B200_PRECISION', 'fp16')
         if self.precision not in ('fp16', 'split'):
             raise ValueError(f"precision must be 'fp16' or 'split', got {self.precision!r}")
+        # latency_mode: schedules for batches of <= 16 crops run every HRNet branch as one persistent chained launch
+        # (video streams: a few detections per frame, launch-latency bound); see arch.chain_policy
+        self.latency_mode = bool(latency_mode)
         self.use_cuda_graph = (os.environ.get('POCO_B200_GRAPH', '1') != '0') if use_cuda_graph is None else use_cuda_graph
         self.conv_impl = int(os.environ.get('POCO_B200_CONV_IMPL', '0'))
         self._engines = {}
@@ -273,7 +277,8 @@ class POCO(nn.Module):
         # one device -> host copy of the parameters: all weight preparation (BN folding, repacking, the fp64 fold of
         # fc1 / fc2) is host work, the plan build launches no torch arithmetic kernels on the GPU
         sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
-        b = PlanBuilder(sd, B, device, conv_impl=self.conv_impl, split=self.precision == 'split')
+        b = PlanBuilder(sd, B, device, conv_impl=self.conv_impl, split=self.precision == 'split',
+                        latency_mode=self.latency_mode)
         eng = _Engine()
         eng.img = b.f32(B, 3, self.img_res, self.img_res)
         feats = arch.BACKBONES[self.backbone_name][0](b, eng.img)
@@ -490,8 +495,8 @@ class _Engine:
         self.warm = False
 
     def run(self, use_graph):
-        if not use_graph:
-            self.plan.run()
+        if not use_graph or torch.cuda.is_current_stream_capturing():
+            self.plan.run()         # (inside an outer capture -- StreamRunner's per-frame graph -- the plan is recorded as is)
             return
         if self.graph is None:
             if not self.warm:           # first call runs eagerly (one-time attribute setup happens outside capture)

@@ -16,5 +16,6 @@ def synthetic_boxes(seed=0, n=9, H=360, W=480):
     rng = np.random.default_rng(seed + 100)
     b = np.stack([rng.uniform(-20, W + 20, n), rng.uniform(-20, H + 20, n), rng.uniform(30, 400, n), rng.uniform(30, 400, n)], 1)
     b[0] = [W / 2, H / 2, 200, 200]
-    b[1] = [10.5, 12.25, 150, 90]
+    if n > 1:
+        b[1] = [10.5, 12.25, 150, 90]
     return b.astype(np.float32).astype(np.float64)

@@ -226,3 +226,48 @@ def test_stream_runner_equals_the_separate_steps():
                                                                   torch.from_numpy(boxes.astype(np.float32)))
     assert np.array_equal(raw['variance_global'].cpu().numpy(), gl)                        # tester.py:418-421
     assert out['orig_cam'].shape == (5, 4) and torch.isfinite(out['orig_cam']).all()
+
+
+def test_latency_mode_chains_match_the_default_schedule():
+    """POCO(latency_mode=True): small batches run every HRNet branch as one persistent chained launch; same results
+    as the conv-by-conv schedule up to the fp32 accumulation order (one fp16 rounding per layer can flip)"""
+    from common import build_model
+    from poco_b200 import _lib as L
+    a = build_model('cliff_w32', 'cuda')
+    b = build_model('cliff_w32', 'cuda', latency_mode=True)
+    batch = synthetic_batch('cliff_w32', 'cuda')
+    with torch.no_grad():
+        oa, ob = a.hot_path(batch), b.hot_path(batch)
+        ob2 = b.hot_path(batch)
+    sync_or_die(120)
+    kinds = [op.kind for op in b._engine(4, batch['img'].device).plan.ops]
+    assert L.OP_CONV_CHAIN in kinds and L.OP_CONV_CHAIN not in [op.kind for op in a._engine(4, batch['img'].device).plan.ops]
+    meta, gold, _ = load_preset('cliff_w32')
+    for k in GATED:
+        assert torch.equal(ob[k], ob2[k]), k
+        assert rel_err(ob[k].cpu().numpy(), oa[k].cpu().numpy()) < E2E_TOL[k], k
+        assert rel_err(ob[k].cpu().numpy(), gold[k]) < E2E_TOL[k], k
+
+
+def test_stream_runner_graph_replay_and_padded_buckets():
+    """f2: the per-frame CUDA graph (crop -> plan -> uncertainty -> cameras) replays bit-identically to the eager body,
+    and a detection count between buckets (11 -> 16, padded with copies of the first box) returns the 11 real rows"""
+    from common import build_model
+    from oracle import crop_oracle as C
+    from poco_b200 import StreamRunner
+    m = build_model('cliff_w32', 'cuda')
+    eager, graphed = StreamRunner(m, graph=False), StreamRunner(m, graph=True)
+    for seed, n in ((3, 4), (4, 11), (5, 4), (6, 11)):          # second visit of a bucket = pure replay with new inputs
+        frame = torch.from_numpy(C.synthetic_frame(seed, 720, 1280)).cuda()
+        boxes = torch.from_numpy(C.synthetic_boxes(seed, n, 720, 1280).astype(np.float32))
+        a = eager.step(frame, boxes)
+        b = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in graphed.step(frame, boxes).items()}
+        torch.cuda.synchronize()
+        assert b['pred_pose'].shape[0] == n and b['confidence'].shape == (n,)
+        for k in ('uncert_feat', 'variance', 'variance_global', 'orig_cam') + GATED:
+            if n == m.bucket(n):
+                assert torch.equal(a[k], b[k]), (k, n)
+            else:       # another plan batch size: the split-K linear layers re-associate (crops themselves are exact)
+                assert rel_err(b[k].cpu().numpy(), a[k].cpu().numpy()) < 1e-5, (k, n)
+        assert torch.equal(a['uncert_feat'], b['uncert_feat'])
+    assert len(graphed._graphs) == 2

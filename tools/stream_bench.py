@@ -40,8 +40,9 @@ kw = {}
 if with_smpl:
     from synth import smpl_model
     kw['smpl_model'] = smpl_model.synthetic_model(0)
+kw['latency_mode'] = '--no-chains' not in sys.argv[1:]
 m = build_model('cliff_w32', dev, **kw)
-run = StreamRunner(m)
+run = StreamRunner(m, graph='--no-graph' not in sys.argv[1:])
 frames = [torch.from_numpy(C.synthetic_frame(s + 4 * rank, 1080, 1920)).to(dev) for s in range(4)]
 boxes = torch.from_numpy(C.synthetic_boxes(1 + rank, D, 1080, 1920).astype(np.float32)).to(dev)
 for i in range(10):
@@ -55,12 +56,16 @@ def barrier():
 
 
 barrier()
+lat = []
 t0 = time.perf_counter()
 for i in range(F):
+    t1 = time.perf_counter()
     out = run.step(frames[i % 4], boxes)
-    conf = out['confidence'].cpu()          # the per-frame result a caller reads back
+    conf = out['confidence'].cpu()          # the per-frame result a caller reads back (synchronises the frame)
+    lat.append(time.perf_counter() - t1)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
+lat.sort()
 t = torch.tensor([dt], device=dev)
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -72,6 +77,9 @@ if rank == 0:
     print(json.dumps({'metric': 'frames/sec', 'value': round(world * F / dt, 1), 'per_stream_fps': round(F / dt, 1),
                       'n_gpus': world, 'streams': world, 'detections_per_frame': D, 'frames_per_stream': F,
                       'ms_per_frame': round(dt / F * 1e3, 3), 'frame': '1080p uint8 RGB resident on the device',
+                      'frame_latency_ms': {'p50': round(lat[len(lat) // 2] * 1e3, 3), 'p99': round(lat[int(len(lat) * 0.99)] * 1e3, 3),
+                                           'note': 'rank 0: step() + read-back of the confidence, wall clock'},
+                      'cuda_graph_per_frame': run.use_graph,
                       'smpl_mesh_stage': with_smpl, 'timing': 'wall clock between barriers, max over ranks'}))
 if world > 1:
     dist.destroy_process_group()
