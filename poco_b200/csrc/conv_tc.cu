@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
             const ChainSeg& sg = p.seg[s];
             const __half* wg = sg.w + size_t(nb) * p.n_tile * 8;
             const int* flags_prev = s > 0 ? p.flags + size_t(s - 1) * p.num_m_tiles : nullptr;
-            int ready_upto = flags_prev != nullptr ? 0 : my_tiles;     // local tiles [0, ready_upto) may be loaded
+            int ready_upto = (flags_prev != nullptr && !(p.debug & 256)) ? 0 : my_tiles;     // local tiles [0, ready_upto) may be loaded
             for (int ju = 0; ju < my_units; ++ju) {
                 const int unit = unit_of(ju), gcount = unit_tiles(unit);
                 const int j = ju * G;                       // first local tile of the unit
@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
             int sig_first = 0, sig_owned = 0;               // local tiles [sig_first, j] still unpublished
             const uint32_t tl_seg0 = tl;
             auto signal_tiles = [&](int j_last) {
-                fence_acq_rel_gpu();
+                if (!(p.debug & 128)) fence_acq_rel_gpu();          // (128: timing experiment only -- no ordering)
                 __syncwarp();
                 const int jl = sig_first + lane;
                 if (jl <= j_last && k_first(tl_seg0 + uint32_t(jl)) < items)

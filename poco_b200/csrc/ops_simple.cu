@@ -197,22 +197,25 @@ struct FuseArgs {
     int shift[POCO_MAX_FUSE_INPUTS];
     int n_in, relu;
 };
-__global__ void __launch_bounds__(256) fuse_sum_kernel(FuseArgs a, RowMap m, int planes_per_thread) {
+// Occupancy is what these two HBM-bound kernels live on (round 2 ncu: 74 / 64 registers per thread held them at 3-4
+// blocks per SM, 34-44 % of the warp slots, and at 40 % of the HBM rate): the precision mode is a template parameter so
+// that the fp16 instantiation does not carry the lo-tensor registers, one plane is in flight per loop iteration, and
+// __launch_bounds__ keeps 5-6 blocks (62-75 % of the slots) resident in fp16 mode.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, SPLIT ? 4 : 5) fuse_sum_kernel(FuseArgs a, RowMap m, int planes_per_thread) {
     int n, y, x;
     if (!row_coords(m, a.out.H, a.out.W, n, y, x)) return;
-    long long pin[POCO_MAX_FUSE_INPUTS];
-    for (int k = 0; k < a.n_in; ++k) pin[k] = pix_index(a.in[k], n, y >> a.shift[k], x >> a.shift[k]);
+    int pin[POCO_MAX_FUSE_INPUTS];          // pixel index inside a plane (< 2^31: checked by the launcher)
+#pragma unroll
+    for (int k = 0; k < POCO_MAX_FUSE_INPUTS; ++k)
+        pin[k] = k < a.n_in ? int(pix_index(a.in[k], n, y >> a.shift[k], x >> a.shift[k])) : 0;
     const long long po = pix_index(a.out, n, y, x);
     const int pl0 = blockIdx.y * planes_per_thread;
     for (int pl = pl0; pl < pl0 + planes_per_thread; ++pl) {
-        uint4 v[POCO_MAX_FUSE_INPUTS], vl[POCO_MAX_FUSE_INPUTS];
-        const bool split = a.out.lo != nullptr;
+        uint4 v[POCO_MAX_FUSE_INPUTS];
 #pragma unroll
         for (int k = 0; k < POCO_MAX_FUSE_INPUTS; ++k)
-            if (k < a.n_in) {
-                v[k] = ld16(a.in[k], pl, pin[k]);
-                if (split) vl[k] = *reinterpret_cast<const uint4*>(a.in[k].lo + ((long long)pl * a.in[k].plane + pin[k]) * 8);
-            }
+            if (k < a.n_in) v[k] = ld16(a.in[k], pl, pin[k]);
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int k = 0; k < POCO_MAX_FUSE_INPUTS; ++k)
@@ -221,12 +224,20 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseArgs a, RowMap m, int
                 unpack8(v[k], f);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] += f[i];
-                if (split) {
-                    unpack8(vl[k], f);
+            }
+        if (SPLIT) {
+#pragma unroll
+            for (int k = 0; k < POCO_MAX_FUSE_INPUTS; ++k)
+                if (k < a.n_in) v[k] = *reinterpret_cast<const uint4*>(a.in[k].lo + ((long long)pl * a.in[k].plane + pin[k]) * 8);
+#pragma unroll
+            for (int k = 0; k < POCO_MAX_FUSE_INPUTS; ++k)
+                if (k < a.n_in) {
+                    float f[8];
+                    unpack8(v[k], f);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) acc[i] += f[i];
                 }
-            }
+        }
         if (a.relu) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
@@ -236,43 +247,29 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseArgs a, RowMap m, int
 }
 
 // bilinear x2, align_corners=True: src = dst * (in-1)/(out-1)  (matches aten upsample_bilinear2d)
-__global__ void __launch_bounds__(256) upsample2x_kernel(Act in, Act out, float sy, float sx, RowMap m, int planes_per_thread) {
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, SPLIT ? 4 : 6) upsample2x_kernel(Act in, Act out, float sy, float sx, RowMap m, int planes_per_thread) {
     int n, y, x;
     if (!row_coords(m, out.H, out.W, n, y, x)) return;
     const float fy = sy * y, fx = sx * x;
     const int y0 = min(int(fy), in.H - 1), x0 = min(int(fx), in.W - 1);
     const int y1 = min(y0 + 1, in.H - 1), x1 = min(x0 + 1, in.W - 1);
     const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const long long p00 = pix_index(in, n, y0, x0), p01 = pix_index(in, n, y0, x1);
-    const long long p10 = pix_index(in, n, y1, x0), p11 = pix_index(in, n, y1, x1);
+    const int p00 = int(pix_index(in, n, y0, x0)), p01 = int(pix_index(in, n, y0, x1));     // (< 2^31: checked by the launcher)
+    const int p10 = int(pix_index(in, n, y1, x0)), p11 = int(pix_index(in, n, y1, x1));
     const long long po = pix_index(out, n, y, x);
     const int pl0 = blockIdx.y * planes_per_thread;
-    for (int pl = pl0; pl < pl0 + planes_per_thread; pl += 2) {       // two planes = eight 16-byte loads in flight
-        if (in.lo != nullptr) {         // split-precision mode: interpolate hi + lo in fp32
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                float a[8], b[8], c[8], d[8], o[8];
-                ld8f(in, pl + q, p00, a); ld8f(in, pl + q, p01, b); ld8f(in, pl + q, p10, c); ld8f(in, pl + q, p11, d);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
-                st8f(out, pl + q, po, o);
-            }
-            continue;
-        }
-        uint4 v[2][4];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            v[q][0] = ld16(in, pl + q, p00); v[q][1] = ld16(in, pl + q, p01);
-            v[q][2] = ld16(in, pl + q, p10); v[q][3] = ld16(in, pl + q, p11);
+    for (int pl = pl0; pl < pl0 + planes_per_thread; ++pl) {
+        float a[8], b[8], c[8], d[8], o[8];
+        if (SPLIT) {            // split-precision mode: interpolate hi + lo in fp32
+            ld8f(in, pl, p00, a); ld8f(in, pl, p01, b); ld8f(in, pl, p10, c); ld8f(in, pl, p11, d);
+        } else {
+            const uint4 v0 = ld16(in, pl, p00), v1 = ld16(in, pl, p01), v2 = ld16(in, pl, p10), v3 = ld16(in, pl, p11);
+            unpack8(v0, a); unpack8(v1, b); unpack8(v2, c); unpack8(v3, d);
         }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            float a[8], b[8], c[8], d[8], o[8];
-            unpack8(v[q][0], a); unpack8(v[q][1], b); unpack8(v[q][2], c); unpack8(v[q][3], d);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
-            st16(out, pl + q, po, pack8(o));
-        }
+        for (int i = 0; i < 8; ++i) o[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+        st8f(out, pl, po, o);
     }
 }
 
@@ -406,7 +403,9 @@ extern "C" int poco_fuse_sum_run(const poco_fuse_sum* d, void* stream) {
     const int planes = d->out.C / 8;
     const int ppt = planes % 4 == 0 ? 4 : (planes % 2 == 0 ? 2 : 1);      // planes per thread: independent loads in flight
     dim3 grid(row_blocks(m), planes / ppt);
-    fuse_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, m, ppt);
+    POCO_CHECK(d->out.plane_stride < (1ll << 31), "fuse_sum: plane too large for 32-bit pixel indices");
+    if (d->out.lo != nullptr) fuse_sum_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, m, ppt);
+    else fuse_sum_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, m, ppt);
     POCO_LAUNCHED();
     return 0;
 }
@@ -423,7 +422,9 @@ extern "C" int poco_upsample2x_run(const poco_upsample2x* d, void* stream) {
     const int planes = d->out.C / 8;
     const int ppt = planes % 4 == 0 ? 4 : 2;
     dim3 grid(row_blocks(m), planes / ppt);
-    upsample2x_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(d->in), mk(d->out), sy, sx, m, ppt);
+    POCO_CHECK(d->out.plane_stride < (1ll << 31), "upsample2x: plane too large for 32-bit pixel indices");
+    if (d->out.lo != nullptr) upsample2x_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(d->in), mk(d->out), sy, sx, m, ppt);
+    else upsample2x_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mk(d->in), mk(d->out), sy, sx, m, ppt);
     POCO_LAUNCHED();
     return 0;
 }
