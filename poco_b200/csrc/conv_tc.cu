@@ -119,7 +119,6 @@ struct ConvTcParams {
     int tap_group;        // gather mode: filter taps per stage
     int debug;            // POCO_CONV_DEBUG bits (bring-up only): 1 skip epilogue work, 2 skip MMAs, 4 skip A loads,
                           // 8 skip output stores, 16 ignore the residual, 32 cycle accounting of the MMA issuers
-    int stagger;          // cycles the second MMA issuer waits before its first unit (keeps the two issuers out of phase)
     unsigned long long* prof;   // debug & 32: [2 issuers][8] cycle sums (POCO_CONV_PROF points the launcher at a buffer)
 };
 
@@ -575,11 +574,6 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         uint32_t a_buf = 0, a_par = 1u;                 // accumulator ring position of the next tile (all tiles, both issuers)
         const bool prof = (p.debug & 32) != 0;
         long long pt_acc = 0, pt_full = 0, pt_issue = 0, pt_units = 0, pt_t0 = prof ? clock64() : 0, pt_mark = 0;
-        if (mw == 1u && p.rings == 2 && p.stagger > 0) {
-            const long long t_end = clock64() + p.stagger;
-            while (clock64() < t_end) {
-            }
-        }
         for (int s = 0; s < n_segs; ++s) {
             const uint32_t w_res_u32 = smem_u32(w_res) + uint32_t(wbuf_of(s)) * uint32_t(p.w_res_bytes);
             if (p.w_resident && active) MBAR_WAIT(smem_u32(&hdr->w_ready[wbuf_of(s)]), uint32_t(wuse_of(s)) & 1u);
@@ -1106,8 +1100,6 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         const char* pr = getenv("POCO_CONV_PROF");         // device address (decimal) of 16 zeroed uint64 counters
         p.prof = pr ? reinterpret_cast<unsigned long long*>(strtoull(pr, nullptr, 10)) : nullptr;
         if (p.prof == nullptr) p.debug &= ~(32 | 64);
-        static const int stagger = [] { const char* e = getenv("POCO_B200_STAGGER"); return e ? atoi(e) : 0; }();
-        p.stagger = stagger;
     }
     p.P_out = int64_t(out.N) * (out.H + 2) * (out.W + 2);
     // weight format 1 = dx-in-N: [3 filter rows][Cin/8][3 * Cout (s-major)][8], see conv_tc_kernel
