@@ -56,7 +56,10 @@ typedef struct poco_conv {
     int32_t max_ctas; /* 0 = one CTA per SM; else cap on the persistent grid (concurrent plan lanes share the SMs) */
     int32_t wfmt; /* weight layout: 0 = [kh*kw][Cin/8][Cout][8]; 1 = "dx in N" for 3x3 / stride 1 / pad 1 with
                    * Cout in {32, 64}: [kh][Cin/8][kw*Cout][8] (column s*Cout + co of filter row r) -- the three
-                   * horizontal taps share one MMA, a third of the shared-memory operand reads */
+                   * horizontal taps share one MMA, a third of the shared-memory operand reads;
+                   * 2 = split precision with N-concatenated weights, stride-1 3x3 / 1x1 convs with Cout <= 64:
+                   * ONE tensor [kh*kw][Cin/8][2*Cout][8] whose slab rows are W_hi (rows 0..Cout-1) then W_lo -- x_hi meets
+                   * both in one N = 2*Cout MMA, the two column groups are summed in the epilogue */
     const void* residual_lo; /* split-precision mode: rounding residual of `residual` (same plane stride), else NULL */
 } poco_conv;
 

@@ -256,7 +256,12 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // are [W_hi][W_lo]; a K chunk lands as kc/8 hi planes followed by kc/8 lo planes, the issuer runs the same straight-line
 // MMA sequence three times into one accumulator -- (x_hi, W_hi), (x_lo, W_hi), (x_hi, W_lo) -- and the epilogue adds
 // residual hi + lo in fp32 and stores hi = fp16(y), lo = fp16(y - hi).  Everything else (roles, barriers, rings) is shared.
-template <int MODE, int IPL, bool DXN, int MINB = 1, bool SPLIT = false>
+// SPLIT == 2 ("N concatenation", weight format 2, Cout <= 64): the weights are ONE tensor [tap][Cin/8][2 Cout][8] whose slab
+// rows are W_hi then W_lo.  One N = 2 Cout MMA forms x_hi W_hi | x_hi W_lo side by side (the A operand -- 4 KB per MMA,
+// what bounds small-N MMAs -- is fetched once for both products), one N = Cout MMA adds x_lo W_hi to the first half, and
+// the epilogue sums the two column groups in fp32: 88 instead of 120 tensor cycles per K step at Cout = 32 (112 / 144 at
+// 64), and the 2^-11-sized x_hi W_lo term gets an accumulator of its own.
+template <int MODE, int IPL, bool DXN, int MINB = 1, int SPLIT = 0>
 __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
@@ -265,6 +270,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
     const int res_ring_n = p.res_ring;
     constexpr int ipl = IPL;                            // output planes (8 columns each) per epilogue work item
     constexpr int SP = SPLIT ? 2 : 1;
+    constexpr bool NCAT = SPLIT == 2;
     const int warp_ring_bytes = (kOutRing + res_ring_n) * ipl * 512 * SP;      // per epilogue warp: out ring + residual ring
     uint8_t* w_res = smem + kHeaderBytes + 8 * warp_ring_bytes;
     uint8_t* stage0 = w_res + p.w_res_bytes * p.w_bufs;
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
     const int planes_per_chunk = p.kc >> 3;
     const int cin8 = p.Cin >> 3;
     const int kiters = MODE == MODE_LINEAR ? p.n_chunks : p.n_chunks * (taps / p.tap_group);
-    const uint32_t slab_bytes = uint32_t(p.n_tile) * 16u;     // one (tap, 8-channel) weight slab
+    const uint32_t slab_bytes = uint32_t(p.n_tile) * (NCAT ? 32u : 16u);     // one (tap, 8-channel) weight slab
     const int n_segs = MODE == MODE_LINEAR ? p.n_segs : 1;
     // Work unit = G adjacent tiles (G = 1 outside MODE_LINEAR): unit u of this CTA's j-th turn is
     // blockIdx.x + j * gridDim.x and covers tiles [u * G, u * G + G); only the globally last unit can be short.
@@ -329,15 +335,15 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
     // UTCHMMA in a vote + branch "waterfall", ~60 issue slots per MMA -- see profiles/).
     // When this CTA covers all of Cout (one N block), consecutive 8-channel slabs are contiguous in
     // global and shared memory, so `group` slabs travel as one bulk copy.
-    const int w_n = DXN ? 3 * p.Cout : p.Cout;       // columns of one (tap, 8-channel) slab of the weight tensor
-    const bool whole_n = p.n_tile == w_n;
+    const int w_n = DXN ? 3 * p.Cout : (NCAT ? 2 * p.Cout : p.Cout);       // columns of one (tap, 8-channel) slab of the weight tensor
+    const bool whole_n = NCAT || p.n_tile == w_n;
     auto load_resident_weights = [&](int s) {      // weights of segment s -> resident buffer s % w_bufs
         const int b = p.w_bufs == 2 ? (s & 1) : 0;
         const __half* wg = p.seg[s].w + size_t(nb) * p.n_tile * 8;
         const uint32_t dst = smem_u32(w_res) + uint32_t(b) * uint32_t(p.w_res_bytes);
         const uint32_t bar = smem_u32(&hdr->w_ready[b]);
         mbar_arrive_expect_tx(bar, uint32_t(p.w_res_bytes));
-        const int total = taps * cin8 * SP;                      // (split mode: the W_lo tensor follows W_hi, slab for slab)
+        const int total = taps * cin8 * (NCAT ? 1 : SP);         // (split mode: the W_lo tensor follows W_hi, slab for slab; N concatenation: double-size slabs)
         const int group = whole_n ? min(total, 64) : 1;          // <= 64 slabs (<= 256 KB) per copy
         for (int i = 0; i < total; i += group) {
             const int g = min(group, total - i);
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                         }
                         if (!p.w_resident) {
                             load_stage_weights(wg, st + p.a_stage_bytes, bar, 0, taps, c);
-                            if (SPLIT) load_stage_weights(wg + w_lo_off, st + p.a_stage_bytes + (p.w_stage_bytes >> 1), bar, 0, taps, c);
+                            if (SPLIT == 1) load_stage_weights(wg + w_lo_off, st + p.a_stage_bytes + (p.w_stage_bytes >> 1), bar, 0, taps, c);
                         }
                     }
                     __syncwarp();
@@ -556,7 +562,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         // Two warps take alternate tiles, one stage ring each, so one warp's barrier round trips overlap
         // the other's MMAs (profiles/r01_conv_role_bench.csv).
         const uint32_t mw = uint32_t(warp - R::kMmaWarp);
-        const uint32_t idesc = umma_idesc_f16(kTileM, uint32_t(p.n_tile));
+        const uint32_t idesc = umma_idesc_f16(kTileM, uint32_t(p.n_tile) * (NCAT ? 2u : 1u));
+        const uint32_t idesc_half = umma_idesc_f16(kTileM, uint32_t(p.n_tile));      // N concatenation: the x_lo W_hi product
         // descriptor = hi:lo, lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version<<14: only lo changes
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);
         const uint32_t a_lbo = (uint32_t(p.a_plane_bytes) >> 4) << 16, b_lbo = (slab_bytes >> 4) << 16;
@@ -624,6 +631,11 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                             if (!(p.debug & 2)) {
 #define POCO_ISSUE(T, K)                                                                                                    \
     do {                                                                                                                    \
+        if (NCAT) {         /* x_hi [W_hi | W_lo] into both column groups, then x_lo W_hi onto the first */                 \
+            issue_linear<T, K>(d_tmem, a_lo, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, acc);                \
+            issue_linear<T, K>(d_tmem, a_lo2, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc_half, 1u);           \
+            break;                                                                                                          \
+        }                                                                                                                   \
         if (SPLIT) {        /* x_lo W_hi + x_hi W_lo first: the tensor core truncates every accumulation to the magnitude */ \
                             /* of the running sum, so the 2^-11-sized correction terms go in while it is still small     */ \
             issue_linear<T, K>(d_tmem, a_lo2, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, acc);               \
@@ -918,7 +930,16 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                     } else {
                         tmem_ld16(taddr + uint32_t(c0), v);
                         if (IPL == 4 && planes == 4) tmem_ld16(taddr + uint32_t(c0 + 16), v + (IPL == 4 ? 16 : 0));
-                        tmem_ld_wait();
+                        if (NCAT) {             // second column group: the x_hi W_lo products of the same output channels
+                            uint32_t v2[IPL * 8];
+                            tmem_ld16(taddr + uint32_t(n_out + c0), v2);
+                            if (IPL == 4 && planes == 4) tmem_ld16(taddr + uint32_t(n_out + c0 + 16), v2 + (IPL == 4 ? 16 : 0));
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < IPL * 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+                        } else {
+                            tmem_ld_wait();
+                        }
                         if (item + 2 >= items) {            // this warp is done with the accumulator buffer
                             tc_fence_before();
                             __syncwarp();
@@ -1050,7 +1071,9 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
 
     const bool split = in.lo != nullptr;          // split-precision ("parity") mode: see the SPLIT template parameter
     const int sp = split ? 2 : 1;
-    POCO_CHECK(!split || (out.lo != nullptr && n_segs == 1 && d->wfmt == 0), "split precision: out.lo missing, or a chain / dx-in-N conv");
+    POCO_CHECK(!split || (out.lo != nullptr && n_segs == 1 && (d->wfmt == 0 || d->wfmt == 2)), "split precision: out.lo missing, or a chain / dx-in-N conv");
+    const bool ncat = d->wfmt == 2;        // split precision with N-concatenated weights [tap][Cin/8][2 Cout][8]
+    POCO_CHECK(!ncat || (split && out.C <= 64), "weight format 2 needs split precision and Cout <= 64");
     POCO_CHECK(split || out.lo == nullptr, "out.lo given but in.lo is null");
     POCO_CHECK(!split || !d->residual || d->residual_lo, "split precision: residual_lo missing");
     ConvTcParams p{};
@@ -1104,7 +1127,7 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     p.P_out = int64_t(out.N) * (out.H + 2) * (out.W + 2);
     // weight format 1 = dx-in-N: [3 filter rows][Cin/8][3 * Cout (s-major)][8], see conv_tc_kernel
     const bool dxn = d->wfmt == 1;
-    POCO_CHECK(d->wfmt == 0 || d->wfmt == 1, "unknown weight format");
+    POCO_CHECK(d->wfmt >= 0 && d->wfmt <= 2, "unknown weight format");
     p.tile_stride = dxn ? kTileM - 2 : kTileM;
     p.tile_origin = dxn ? -1 : 0;
     p.num_m_tiles = int((p.P_out + p.tile_stride - 1) / p.tile_stride);
@@ -1130,8 +1153,8 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     POCO_CHECK(n_tile > 0 && n_tile <= 256, "no valid N tile");
     p.n_tile = n_tile;
     const int n_blocks = dxn ? 1 : out.C / n_tile;
-    int cols = 32;                      // accumulator buffer pitch: power of two >= n_tile
-    while (cols < n_tile) cols <<= 1;
+    int cols = 32;                      // accumulator buffer pitch: power of two >= n_tile (two column groups with N concatenation)
+    while (cols < n_tile * (ncat ? 2 : 1)) cols <<= 1;
     // Two CTAs per SM ("half" configuration: <= 110 KB of shared memory, <= 256 TMEM columns) for the layers with
     // N <= 64: measured on one box against the one-CTA configuration, 32->32 @56 33.6 -> 30.3 us (no residual) and
     // 42.6 -> 40.0 us (residual), 64->64 @28 29.5 -> 27.2 us -- two independent producer / issuer / epilogue sets
@@ -1302,15 +1325,20 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         cfg.blockDim = dim3(threads);
         return cudaLaunchKernelEx(&cfg, kernel, pk);
     };
-    static std::once_flag once4[11];
-    if (split && mode == MODE_LINEAR && p.item_planes == 2)
-        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 1, true>, once4[7], Roles<MODE_LINEAR>::kThreads));
+    static std::once_flag once4[13];
+    POCO_CHECK(!ncat || mode == MODE_LINEAR, "weight format 2 is for stride-1 3x3 / 1x1 convs");
+    if (ncat && p.item_planes == 2)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 1, 2>, once4[11], Roles<MODE_LINEAR>::kThreads));
+    else if (ncat)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false, 1, 2>, once4[12], Roles<MODE_LINEAR>::kThreads));
+    else if (split && mode == MODE_LINEAR && p.item_planes == 2)
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 1, 1>, once4[7], Roles<MODE_LINEAR>::kThreads));
     else if (split && mode == MODE_LINEAR)
-        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false, 1, true>, once4[8], Roles<MODE_LINEAR>::kThreads));
+        POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false, 1, 1>, once4[8], Roles<MODE_LINEAR>::kThreads));
     else if (split && p.item_planes == 2)
-        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 2, false, 1, true>, once4[9], Roles<MODE_GATHER>::kThreads));
+        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 2, false, 1, 1>, once4[9], Roles<MODE_GATHER>::kThreads));
     else if (split)
-        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 4, false, 1, true>, once4[10], Roles<MODE_GATHER>::kThreads));
+        POCO_CUDA(launch(conv_tc_kernel<MODE_GATHER, 4, false, 1, 1>, once4[10], Roles<MODE_GATHER>::kThreads));
     else if (half && p.item_planes == 2)
         POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 2>, once4[5], Roles<MODE_LINEAR>::kThreads));
     else if (half)

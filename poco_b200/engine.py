@@ -120,7 +120,16 @@ def pack_conv_weight(w, cin_pad=None, split=False):
     hi = p.to(torch.float16)
     if not split:
         return hi
-    return torch.stack([hi, (p.float() - hi.float()).to(torch.float16)]).contiguous()
+    lo = (p.float() - hi.float()).to(torch.float16)
+    if split == 'ncat':         # weight format 2: [kh*kw][Cin/8][2*Cout][8], slab rows W_hi then W_lo
+        return torch.cat([hi, lo], 2).contiguous()
+    return torch.stack([hi, lo]).contiguous()
+
+
+def split_wfmt(cout, k, stride, pad):
+    """split-precision convs with Cout <= 64 on the stride-1 path use the N-concatenated weight format (2)"""
+    linear = stride == 1 and ((k == 3 and pad == 1) or (k == 1 and pad == 0))
+    return 2 if (linear and cout <= 64 and os.environ.get('POCO_B200_NCAT', '1') != '0') else 0
 
 
 def pack_conv_weight_dxn(w):
@@ -281,12 +290,13 @@ class PlanBuilder:
         wf, bf = fold_bn(w, None, bnp)
         w1 = wf.permute(0, 2, 3, 1).reshape(cout, 27)               # k = (r*3+s)*3 + c
         w1 = torch.cat([w1, w1.new_zeros(cout, 5)], 1).reshape(cout, 32, 1, 1)
-        wp = pack_conv_weight(w1, split=self.split).to(self.device)
+        wfmt = split_wfmt(cout, 1, 1, 0) if (self.split and self.conv_impl == 0) else 0
+        wp = pack_conv_weight(w1, split=('ncat' if wfmt == 2 else self.split)).to(self.device)
         bf = bf.contiguous().to(self.device)
         self.keep += [wp, bf]
         out = self.act(cout, H // 2, W // 2)
         d = L.Conv(col.desc(), out.desc(), wp.data_ptr(), bf.data_ptr(), None, 0, 1, 1, 1, 0, 1, self.conv_impl,
-                   self.shares[self.lane] if self.shares is not None else 0)
+                   self.shares[self.lane] if self.shares is not None else 0, wfmt)
         self.add(d)
         self.conv_log.append((conv, 32, cout, 1, 1, H // 2, H // 2))
         self.free(col)
@@ -313,7 +323,10 @@ class PlanBuilder:
         pad = k // 2 if pad is None else pad
         wfmt = 1 if (self.conv_impl == 0 and self.chain is None and x.C == cin and not self.split and
                      dxn_applies(cin, cout, k, stride, pad)) else 0
-        wp = pack_conv_weight_dxn(torch.cat(ws, 0)) if wfmt else pack_conv_weight(torch.cat(ws, 0), cin_pad=x.C, split=self.split)
+        if self.split and self.conv_impl == 0 and self.chain is None:
+            wfmt = split_wfmt(cout, k, stride, pad)
+        wp = pack_conv_weight_dxn(torch.cat(ws, 0)) if wfmt == 1 else \
+            pack_conv_weight(torch.cat(ws, 0), cin_pad=x.C, split=('ncat' if wfmt == 2 else self.split))
         wp = wp.to(self.device)
         bf = torch.cat(bs, 0).contiguous().to(self.device)
         self.keep += [wp, bf]

@@ -81,9 +81,13 @@ class Emu:
             w = wp.permute(3, 1, 4, 0, 2).reshape(o.C, i.C, 3, 3)
         else:
             nw = taps * i.C * o.C
-            wp = self.flat(d.weight, torch.float16)[:nw].view(taps, i.C // 8, o.C, 8).float()
-            if i.lo:        # split-precision mode: W_lo follows W_hi
-                wp = wp + self.flat(d.weight, torch.float16)[nw:2 * nw].view(taps, i.C // 8, o.C, 8).float()
+            if d.wfmt == 2:     # split precision, N-concatenated: slab rows W_hi then W_lo
+                w2 = self.flat(d.weight, torch.float16)[:2 * nw].view(taps, i.C // 8, 2 * o.C, 8).float()
+                wp = w2[:, :, :o.C] + w2[:, :, o.C:]
+            else:
+                wp = self.flat(d.weight, torch.float16)[:nw].view(taps, i.C // 8, o.C, 8).float()
+                if i.lo:        # split-precision mode: W_lo follows W_hi
+                    wp = wp + self.flat(d.weight, torch.float16)[nw:2 * nw].view(taps, i.C // 8, o.C, 8).float()
             w = wp.permute(2, 1, 3, 0).reshape(o.C, i.C, d.kh, d.kw)
         b = self.flat(d.bias, torch.float32)[:o.C]
         y = F.conv2d(self.act_get(i), w, b, stride=d.stride, padding=d.pad)

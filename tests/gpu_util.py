@@ -38,11 +38,13 @@ def run_conv(x, w, bias, stride=1, pad=None, relu=1, residual=None, impl=0, dxn=
     a = engine.to_planar(x.to(dev), c_pad=cin_p, split=split)
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     o = engine.alloc_act(Cout, N, Ho, Wo, dev, split)
-    wp = engine.pack_conv_weight_dxn(w.to(dev).float()) if dxn else engine.pack_conv_weight(w.to(dev).float(), cin_pad=cin_p, split=split)
+    wfmt = 1 if dxn else (engine.split_wfmt(Cout, k, stride, pad) if (split and impl == 0) else 0)
+    wp = engine.pack_conv_weight_dxn(w.to(dev).float()) if dxn else \
+        engine.pack_conv_weight(w.to(dev).float(), cin_pad=cin_p, split=('ncat' if wfmt == 2 else split))
     b = bias.to(dev).float().contiguous()
     r = engine.to_planar(residual.to(dev), split=split) if residual is not None else None
     d = L.Conv(a.desc(), o.desc(), wp.data_ptr(), b.data_ptr(), r.ptr if r is not None else None,
-               r.plane_stride if r is not None else 0, k, k, stride, pad, relu, impl, 0, 1 if dxn else 0,
+               r.plane_stride if r is not None else 0, k, k, stride, pad, relu, impl, 0, wfmt,
                r.ptr_lo if r is not None else None)
     L.run_op(d, stream())
     sync_or_die()
