@@ -232,6 +232,19 @@ class PlanBuilder:
     def add(self, desc):
         self.ops.append(L.make_op(desc, lane=self.lane))
 
+    def _share(self):
+        """CTA budget of a conv launched now: 0 (all SMs) outside a fork, else POCO_B200_SHARE_SCALE (default 2) x the
+        lane's cost-proportional share of the SMs.  The shares of the concurrent lanes deliberately add up to twice
+        the SM count: a lane's SMs idle for ~10 us around each of its launches (launch gap + pipeline fill), and with
+        oversubscription the hardware block scheduler hands those SMs to another lane's queued CTAs in the meantime
+        (persistent CTAs that start late just take their strided share of the units later).  Measured (round 2, one
+        box): cliff_w32 fp16 11.84 -> 11.66 ms, split 29.2 -> 27.0 ms, cliff_w48cls 19.0 -> 17.0 ms; scale 3 and
+        "every launch asks for all SMs" (scale 0) are slower than 2."""
+        if self.shares is None:
+            return 0
+        sc = float(os.environ.get('POCO_B200_SHARE_SCALE', '2'))
+        return 0 if sc <= 0 else max(1, min(self.num_sms, int(round(self.shares[self.lane] * sc))))
+
     # -- lanes: independent op chains that the plan runs concurrently on internal streams
     def fork(self, costs):
         """start len(costs) concurrent lanes; `costs` (relative work) decide each lane's share of the SMs"""
@@ -296,7 +309,7 @@ class PlanBuilder:
         self.keep += [wp, bf]
         out = self.act(cout, H // 2, W // 2)
         d = L.Conv(col.desc(), out.desc(), wp.data_ptr(), bf.data_ptr(), None, 0, 1, 1, 1, 0, 1, self.conv_impl,
-                   self.shares[self.lane] if self.shares is not None else 0, wfmt)
+                   self._share(), wfmt)
         self.add(d)
         self.conv_log.append((conv, 32, cout, 1, 1, H // 2, H // 2))
         self.free(col)
@@ -341,7 +354,7 @@ class PlanBuilder:
                    residual.ptr if residual is not None else None,
                    residual.plane_stride if residual is not None else 0,
                    k, k, stride, pad, int(relu), self.conv_impl,
-                   self.shares[self.lane] if self.shares is not None else 0, wfmt,
+                   self._share(), wfmt,
                    residual.ptr_lo if residual is not None else None)
         if self.chain is not None:
             self.chain.append(d)
