@@ -35,8 +35,8 @@ per = collections.defaultdict(lambda: collections.defaultdict(float))
 for x in d:
     per[(x['ID'])][x['Metric Name']] = float(x['Metric Value'].replace(',', '')) * {'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'Gbyte': 1e9, 'us': 1, 'usecond': 1, 'ns': 1e-3, 'nsecond': 1e-3, 'ms': 1e3, 'msecond': 1e3}.get(x['Metric Unit'], 1)
     per[(x['ID'])]['name'] = x['Kernel Name']
-lin = [v for v in per.values() if 'conv_tc_kernel<(int)0' in v['name']]
-gat = [v for v in per.values() if 'conv_tc_kernel<(int)1' in v['name']]
+lin = [v for v in per.values() if 'conv_tc_kernel<0' in v['name']]
+gat = [v for v in per.values() if 'conv_tc_kernel<1' in v['name']]
 def avg(vs, k): return sum(v[k] for v in vs) / max(1, len(vs))
 sha = hashlib.sha256(open('poco_b200/libpoco_b200.so', 'rb').read()).hexdigest()[:16]
 out = {'kernel': 'conv_tc_linear', 'launches_captured': len(lin),
