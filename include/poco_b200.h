@@ -61,6 +61,17 @@ typedef struct poco_conv {
                    * ONE tensor [kh*kw][Cin/8][2*Cout][8] whose slab rows are W_hi (rows 0..Cout-1) then W_lo -- x_hi meets
                    * both in one N = 2*Cout MMA, the two column groups are summed in the epilogue */
     const void* residual_lo; /* split-precision mode: rounding residual of `residual` (same plane stride), else NULL */
+    /* Space-to-depth plumbing of the stride-2 convs (hrnet.py:213-240, :345-384, resnet.py:100-121 with stride 2).
+     * A 3x3 / stride 2 / pad 1 conv reads input pixel (2y + r - 1, 2x + s - 1): in the PHASE-SPLIT form of its input --
+     * 4*C channels at half resolution, channel ((y & 1) * 2 + (x & 1)) * C + c of pixel (y / 2, x / 2) -- every tap is
+     * one phase block at a shift of -1 / 0 rows and pixels, so the conv runs on the contiguous halo-run path of the
+     * stride-1 convs (one bulk copy per plane, every input byte fetched once) instead of gathering 16 bytes of every
+     * 32-byte sector.  The producing conv writes that form from its epilogue: */
+    poco_act out_s2d;  /* data NULL: none.  Else a second output, the phase-split form of `out` (4*out.C channels,
+                        * out.H/2 x out.W/2, H and W even, same precision mode), written next to `out` */
+    int32_t s2d_only;  /* 1: write out_s2d only (`out` still describes the geometry; its memory is not touched) */
+    int32_t in_s2d;    /* 1: `in` IS the phase-split form of the real input (in.C = 4*Cin, in.H = out.H) and the conv is
+                        * the 3x3 / stride 2 / pad 1 conv of that real input; weights keep the [9][Cin/8][Cout][8] layout */
 } poco_conv;
 
 /* A chain of convolutions of ONE geometry (3x3/s1/p1 or 1x1/s1, Cin == Cout) executed by one persistent

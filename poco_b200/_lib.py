@@ -29,7 +29,7 @@ class Conv(C.Structure):
                 ('residual', C.c_void_p), ('res_plane_stride', C.c_int64),
                 ('kh', C.c_int32), ('kw', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
                 ('relu', C.c_int32), ('impl', C.c_int32), ('max_ctas', C.c_int32), ('wfmt', C.c_int32),
-                ('residual_lo', C.c_void_p)]
+                ('residual_lo', C.c_void_p), ('out_s2d', Act), ('s2d_only', C.c_int32), ('in_s2d', C.c_int32)]
 
 
 class ConvChain(C.Structure):

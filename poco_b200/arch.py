@@ -44,12 +44,13 @@ class SpecBackend:
     def pack_image(self, img, H, W):
         return SymAct(16, H, W)
 
-    def stem_conv(self, img, H, W, conv, bn, cout):
+    def stem_conv(self, img, H, W, conv, bn, cout, s2d=None):
         self._p(conv + '.weight', (cout, 3, 3, 3))
         self._bn(bn, cout)
         return SymAct(cout, H // 2, W // 2)
 
-    def conv_bn(self, x, conv, bn, cin, cout, k, stride=1, relu=True, residual=None, out=None, pad=None, bias=False):
+    def conv_bn(self, x, conv, bn, cin, cout, k, stride=1, relu=True, residual=None, out=None, pad=None, bias=False,
+                s2d=None):
         convs = conv if isinstance(conv, (list, tuple)) else [conv]
         bns = bn if isinstance(bn, (list, tuple)) else [bn] * len(convs)
         each = cout // len(convs)
@@ -139,26 +140,29 @@ def conv_cost(N, cin, cout, k, Hout, Wout):
 # ------------------------------------------------------------------------------------------------
 # residual blocks
 # ------------------------------------------------------------------------------------------------
-def basic_block(b, x, name, cin, cout, free_input=True):
-    """conv3x3-BN-ReLU, conv3x3-BN, += x, ReLU  (hrnet.py:42-58); HRNet branches never downsample"""
+def basic_block(b, x, name, cin, cout, free_input=True, s2d_out=None):
+    """conv3x3-BN-ReLU, conv3x3-BN, += x, ReLU  (hrnet.py:42-58); HRNet branches never downsample.
+    s2d_out: the block's output also feeds stride-2 convs -> its last conv writes the phase-split copy too"""
     y = b.conv_bn(x, name + '.conv1', name + '.bn1', cin, cout, 3)
-    o = b.conv_bn(y, name + '.conv2', name + '.bn2', cout, cout, 3, residual=x)
+    o = b.conv_bn(y, name + '.conv2', name + '.bn2', cout, cout, 3, residual=x, s2d=s2d_out)
     b.free(y)
     if free_input:
         b.free(x)
     return o
 
 
-def bottleneck(b, x, name, cin, planes, stride=1, downsample=False, free_input=True):
-    """1x1 -> 3x3(stride) -> 1x1 x4, residual (v1.5)  (hrnet.py:79-99, resnet.py:100-121)"""
+def bottleneck(b, x, name, cin, planes, stride=1, downsample=False, free_input=True, s2d_out=None):
+    """1x1 -> 3x3(stride) -> 1x1 x4, residual (v1.5)  (hrnet.py:79-99, resnet.py:100-121).
+    s2d_out: see basic_block (a strided block reads phase-split copies: of conv1's output, and of the block input
+    for the strided 1x1 downsample when the previous block wrote one)"""
     cout = planes * 4
-    y1 = b.conv_bn(x, name + '.conv1', name + '.bn1', cin, planes, 1)
+    y1 = b.conv_bn(x, name + '.conv1', name + '.bn1', cin, planes, 1)      # (phase-split hand-off to a strided conv2 measured slower on ResNet-50)
     y2 = b.conv_bn(y1, name + '.conv2', name + '.bn2', planes, planes, 3, stride)
     b.free(y1)
     r = x
     if downsample:
         r = b.conv_bn(x, name + '.downsample.0', name + '.downsample.1', cin, cout, 1, stride, relu=False)
-    o = b.conv_bn(y2, name + '.conv3', name + '.bn3', planes, cout, 1, residual=r)
+    o = b.conv_bn(y2, name + '.conv3', name + '.bn3', planes, cout, 1, residual=r, s2d=s2d_out)
     b.free(y2)
     if r is not x:
         b.free(r)
@@ -212,7 +216,11 @@ def hr_module(b, xs, name, chans, out0=None):
         if chained:
             b.begin_chain()
         for k in range(4):
-            x = basic_block(b, x, f'{name}.branches.{i}.{k}', chans[i], chans[i])
+            # A branch's output feeds the stride-2 fuse convs of every lower-resolution output.  Its last conv writes the
+            # phase-split copy as well when at least two of them read it: the second write of the tensor costs about what
+            # ONE consumer gains by leaving the gather path (measured: +16 us on 32->32 @56, -11...-15 us per consumer).
+            x = basic_block(b, x, f'{name}.branches.{i}.{k}', chans[i], chans[i],
+                            s2d_out='dual' if (k == 3 and nb - 1 - i >= 2 and not chained) else None)
         if chained:
             b.end_chain(groups=chain_groups(i, nb))
         xs[i] = x
@@ -247,8 +255,8 @@ def hr_module(b, xs, name, chans, out0=None):
                 t = xs[j]
                 for k in range(i - j):
                     f = f'{name}.fuse_layers.{i}.{j}.{k}'
-                    if k != i - j - 1:
-                        t2 = b.conv_bn(t, f + '.0', f + '.1', chans[j], chans[j], 3, 2, relu=True)
+                    if k != i - j - 1:      # (read by the next stride-2 conv only: phase-split form only)
+                        t2 = b.conv_bn(t, f + '.0', f + '.1', chans[j], chans[j], 3, 2, relu=True, s2d='only')
                     else:
                         t2 = b.conv_bn(t, f + '.0', f + '.1', chans[j], chans[i], 3, 2, relu=(j == i - 1), residual=acc)
                         if acc is not xs[i]:
@@ -271,7 +279,7 @@ def hrnet_trunk(b, img, widths, H=224, W=224, prefix='backbone.', final_out0=Non
     """final_out0(H, W) -> activation slice the LAST module writes its branch-0 output into (hrnet_pose: the
     first 32 channels of the 480-channel feature buffer, which saves a copy kernel)"""
     p = prefix
-    y = b.stem_conv(img, H, W, p + 'conv1', p + 'bn1', 64)
+    y = b.stem_conv(img, H, W, p + 'conv1', p + 'bn1', 64, s2d='only')      # read by the stride-2 conv2 only
     x = b.conv_bn(y, p + 'conv2', p + 'bn2', 64, 64, 3, 2)
     b.free(y)
     for k in range(4):
@@ -328,12 +336,14 @@ def hrnet_cls(b, img, width=48, prefix='backbone.'):
     widths = [width, 2 * width, 4 * width, 8 * width]
     ys = hrnet_trunk(b, img, widths, prefix=prefix)
     head = [32, 64, 128, 256]
-    y = bottleneck(b, ys[0], f'{prefix}incre_modules.0.0', widths[0], head[0], downsample=True)
+    # (every y below is read by the next stride-2 downsamp conv only: phase-split form only)
+    y = bottleneck(b, ys[0], f'{prefix}incre_modules.0.0', widths[0], head[0], downsample=True, s2d_out='only')
     for i in range(3):
         inc = bottleneck(b, ys[i + 1], f'{prefix}incre_modules.{i + 1}.0', widths[i + 1], head[i + 1], downsample=True)
         d = f'{prefix}downsamp_modules.{i}'
         # y = incre(x_{i+1}) + ReLU(BN(conv3x3 s2 (y)))  -> ReLU *before* the residual add (relu=2)
-        y2 = b.conv_bn(y, d + '.0', d + '.1', head[i] * 4, head[i + 1] * 4, 3, 2, relu=2, residual=inc, bias=True)
+        y2 = b.conv_bn(y, d + '.0', d + '.1', head[i] * 4, head[i + 1] * 4, 3, 2, relu=2, residual=inc, bias=True,
+                       s2d='only' if i < 2 else None)
         b.free(y)
         b.free(inc)
         y = y2

@@ -45,12 +45,20 @@ extern "C" int poco_device_check(int device) {
 }
 
 extern "C" int poco_conv_run(const poco_conv* d, void* stream) {
-    if (check_act(d->in, "in") || check_act(d->out, "out")) return 1;
+    if (check_act(d->in, "in")) return 1;
+    if (d->s2d_only && d->out.data == nullptr) {        // geometry-only: nothing is written through `out`
+        POCO_CHECK(d->out.C > 0 && d->out.C % 8 == 0 && d->out.N > 0 && d->out.H > 0 && d->out.W > 0 &&
+                       d->out.plane_stride >= int64_t(d->out.N) * (d->out.H + 2) * (d->out.W + 2), "out: bad geometry");
+    } else if (check_act(d->out, "out")) {
+        return 1;
+    }
     POCO_CHECK(d->weight && d->bias, "null weight / bias");
     POCO_CHECK(d->kh >= 1 && d->kw >= 1 && d->pad >= 0, "bad kernel geometry");
     POCO_CHECK(!d->residual || d->res_plane_stride >= int64_t(d->out.N) * (d->out.H + 2) * (d->out.W + 2),
                "residual plane stride too small");
-    POCO_CHECK(d->impl == 0 || d->wfmt == 0, "the debug kernel reads the standard weight layout only");
+    POCO_CHECK(d->impl == 0 || (d->wfmt == 0 && !d->in_s2d && d->out_s2d.data == nullptr),
+               "the debug kernel reads the standard weight layout and knows no space-to-depth plumbing");
+    if (d->out_s2d.data != nullptr && check_act(d->out_s2d, "out_s2d")) return 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return d->impl == 1 ? conv_ref_launch(d, s) : conv_tc_launch(d, s);
 }

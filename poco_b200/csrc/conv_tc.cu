@@ -117,6 +117,14 @@ struct ConvTcParams {
     int res_ring;         // residual prefetch ring depth per epilogue half
     int item_planes;      // epilogue work item = item_planes x 8 accumulator columns (2 or 4)
     int tap_group;        // gather mode: filter taps per stage
+    // space-to-depth plumbing of the stride-2 convs (see poco_conv.in_s2d / out_s2d)
+    int in_s2d;           // the input is the phase-split tensor: 4 phase blocks of Cin/8 planes at the OUTPUT resolution
+    int halo_hi;          // pixels fetched behind the tile run (= halo, 0 for in_s2d: its taps reach back only)
+    __half* s2d_out;      // second output: phase-split copy of `out` (4 Cout channels at half resolution), or nullptr
+    __half* s2d_out_lo;
+    long long s2d_plane;  // its plane stride (pixels)
+    int s2d_Wp, s2d_HpWp; // its padded row pitch / padded pixels per crop
+    int s2d_only;         // skip the normal store
     int debug;            // POCO_CONV_DEBUG bits (bring-up only): 1 skip epilogue work, 2 skip MMAs, 4 skip A loads,
                           // 8 skip output stores, 16 ignore the residual, 32 cycle accounting of the MMA issuers
     unsigned long long* prof;   // debug & 32: [2 issuers][8] cycle sums (POCO_CONV_PROF points the launcher at a buffer)
@@ -169,7 +177,7 @@ __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return (u
 #define POCO_ISSUE_BATCH 12
 #endif
 template <int TAPS, int KS>
-__device__ __forceinline__ void issue_linear(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, int Wp, uint32_t a_kstep,
+__device__ __forceinline__ void issue_linear(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, const uint32_t (&sh)[9], uint32_t a_kstep,
                                              uint32_t b_kstep, uint32_t b_tap, uint32_t desc_hi, uint32_t idesc,
                                              uint32_t acc0) {
 #if POCO_ISSUE_BATCH > 0
@@ -182,7 +190,7 @@ __device__ __forceinline__ void issue_linear(uint32_t d_tmem, uint32_t a_lo, uin
         for (int i = 0; i < BATCH; ++i) {
             const int j = j0 + i, t = j / KS, k = j % KS;
             if (j < TOTAL) {
-                al[i] = a_lo + (TAPS == 1 ? 0u : TAPS == 3 ? uint32_t((t - 1) * Wp) : uint32_t((t / 3 - 1) * Wp + (t % 3 - 1))) + uint32_t(k) * a_kstep;
+                al[i] = a_lo + sh[t] + uint32_t(k) * a_kstep;       // sh: where tap t starts inside the landed run
                 bl[i] = b_lo + uint32_t(t) * b_tap + uint32_t(k) * b_kstep;
             }
         }
@@ -196,8 +204,7 @@ __device__ __forceinline__ void issue_linear(uint32_t d_tmem, uint32_t a_lo, uin
 #else
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) {
-        // tap (r,s): shift of (r-1) rows and (s-1) pixels inside the landed run (16 B per pixel = 1 descriptor unit)
-        const uint32_t at = a_lo + (TAPS == 1 ? 0u : TAPS == 3 ? uint32_t((t - 1) * Wp) : uint32_t((t / 3 - 1) * Wp + (t % 3 - 1)));
+        const uint32_t at = a_lo + sh[t];
         const uint32_t bt = b_lo + uint32_t(t) * b_tap;
 #pragma unroll
         for (int k = 0; k < KS; ++k)
@@ -261,7 +268,10 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // what bounds small-N MMAs -- is fetched once for both products), one N = Cout MMA adds x_lo W_hi to the first half, and
 // the epilogue sums the two column groups in fp32: 88 instead of 120 tensor cycles per K step at Cout = 32 (112 / 144 at
 // 64), and the 2^-11-sized x_hi W_lo term gets an accumulator of its own.
-template <int MODE, int IPL, bool DXN, int MINB = 1, int SPLIT = 0>
+// S2DOUT: the epilogue also writes the phase-split copy of the output (poco_conv.out_s2d).  A template parameter, not a
+// run-time branch: carrying the extra address arithmetic and predicates in every instantiation cost the epilogue-bound
+// layers up to 27 % (64->256 1x1 + residual: 205 -> 261 us) when it was tried as a branch.
+template <int MODE, int IPL, bool DXN, int MINB = 1, int SPLIT = 0, bool S2DOUT = false>
 __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
@@ -412,7 +422,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                 }
                 // one contiguous run per plane: the unit's tiles plus ONE halo on each side
                 const long long q0 = (long long)unit * G * p.tile_stride + p.tile_origin - p.halo;
-                const uint32_t copy_bytes = uint32_t(((gcount - 1) * p.tile_stride + kTileM + 2 * p.halo) * 16);
+                const uint32_t copy_bytes = uint32_t(((gcount - 1) * p.tile_stride + kTileM + p.halo + p.halo_hi) * 16);
                 const uint32_t ring = p.rings == 2 ? (ul & 1u) : 0u;
                 ++ul;
                 for (int c = 0; c < p.n_chunks; ++c) {
@@ -422,18 +432,23 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                     if (elect_one()) {
                         const uint32_t bar = smem_u32(&hdr->full[slot]);
                         const bool skip_a = (p.debug & 4) != 0;
-                        const uint32_t tx = (skip_a ? 0u : uint32_t(planes_per_chunk * SP) * copy_bytes) +
+                        const int phases = p.in_s2d ? 4 : 1;       // phase-split input: the chunk's channels of all four phases
+                        const uint32_t tx = (skip_a ? 0u : uint32_t(planes_per_chunk * phases * SP) * copy_bytes) +
                                             (p.w_resident ? 0u : uint32_t(p.w_stage_bytes));
                         mbar_arrive_expect_tx(bar, tx);
                         const uint32_t st = smem_u32(stage0 + size_t(slot) * stage_bytes);
-                        const long long src_off = ((long long)(c * planes_per_chunk) * p.in_plane + q0) * 8;
-                        const __half* src = sg.in + src_off;
-                        for (int jj = 0; jj < planes_per_chunk && !skip_a; ++jj, src += p.in_plane * 8)
-                            bulk_g2s(st + uint32_t(jj) * p.a_plane_bytes, src, copy_bytes, bar);
-                        if (SPLIT) {        // the lo planes of the chunk land behind its hi planes
-                            const __half* srl = sg.in_lo + src_off;
-                            for (int jj = 0; jj < planes_per_chunk && !skip_a; ++jj, srl += p.in_plane * 8)
-                                bulk_g2s(st + uint32_t(planes_per_chunk + jj) * p.a_plane_bytes, srl, copy_bytes, bar);
+                        for (int ph = 0; ph < phases && !skip_a; ++ph) {
+                            const long long src_off = ((long long)(ph * cin8 + c * planes_per_chunk) * p.in_plane + q0) * 8;
+                            const __half* src = sg.in + src_off;
+                            const uint32_t dst = st + uint32_t(ph * planes_per_chunk) * p.a_plane_bytes;
+                            for (int jj = 0; jj < planes_per_chunk; ++jj, src += p.in_plane * 8)
+                                bulk_g2s(dst + uint32_t(jj) * p.a_plane_bytes, src, copy_bytes, bar);
+                            if (SPLIT) {        // the lo planes of the chunk land behind all of its hi planes
+                                const __half* srl = sg.in_lo + src_off;
+                                const uint32_t dstl = dst + uint32_t(phases * planes_per_chunk) * p.a_plane_bytes;
+                                for (int jj = 0; jj < planes_per_chunk; ++jj, srl += p.in_plane * 8)
+                                    bulk_g2s(dstl + uint32_t(jj) * p.a_plane_bytes, srl, copy_bytes, bar);
+                            }
                         }
                         if (!p.w_resident) {
                             load_stage_weights(wg, st + p.a_stage_bytes, bar, 0, taps, c);
@@ -576,6 +591,24 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
             : ((p.w_resident ? uint32_t(cin8) : 2u) * slab_bytes) >> 4;
         const bool active = p.rings == 2 || mw == 0u;       // a single ring is served by warp 0
         const uint32_t tile_bytes = uint32_t(p.tile_stride) * 16u;
+        // where filter tap t starts inside the landed run, in 16-byte descriptor units.  Plain 3x3: (r-1) rows + (s-1)
+        // pixels.  Phase-split input of a stride-2 conv (in_s2d): input row 2y + r - 1 is row y - 1 of the odd-row phase
+        // for r = 0, row y of the even phase for r = 1, row y of the odd phase for r = 2 (columns alike), so tap (r, s)
+        // reads phase block (r != 1) * 2 + (s != 1) at a shift of -1 / 0 rows and pixels: the nine taps are nine
+        // (phase block, shift) pairs over the SAME halo run, and the weights keep their [tap][Cin/8][Cout][8] layout.
+        const uint32_t phase_units = (uint32_t(planes_per_chunk) * uint32_t(p.a_plane_bytes)) >> 4;
+        uint32_t sh[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            int v = 0;
+            if (MODE == MODE_LINEAR) {
+                const int r = t / 3, s_ = t % 3;
+                if (p.in_s2d) v = (r == 0 ? -Wp : 0) + (s_ == 0 ? -1 : 0) + int(((r != 1) * 2 + (s_ != 1)) * phase_units);
+                else if (taps == 9) v = (r - 1) * Wp + (s_ - 1);
+                else if (taps == 3) v = (t - 1) * Wp;
+            }
+            sh[t] = uint32_t(v);
+        }
         uint32_t tl = 0, ul = 0;
         uint32_t m_slot = 0, m_ph = 0;                  // this issuer's position in its stage ring
         uint32_t a_buf = 0, a_par = 1u;                 // accumulator ring position of the next tile (all tiles, both issuers)
@@ -632,18 +665,18 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
 #define POCO_ISSUE(T, K)                                                                                                    \
     do {                                                                                                                    \
         if (NCAT) {         /* x_hi [W_hi | W_lo] into both column groups, then x_lo W_hi onto the first */                 \
-            issue_linear<T, K>(d_tmem, a_lo, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, acc);                \
-            issue_linear<T, K>(d_tmem, a_lo2, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc_half, 1u);           \
+            issue_linear<T, K>(d_tmem, a_lo, b_lo, sh, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, acc);                \
+            issue_linear<T, K>(d_tmem, a_lo2, b_lo, sh, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc_half, 1u);           \
             break;                                                                                                          \
         }                                                                                                                   \
         if (SPLIT) {        /* x_lo W_hi + x_hi W_lo first: the tensor core truncates every accumulation to the magnitude */ \
                             /* of the running sum, so the 2^-11-sized correction terms go in while it is still small     */ \
-            issue_linear<T, K>(d_tmem, a_lo2, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, acc);               \
-            issue_linear<T, K>(d_tmem, a_lo, b_lo2, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, 1u);                \
+            issue_linear<T, K>(d_tmem, a_lo2, b_lo, sh, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, acc);               \
+            issue_linear<T, K>(d_tmem, a_lo, b_lo2, sh, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, 1u);                \
         }                                                                                                                   \
-        issue_linear<T, K>(d_tmem, a_lo, b_lo, Wp, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, SPLIT ? 1u : acc);       \
+        issue_linear<T, K>(d_tmem, a_lo, b_lo, sh, a_kstep, b_kstep, w_tap_stride, desc_hi, idesc, SPLIT ? 1u : acc);       \
     } while (0)
-                                const uint32_t a_lo2 = a_lo + ((uint32_t(planes_per_chunk) * uint32_t(p.a_plane_bytes)) >> 4);
+                                const uint32_t a_lo2 = a_lo + (p.in_s2d ? 4u : 1u) * phase_units;
                                 const uint32_t b_lo2 = b_lo + ((p.w_resident ? uint32_t(p.w_res_bytes) : uint32_t(p.w_stage_bytes)) >> 5);
                                 if (taps == 9) {
                                     switch (ksteps) {
@@ -809,6 +842,7 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
         const uint32_t step_in = uint32_t(p.tile_stride % HpWp_o);
         const uint32_t step_unit = uint32_t((((long long)gridDim.x * G - (G - 1)) * p.tile_stride) % HpWp_o);
         const uint32_t magic_w = 0xFFFFFFFFu / uint32_t(Wp_o) + 1u;      // exact floor(n / Wp) for n < 2^16
+        const uint32_t magic_hw = 0xFFFFFFFFu / uint32_t(HpWp_o) + 1u;   // exact n / HpWp for exact multiples n < 2^32
         uint32_t tl = 0, g = 0;                         // g counts residual items consumed
         uint32_t e_buf = 0, e_par = 0;                  // accumulator ring position of tile `tl`
         uint32_t rs_slot = 0, rs_par = 0;               // residual ring position of item `g`
@@ -858,6 +892,14 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                 const uint32_t yy = __umulhi(rem, magic_w), xx = rem - yy * uint32_t(Wp_o);
                 const bool interior = qw + lane < p.P_out && yy >= 1u && yy <= uint32_t(p.Hout) && xx >= 1u && xx <= uint32_t(p.Wout) &&
                                       !(DXN && (row == 0 || row == kTileM - 1));     // (dx-in-N: the tile's edge rows belong to its neighbours)
+                long long s2d_off = 0;      // this row's pixel in the phase-split second output (plane 0 of its phase)
+                if (S2DOUT && interior) {
+                    const uint32_t n_crop = __umulhi(uint32_t(qw + lane) - rem, magic_hw);      // (q - rem) = crop * HpWp
+                    const uint32_t y = yy - 1u, x = xx - 1u;
+                    const uint32_t ph = (y & 1u) * 2u + (x & 1u);
+                    s2d_off = ((long long)(ph * uint32_t(p.Cout >> 3)) * p.s2d_plane + (long long)n_crop * p.s2d_HpWp +
+                               ((y >> 1) + 1u) * uint32_t(p.s2d_Wp) + (x >> 1) + 1u) * 8;
+                }
                 rem += (g_ + 1 == G) ? step_unit : step_in;
                 if (rem >= uint32_t(HpWp_o)) rem -= uint32_t(HpWp_o);
                 const long long left = p.P_out - qw;
@@ -992,7 +1034,8 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                             uint4 o4;
                             o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
                             o4.z = pack_half2(f[4], f[5]); o4.w = pack_half2(f[6], f[7]);
-                            *reinterpret_cast<uint4*>(outp + (long long)pl * p.out_plane * 8) = o4;
+                            if (!S2DOUT || !p.s2d_only) *reinterpret_cast<uint4*>(outp + (long long)pl * p.out_plane * 8) = o4;
+                            uint4 l4 = make_uint4(0, 0, 0, 0);
                             if (SPLIT) {        // lo = fp16(y - hi)
                                 const uint32_t oh[4] = {o4.x, o4.y, o4.z, o4.w};
                                 uint32_t ol[4];
@@ -1001,8 +1044,13 @@ __global__ void __launch_bounds__(Roles<MODE>::kThreads, MINB) conv_tc_kernel(co
                                     const float2 h2 = unpack_half2(oh[i]);
                                     ol[i] = pack_half2(f[2 * i] - h2.x, f[2 * i + 1] - h2.y);
                                 }
-                                *reinterpret_cast<uint4*>(sg.out_lo + out_off + (long long)pl * p.out_plane * 8) =
-                                    make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                                l4 = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                                if (!S2DOUT || !p.s2d_only) *reinterpret_cast<uint4*>(sg.out_lo + out_off + (long long)pl * p.out_plane * 8) = l4;
+                            }
+                            if (S2DOUT) {       // the same pixel in the phase-split copy (feeds a stride-2 conv)
+                                const long long so = s2d_off + (long long)(plane0 + item * ipl + pl) * p.s2d_plane * 8;
+                                *reinterpret_cast<uint4*>(p.s2d_out + so) = o4;
+                                if (SPLIT) *reinterpret_cast<uint4*>(p.s2d_out_lo + so) = l4;
                             }
                         }
                     }
@@ -1052,7 +1100,7 @@ int num_sms() {
 }  // namespace
 
 int64_t conv_flops(const poco_conv* d) {
-    return 2ll * d->out.N * d->out.H * d->out.W * d->out.C * d->in.C * d->kh * d->kw;
+    return 2ll * d->out.N * d->out.H * d->out.W * d->out.C * (d->in_s2d ? d->in.C / 4 : d->in.C) * d->kh * d->kw;
 }
 
 int conv_tc_launch(const poco_conv* d, cudaStream_t s) { return conv_tc_launch_chain(d, 1, nullptr, s); }
@@ -1065,13 +1113,28 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     POCO_CHECK(in.C % 16 == 0 && out.C % 16 == 0, "Cin and Cout must be multiples of 16");
     POCO_CHECK(in.N == out.N, "batch mismatch");
     POCO_CHECK(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
-    POCO_CHECK((in.H + 2 * d->pad - d->kh) / d->stride + 1 == out.H && (in.W + 2 * d->pad - d->kw) / d->stride + 1 == out.W,
-               "output geometry does not match the convolution");
+    const bool in_s2d = d->in_s2d != 0;
+    if (in_s2d) {
+        POCO_CHECK(n_segs == 1 && d->kh == 3 && d->kw == 3 && d->stride == 2 && d->pad == 1 && d->wfmt == 0 && in.C % 64 == 0 &&
+                       in.H == out.H && in.W == out.W,
+                   "in_s2d: a 3x3 / stride 2 / pad 1 conv whose input is given phase-split (4 Cin channels at the output resolution)");
+    } else {
+        POCO_CHECK((in.H + 2 * d->pad - d->kh) / d->stride + 1 == out.H && (in.W + 2 * d->pad - d->kw) / d->stride + 1 == out.W,
+                   "output geometry does not match the convolution");
+    }
+    if (d->out_s2d.data != nullptr) {
+        const poco_act& s = d->out_s2d;
+        POCO_CHECK(n_segs == 1 && d->wfmt != 1 && out.H % 2 == 0 && out.W % 2 == 0 && s.C == 4 * out.C && s.N == out.N && s.H == out.H / 2 &&
+                       s.W == out.W / 2 && (s.lo != nullptr) == (in.lo != nullptr),
+                   "out_s2d: 4 Cout channels at half the (even) output resolution, same precision mode");
+    }
+    POCO_CHECK(!d->s2d_only || d->out_s2d.data != nullptr, "s2d_only without out_s2d");
     POCO_CHECK((kTileM + out.W + 3) * 16 <= POCO_ACT_GUARD_BYTES, "tile halo exceeds the activation guard");
 
     const bool split = in.lo != nullptr;          // split-precision ("parity") mode: see the SPLIT template parameter
     const int sp = split ? 2 : 1;
-    POCO_CHECK(!split || (out.lo != nullptr && n_segs == 1 && (d->wfmt == 0 || d->wfmt == 2)), "split precision: out.lo missing, or a chain / dx-in-N conv");
+    POCO_CHECK(!split || ((out.lo != nullptr || d->s2d_only) && n_segs == 1 && (d->wfmt == 0 || d->wfmt == 2)),
+               "split precision: out.lo missing, or a chain / dx-in-N conv");
     const bool ncat = d->wfmt == 2;        // split precision with N-concatenated weights [tap][Cin/8][2 Cout][8]
     POCO_CHECK(!ncat || (split && out.C <= 64), "weight format 2 needs split precision and Cout <= 64");
     POCO_CHECK(split || out.lo == nullptr, "out.lo given but in.lo is null");
@@ -1114,7 +1177,14 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         POCO_CHECK(c.residual != segs[i - 1].out.data, "chain: residual must not be the previous segment's output");
         POCO_CHECK(c.out.data != c.in.data && c.out.data != c.residual, "chain: in-place segments are not supported");
     }
-    p.Cin = in.C; p.Cout = out.C;
+    p.Cin = in_s2d ? in.C / 4 : in.C; p.Cout = out.C;         // Cin: channels the weights see
+    p.in_s2d = in_s2d ? 1 : 0;
+    p.s2d_out = static_cast<__half*>(d->out_s2d.data);
+    p.s2d_out_lo = static_cast<__half*>(d->out_s2d.lo);
+    p.s2d_plane = d->out_s2d.plane_stride;
+    p.s2d_Wp = d->out_s2d.W + 2;
+    p.s2d_HpWp = (d->out_s2d.H + 2) * (d->out_s2d.W + 2);
+    p.s2d_only = d->s2d_only;
     p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad;
     p.w_bufs = 1;
     {
@@ -1144,9 +1214,10 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     static const int stream_group = [] { const char* e = getenv("POCO_B200_STREAM_GROUP"); return e ? atoi(e) : 2; }();
     const bool linear_geom = d->stride == 1 && in.H == out.H && in.W == out.W &&
                              ((d->kh == 3 && d->kw == 3 && d->pad == 1) || (d->kh == 1 && d->kw == 1 && d->pad == 0));
-    const bool stream_grouped = stream_group >= 2 && linear_geom && d->wfmt == 0 && n_segs == 1 &&
+    const bool stream_grouped = stream_group >= 2 && linear_geom && !d->in_s2d && d->wfmt == 0 && n_segs == 1 &&
                                 int64_t(d->kh) * d->kw * in.C * std::min(n_cap, out.C) * 2 * sp > (split ? 160 : 112) * 1024;
     if (stream_grouped && out.C % 128 == 0) n_cap = 128;
+    if (split && d->in_s2d) n_cap = 64;         // four phase blocks of [hi | lo] planes per K chunk: keep the weight stage small
     for (int t = std::min(n_cap, out.C); t >= 16; t -= 16)
         if (out.C % t == 0) { n_tile = t; break; }
     if (dxn) n_tile = 3 * out.C;
@@ -1164,7 +1235,8 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     // other lanes' full-size CTAs no empty SM (A/B inside the HR modules: 19.5 k vs 19.8 k crops/s).
     static const int half_mode = [] { const char* e = getenv("POCO_B200_HALF"); return e ? atoi(e) : 1; }();   // 0 off, 1 outside lanes, 2 always
     const bool half_stride1 = d->stride == 1 && in.H == out.H && in.W == out.W && d->kh == 3 && d->pad == 1;
-    bool half = half_mode > 0 && (half_mode == 2 || d->max_ctas == 0) && !dxn && !split && n_segs == 1 && n_tile <= 64 && half_stride1;
+    bool half = half_mode > 0 && (half_mode == 2 || d->max_ctas == 0) && !dxn && !split && n_segs == 1 && n_tile <= 64 && half_stride1 &&
+                d->out_s2d.data == nullptr;
     int smem_budget = kSmemBudget;
     auto set_half = [&](bool h) {
         half = h;
@@ -1176,15 +1248,18 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
 
     const int taps = dxn ? 3 : d->kh * d->kw;       // taps the MMA loop walks
     p.taps = taps;
-    const bool linear = d->stride == 1 && in.H == out.H && in.W == out.W &&
-                        ((d->kh == 3 && d->kw == 3 && d->pad == 1) || (d->kh == 1 && d->kw == 1 && d->pad == 0));
+    // (a stride-2 conv on a phase-split input walks one halo run per plane like a 3x3 / stride 1 conv: linear mode)
+    const bool linear = in_s2d || (d->stride == 1 && in.H == out.H && in.W == out.W &&
+                                   ((d->kh == 3 && d->kw == 3 && d->pad == 1) || (d->kh == 1 && d->kw == 1 && d->pad == 0)));
     const int mode = linear ? MODE_LINEAR : MODE_GATHER;
+    const int cin_w = in_s2d ? in.C / 4 : in.C;         // input channels the weights see
+    const int phases = in_s2d ? 4 : 1;
     POCO_CHECK(!dxn || (linear && d->kh == 3 && n_segs == 1 && out.C % 32 == 0 && 3 * out.C <= 256),
                "dx-in-N weights need a single 3x3 / stride 1 / pad 1 conv with 32 or 64 output channels");
     for (int i = 1; i < n_segs; ++i) POCO_CHECK(segs[i].wfmt == 0, "chain: dx-in-N weights are not supported");
     POCO_CHECK(n_segs == 1 || (linear && out.W + 3 <= kTileM), "chain: only 3x3/s1/p1 and 1x1/s1 convolutions chain");
     int budget = 0;         // set per attempt below
-    const int w_total = taps * in.C * n_tile * 2 * sp;
+    const int w_total = taps * cin_w * n_tile * 2 * sp;
     const int w_res_cap = split ? 160 * 1024 : 112 * 1024;      // largest weight block kept resident
 
     // M grouping: G adjacent tiles of a 3x3 conv are fetched as ONE run per plane, so the (W+3)-pixel halo is
@@ -1204,7 +1279,8 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
     auto set_group = [&](int G) {
         p.m_group = G;
         p.halo = dxn ? (out.W + 2) : (taps == 9 ? (out.W + 2) + 1 : 0);
-        p.a_copy_bytes = ((G - 1) * p.tile_stride + kTileM + 2 * p.halo) * 16;
+        p.halo_hi = in_s2d ? 0 : p.halo;        // the taps of a phase-split input reach back only
+        p.a_copy_bytes = ((G - 1) * p.tile_stride + kTileM + p.halo + p.halo_hi) * 16;
         p.a_plane_bytes = round_up(p.a_copy_bytes, 128);
     };
     if (mode == MODE_LINEAR) {
@@ -1239,13 +1315,13 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
                 if (resident && w_total > w_res_cap) continue;
                 for (int ki = 0; ki < 4 && !found; ++ki) {
                     const int kc = kcs[ki];
-                    if (in.C % kc != 0) continue;
-                    const int a_stage = (kc / 8) * p.a_plane_bytes * sp;
+                    if (cin_w % kc != 0) continue;
+                    const int a_stage = (kc / 8) * phases * p.a_plane_bytes * sp;
                     const int w_stage = resident ? 0 : taps * kc * n_tile * 2 * sp;
                     const int avail = budget - wb * w_total;
                     const int stages = std::min(max_stages(), avail / (a_stage + w_stage));
                     if (stages < (want4 ? 4 : 2)) continue;
-                    p.kc = kc; p.n_chunks = in.C / kc;
+                    p.kc = kc; p.n_chunks = cin_w / kc;
                     p.w_resident = resident;
                     p.w_bufs = std::max(1, wb);
                     p.w_res_bytes = resident ? w_total : 0;
@@ -1325,9 +1401,19 @@ int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cuda
         cfg.blockDim = dim3(threads);
         return cudaLaunchKernelEx(&cfg, kernel, pk);
     };
-    static std::once_flag once4[13];
+    static std::once_flag once4[13], once_s2d[6];
     POCO_CHECK(!ncat || mode == MODE_LINEAR, "weight format 2 is for stride-1 3x3 / 1x1 convs");
-    if (ncat && p.item_planes == 2)
+    const bool s2dout = p.s2d_out != nullptr;
+    POCO_CHECK(!s2dout || (mode == MODE_LINEAR && !dxn), "out_s2d needs a conv on the halo-run path");
+    if (s2dout) {       // (never the two-CTA "half" flavour: set below)
+        const int sv = ncat ? 2 : (split ? 1 : 0);
+        if (sv == 0 && p.item_planes == 2) POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 1, 0, true>, once_s2d[0], Roles<MODE_LINEAR>::kThreads));
+        else if (sv == 0) POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false, 1, 0, true>, once_s2d[1], Roles<MODE_LINEAR>::kThreads));
+        else if (sv == 1 && p.item_planes == 2) POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 1, 1, true>, once_s2d[2], Roles<MODE_LINEAR>::kThreads));
+        else if (sv == 1) POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false, 1, 1, true>, once_s2d[3], Roles<MODE_LINEAR>::kThreads));
+        else if (p.item_planes == 2) POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 1, 2, true>, once_s2d[4], Roles<MODE_LINEAR>::kThreads));
+        else POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false, 1, 2, true>, once_s2d[5], Roles<MODE_LINEAR>::kThreads));
+    } else if (ncat && p.item_planes == 2)
         POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 2, false, 1, 2>, once4[11], Roles<MODE_LINEAR>::kThreads));
     else if (ncat)
         POCO_CUDA(launch(conv_tc_kernel<MODE_LINEAR, 4, false, 1, 2>, once4[12], Roles<MODE_LINEAR>::kThreads));

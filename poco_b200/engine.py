@@ -20,6 +20,8 @@ BN_EPS = 1e-5
 class ActT:
     """[C/8][N][H+2][W+2][8] fp16 view into a torch buffer (see include/poco_b200.h)."""
 
+    s2d = None      # the phase-split (space-to-depth) copy a producing conv wrote next to this tensor, if any
+
     def __init__(self, buf, ptr, C_, N, H, W, plane_stride, cap_planes, root=None, lo_off=0):
         self.buf, self.ptr = buf, ptr
         self.C, self.N, self.H, self.W = C_, N, H, W
@@ -174,6 +176,11 @@ class PlanBuilder:
 
     def __init__(self, sd, N, device, conv_impl=0, split=False, latency_mode=False):
         self.sd = sd
+        # space-to-depth plumbing of the stride-2 convs (conv_bn s2d=...): fp16 mode only -- in split precision the four
+        # phase blocks of [hi | lo] planes per K chunk leave too little shared memory (measured 28.2 vs 26.3 ms per step);
+        # POCO_B200_S2D=0 / =2 force it off / on
+        env_s2d = os.environ.get('POCO_B200_S2D', '1')
+        self.use_s2d = conv_impl == 0 and (env_s2d == '2' or (env_s2d == '1' and not split))
         self.latency_mode = bool(latency_mode)      # small batches: branch convs as persistent chains (arch.chain_policy)
         self.split = bool(split)    # split-precision ("parity") mode: hi + lo fp16 activations and weights everywhere
         self.N = N
@@ -210,8 +217,11 @@ class PlanBuilder:
 
     def free(self, a):
         """return the buffer behind `a` to the pool (safe: ops run in program order on one stream)"""
+        if a.s2d is not None:           # its phase-split copy goes with it
+            s2d, a.s2d = a.s2d, None
+            self.free(s2d)
         root = a.root
-        if root is not a and a.ptr != root.ptr:
+        if root.buf is None or (root is not a and a.ptr != root.ptr):      # (geometry-only tensor of an s2d='only' conv; a slice)
             return
         full = ActT(root.buf, root.ptr, root.cap_planes * 8, root.N, root.H, root.W, root.plane_stride, root.cap_planes,
                     None, root.lo_off)
@@ -289,7 +299,7 @@ class PlanBuilder:
         self.add(L.PackImage(img.data_ptr(), out.desc(), 0, 0))
         return out
 
-    def stem_conv(self, img, H, W, conv, bn, cout):
+    def stem_conv(self, img, H, W, conv, bn, cout, s2d=None):
         """conv3x3(3 -> cout, stride 2, pad 1) + BN + ReLU straight from the f32 image (hrnet.py:299-301,
         :467-469): the packing kernel writes the 27-tap im2col (32 fp16 channels at half resolution) and the
         conv runs as a 1x1 conv with K = 32 -- half the activation bytes of a 3x3 conv over 16 zero-padded
@@ -309,17 +319,28 @@ class PlanBuilder:
         wp = pack_conv_weight(w1, split=('ncat' if wfmt == 2 else self.split)).to(self.device)
         bf = bf.contiguous().to(self.device)
         self.keep += [wp, bf]
-        out = self.act(cout, H // 2, W // 2)
+        use_s2d = s2d and self.use_s2d
+        Ho, Wo = H // 2, W // 2
+        out = self.act(cout, Ho, Wo) if not (use_s2d and s2d == 'only') else \
+            ActT(None, 0, cout, self.N, Ho, Wo, self.N * (Ho + 2) * (Wo + 2), 0)
         d = L.Conv(col.desc(), out.desc(), wp.data_ptr(), bf.data_ptr(), None, 0, 1, 1, 1, 0, 1, self.conv_impl,
                    self._share(), wfmt)
+        if use_s2d:
+            out.s2d = self.act(4 * cout, Ho // 2, Wo // 2)
+            d.out_s2d = out.s2d.desc()
+            d.s2d_only = 1 if s2d == 'only' else 0
         self.add(d)
         self.conv_log.append((conv, 32, cout, 1, 1, H // 2, H // 2))
         self.free(col)
         return out
 
-    def conv_bn(self, x, conv, bn, cin, cout, k, stride=1, relu=True, residual=None, out=None, pad=None, bias=False):
+    def conv_bn(self, x, conv, bn, cin, cout, k, stride=1, relu=True, residual=None, out=None, pad=None, bias=False,
+                s2d=None):
         """conv (+bias) + eval BatchNorm folded, + residual, ReLU.  `conv` / `bn` may be lists: several
-        convs reading the same input run as one launch with their output channels concatenated."""
+        convs reading the same input run as one launch with their output channels concatenated.
+        s2d='dual' / 'only': the conv also writes (only writes) the phase-split form of its output for a stride-2
+        consumer (returned as out.s2d).  A 3x3 / stride 2 / pad 1 conv whose input carries such a copy runs on it
+        (poco_conv.in_s2d: halo-run path instead of the 16-byte gather); a 1x1 / stride 2 conv reads phase block 0."""
         sd = self.sd
         convs = conv if isinstance(conv, (list, tuple)) else [conv]
         bns = bn if isinstance(bn, (list, tuple)) else [bn] * len(convs)
@@ -336,6 +357,13 @@ class PlanBuilder:
             ws.append(wf)
             bs.append(bf)
         pad = k // 2 if pad is None else pad
+        use_s2d = self.use_s2d and self.chain is None
+        in_s2d = 0
+        if use_s2d and stride == 2 and x.s2d is not None and x.C == cin and x.H % 2 == 0 and x.W % 2 == 0:
+            if k == 3 and pad == 1 and cin % 16 == 0:
+                xs2d, in_s2d = x.s2d, 1                     # the conv walks the phase-split copy
+            elif k == 1 and pad == 0:
+                x, stride = x.s2d.channels(0, cin), 1       # phase (0, 0) IS the stride-2 sampling: a plain 1x1 conv
         wfmt = 1 if (self.conv_impl == 0 and self.chain is None and x.C == cin and not self.split and
                      dxn_applies(cin, cout, k, stride, pad)) else 0
         if self.split and self.conv_impl == 0 and self.chain is None:
@@ -347,17 +375,24 @@ class PlanBuilder:
         self.keep += [wp, bf]
         Ho = (x.H + 2 * pad - k) // stride + 1
         Wo = (x.W + 2 * pad - k) // stride + 1
+        want_s2d = s2d if (use_s2d and s2d and Ho % 2 == 0 and Wo % 2 == 0 and
+                           (stride == 1 and ((k == 3 and pad == 1) or (k == 1 and pad == 0)) or in_s2d)) else None
         if out is None:
-            out = self.act(cout, Ho, Wo)
+            out = self.act(cout, Ho, Wo) if want_s2d != 'only' else ActT(None, 0, cout, self.N, Ho, Wo, self.N * (Ho + 2) * (Wo + 2), 0)
         assert (out.C, out.H, out.W) == (cout, Ho, Wo), (conv, (out.C, out.H, out.W), (cout, Ho, Wo))
         if residual is not None:
             assert (residual.C, residual.H, residual.W) == (cout, Ho, Wo), conv
-        d = L.Conv(x.desc(), out.desc(), wp.data_ptr(), bf.data_ptr(),
+        d = L.Conv((xs2d if in_s2d else x).desc(), out.desc(), wp.data_ptr(), bf.data_ptr(),
                    residual.ptr if residual is not None else None,
                    residual.plane_stride if residual is not None else 0,
                    k, k, stride, pad, int(relu), self.conv_impl,
                    self._share(), wfmt,
                    residual.ptr_lo if residual is not None else None)
+        d.in_s2d = in_s2d
+        if want_s2d:
+            out.s2d = self.act(4 * cout, Ho // 2, Wo // 2)
+            d.out_s2d = out.s2d.desc()
+            d.s2d_only = 1 if want_s2d == 'only' else 0
         if self.chain is not None:
             self.chain.append(d)
         else:

@@ -15,6 +15,18 @@ import torch.nn.functional as F
 from poco_b200 import _lib as L
 
 
+def space_to_depth(x):
+    """[N, C, H, W] -> phase-split [N, 4C, H/2, W/2]: channel ((y & 1) * 2 + (x & 1)) * C + c of pixel (y / 2, x / 2)"""
+    N, C_, H, W = x.shape
+    return x.view(N, C_, H // 2, 2, W // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(N, 4 * C_, H // 2, W // 2)
+
+
+def depth_to_space(p):
+    N, C4, H, W = p.shape
+    C_ = C4 // 4
+    return p.view(N, 2, 2, C_, H, W).permute(0, 3, 4, 1, 5, 2).reshape(N, C_, 2 * H, 2 * W)
+
+
 class Emu:
     def __init__(self, keep):
         items = sorted(((t.data_ptr(), t) for t in keep if t.numel() > 0), key=lambda x: x[0])
@@ -76,21 +88,23 @@ class Emu:
     def _op2(self, d):      # conv
         i, o = d.in_, d.out
         taps = d.kh * d.kw
+        cin = i.C // 4 if d.in_s2d else i.C      # channels the weights see
         if d.wfmt == 1:     # dx-in-N layout [r][Cin/8][s*Cout + co][8]
-            wp = self.flat(d.weight, torch.float16)[:taps * i.C * o.C].view(3, i.C // 8, 3, o.C, 8).float()
-            w = wp.permute(3, 1, 4, 0, 2).reshape(o.C, i.C, 3, 3)
+            wp = self.flat(d.weight, torch.float16)[:taps * cin * o.C].view(3, cin // 8, 3, o.C, 8).float()
+            w = wp.permute(3, 1, 4, 0, 2).reshape(o.C, cin, 3, 3)
         else:
-            nw = taps * i.C * o.C
+            nw = taps * cin * o.C
             if d.wfmt == 2:     # split precision, N-concatenated: slab rows W_hi then W_lo
-                w2 = self.flat(d.weight, torch.float16)[:2 * nw].view(taps, i.C // 8, 2 * o.C, 8).float()
+                w2 = self.flat(d.weight, torch.float16)[:2 * nw].view(taps, cin // 8, 2 * o.C, 8).float()
                 wp = w2[:, :, :o.C] + w2[:, :, o.C:]
             else:
-                wp = self.flat(d.weight, torch.float16)[:nw].view(taps, i.C // 8, o.C, 8).float()
+                wp = self.flat(d.weight, torch.float16)[:nw].view(taps, cin // 8, o.C, 8).float()
                 if i.lo:        # split-precision mode: W_lo follows W_hi
-                    wp = wp + self.flat(d.weight, torch.float16)[nw:2 * nw].view(taps, i.C // 8, o.C, 8).float()
-            w = wp.permute(2, 1, 3, 0).reshape(o.C, i.C, d.kh, d.kw)
+                    wp = wp + self.flat(d.weight, torch.float16)[nw:2 * nw].view(taps, cin // 8, o.C, 8).float()
+            w = wp.permute(2, 1, 3, 0).reshape(o.C, cin, d.kh, d.kw)
         b = self.flat(d.bias, torch.float32)[:o.C]
-        y = F.conv2d(self.act_get(i), w, b, stride=d.stride, padding=d.pad)
+        xin = depth_to_space(self.act_get(i)) if d.in_s2d else self.act_get(i)      # (in_s2d: `in` is the phase-split input)
+        y = F.conv2d(xin, w, b, stride=d.stride, padding=d.pad)
         if d.relu == 2:
             y = F.relu(y)
         if d.residual:
@@ -98,7 +112,10 @@ class Emu:
             y = y + self.act_get(r)
         if d.relu == 1:
             y = F.relu(y)
-        self.act_set(o, y)
+        if d.out_s2d.data:
+            self.act_set(d.out_s2d, space_to_depth(y))
+        if not d.s2d_only:
+            self.act_set(o, y)
 
     def _op3(self, d):      # fuse sum
         y = None

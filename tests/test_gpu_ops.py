@@ -440,3 +440,95 @@ def test_uncert_post_matches_reference():
     conf, _, _ = uncert_post(var, 'hrnet_w32-pare', return_conf=True)
     assert np.array_equal(conf.cpu().numpy(), 1 - g['var'])
     assert np.array_equal(var.cpu().numpy(), g['var'])              # the input is never modified
+
+
+# ------------------------------------------------------------------------------------------------
+# space-to-depth plumbing of the stride-2 convs (poco_conv.out_s2d / in_s2d)
+# ------------------------------------------------------------------------------------------------
+def _s2d_plan(cin, cmid, cout, H, N, use_s2d, split, mode, seed=0):
+    """conv3x3 s1 (cin -> cmid, writes the phase-split copy) -> conv3x3 s2 (cmid -> cout, + residual) -> conv1x1 s2"""
+    import os
+    g = torch.Generator().manual_seed(seed + cin + cout)
+    sd = {}
+    for name, ci, co, k in (('a', cin, cmid, 3), ('b', cmid, cout, 3), ('c', cmid, cout, 1)):
+        sd[f'{name}.weight'] = torch.randn(co, ci, k, k, generator=g) * (2.0 / (ci * k * k)) ** 0.5
+        sd[f'{name}bn.weight'] = 0.8 + 0.4 * torch.rand(co, generator=g)
+        sd[f'{name}bn.bias'] = 0.1 * torch.randn(co, generator=g)
+        sd[f'{name}bn.running_mean'] = 0.1 * torch.randn(co, generator=g)
+        sd[f'{name}bn.running_var'] = 0.8 + 0.4 * torch.rand(co, generator=g)
+    os.environ['POCO_B200_S2D'] = '2' if use_s2d else '0'
+    try:
+        b = engine.PlanBuilder(sd, N, 'cuda', split=split)
+        x0 = torch.randn(N, cin, H, H, generator=g)
+        r0 = torch.randn(N, cout, H // 2, H // 2, generator=g)
+        x = engine.to_planar(x0.cuda(), split=split)
+        r = engine.to_planar(r0.cuda(), split=split)
+        b.keep += [x.buf, r.buf]
+        y = b.conv_bn(x, 'a', 'abn', cin, cmid, 3, s2d=mode)
+        z = b.conv_bn(y, 'b', 'bbn', cmid, cout, 3, 2, relu=True, residual=r)
+        w = b.conv_bn(y, 'c', 'cbn', cmid, cout, 1, 2, relu=False, pad=0)
+    finally:
+        os.environ.pop('POCO_B200_S2D')
+    return b, y, z, w, x0, r0, sd
+
+
+@pytest.mark.parametrize('cin,cmid,cout,H,N,split', [(32, 32, 64, 56, 3, False), (64, 64, 128, 28, 2, False),
+                                                     (16, 64, 64, 112, 1, False), (128, 128, 256, 14, 3, False),
+                                                     (256, 256, 64, 56, 1, False), (32, 32, 64, 56, 2, True),
+                                                     (64, 64, 128, 28, 3, True), (128, 128, 256, 14, 2, True)],
+                         ids=lambda v: str(v))
+def test_stride2_convs_on_phase_split_inputs(cin, cmid, cout, H, N, split):
+    """the producing conv writes the phase-split copy from its epilogue ('dual'), the 3x3 / stride 2 conv walks it on
+    the halo-run path and the 1x1 / stride 2 conv reads phase block 0: same results as the gather path and as the
+    oracle arithmetic"""
+    import emu
+    res = {}
+    for use in (False, True):
+        b, y, z, w, x0, r0, sd = _s2d_plan(cin, cmid, cout, H, N, use, split, 'dual')
+        kinds = [(op.u.conv.in_s2d, bool(op.u.conv.out_s2d.data), op.u.conv.stride) for op in b.ops]
+        assert kinds == ([(0, True, 1), (1, False, 2), (0, False, 1)] if use else [(0, False, 1), (0, False, 2), (0, False, 2)])
+        for op in b.ops:
+            L.run_op(op, stream())
+        sync_or_die(30)
+        res[use] = (engine.from_planar(y).cpu(), engine.from_planar(z).cpu(), engine.from_planar(w).cpu())
+        if use:     # the phase-split copy holds exactly the values of the normal output
+            assert torch.equal(engine.from_planar(y.s2d).cpu(), emu.space_to_depth(res[use][0]))
+            for t in (y, y.s2d, z, w):
+                for lo in ([False, True] if split else [False]):
+                    halo = engine.act_view(t, lo)
+                    assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
+                                 halo[:, :, :, -1].abs().sum()) == 0.0, 'kernel wrote into the zero halo'
+    tol = 2e-5 if split else CONV_TOL
+    assert rel_err(res[True][0].numpy(), res[False][0].numpy()) < tol          # (half-size CTAs without the second output)
+    assert rel_err(res[True][1].numpy(), res[False][1].numpy()) < tol          # (other K chunking than the gather)
+    assert rel_err(res[True][2].numpy(), res[False][2].numpy()) < tol
+    # oracle arithmetic on the engine's operands
+    from gpu_util import split16
+    rnd = (lambda t: split16(t)) if split else (lambda t: t.half().double())
+
+    def cbr(x, name, stride, pad, relu, resid=None):
+        bnp = tuple(sd[f'{name}bn{s_}'] for s_ in ('.weight', '.bias', '.running_mean', '.running_var'))
+        wf, bf = engine.fold_bn(sd[f'{name}.weight'], None, bnp)
+        v = F.conv2d(x, rnd(wf), bf.double(), stride=stride, padding=pad)
+        if resid is not None:
+            v = v + resid
+        return rnd(F.relu(v) if relu else v)
+    yr = cbr(rnd(x0), 'a', 1, 1, True)
+    zr = cbr(yr, 'b', 2, 1, True, rnd(r0))
+    wr = cbr(yr, 'c', 2, 0, False)
+    assert rel_err(res[True][0].numpy(), yr.numpy()) < tol
+    assert rel_err(res[True][1].numpy(), zr.numpy()) < (4e-5 if split else 2 * CONV_TOL)
+    assert rel_err(res[True][2].numpy(), wr.numpy()) < (4e-5 if split else 2 * CONV_TOL)
+
+
+def test_phase_split_only_output_leaves_no_normal_tensor():
+    b, y, z, w, x0, r0, sd = _s2d_plan(32, 32, 64, 28, 2, True, False, 'only')
+    assert y.buf is None and y.s2d is not None and b.ops[0].u.conv.s2d_only == 1
+    for op in b.ops[:2]:
+        L.run_op(op, stream())
+    sync_or_die(30)
+    b2, y2, z2, w2, _, _, _ = _s2d_plan(32, 32, 64, 28, 2, False, False, None)
+    for op in b2.ops[:2]:
+        L.run_op(op, stream())
+    sync_or_die(30)
+    assert rel_err(engine.from_planar(z).cpu().numpy(), engine.from_planar(z2).cpu().numpy()) < CONV_TOL

@@ -27,9 +27,10 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_ctypes_structs_match_header_sizes():
-    # poco_act: ptr + i64 + 4*i32 + ptr (lo) = 40 bytes; poco_conv: 2*40 + 3 ptr + i64 + 8*i32 + ptr (residual_lo) = 152
+    # poco_act: ptr + i64 + 4*i32 + ptr (lo) = 40 bytes;
+    # poco_conv: 2*40 + 3 ptr + i64 + 8*i32 + ptr (residual_lo) + 40 (out_s2d) + 2*i32 = 200
     assert ctypes.sizeof(_lib.Act) == 40
-    assert ctypes.sizeof(_lib.Conv) == 152
+    assert ctypes.sizeof(_lib.Conv) == 200
     assert ctypes.sizeof(_lib.Linear) == 96
     assert _lib.Op.u.offset == 8
 
