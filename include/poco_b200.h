@@ -217,6 +217,15 @@ typedef struct poco_realnvp {
     float* logdet_out;
     int32_t R, D, CTX, HID, L;
     int32_t direction;
+    /* Context hoist (optional; ctx_part == NULL: every CTA walks the full [H][D+CTX] first layers itself).  The context
+     * columns of the first layer of every (coupling layer, s/t net) do not depend on z, and the 24 joints of a crop
+     * share one context vector (nf_head.py:85-101 expands it), so the host computes
+     *     ctx_part[g][(layer*2 + net)*H + u] = b0[u] + sum_k W0[u][D + k] * ctx[g][k]
+     * ONCE per context row with one GEMM (poco_linear on the matrix pack_realnvp_ctx stacks) and passes it here:
+     * row r uses context row r / ctx_group, the kernel only adds the D-column part. */
+    const float* ctx_part; /* [ceil(R / ctx_group)][L * 2 * HID] or NULL */
+    int32_t ctx_group;     /* rows per context row (1 = one per row) */
+    int32_t pad_;
 } poco_realnvp;
 
 /* Per-detection crop + normalisation, the step right before the hot path.  Replaces

@@ -91,7 +91,7 @@ class RealNVP(C.Structure):
     _fields_ = [('x', C.c_void_p), ('ctx', C.c_void_p), ('params', C.c_void_p), ('out', C.c_void_p),
                 ('z_out', C.c_void_p), ('logdet_out', C.c_void_p),
                 ('R', C.c_int32), ('D', C.c_int32), ('CTX', C.c_int32), ('HID', C.c_int32), ('L', C.c_int32),
-                ('direction', C.c_int32)]
+                ('direction', C.c_int32), ('ctx_part', C.c_void_p), ('ctx_group', C.c_int32), ('pad_', C.c_int32)]
 
 
 class Crop(C.Structure):

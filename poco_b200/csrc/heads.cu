@@ -367,10 +367,12 @@ __global__ void __launch_bounds__(128) realnvp_kernel(poco_realnvp d) {
         const int r = e / D, k = e % D;
         z[r][k] = r < nr ? d.x[(long long)(r0 + r) * D + k] : 0.f;
     }
-    for (int e = threadIdx.x; e < RB * CTX; e += blockDim.x) {
-        const int r = e / CTX, k = e % CTX;
-        inp[r][D + k] = r < nr ? d.ctx[(long long)(r0 + r) * CTX + k] : 0.f;
-    }
+    const bool hoisted = d.ctx_part != nullptr;     // the context part of every first layer comes precomputed (one GEMM)
+    if (!hoisted)
+        for (int e = threadIdx.x; e < RB * CTX; e += blockDim.x) {
+            const int r = e / CTX, k = e % CTX;
+            inp[r][D + k] = r < nr ? d.ctx[(long long)(r0 + r) * CTX + k] : 0.f;
+        }
     if (threadIdx.x < RB) logdet[threadIdx.x] = 0.f;
     __syncthreads();
     for (int step = 0; step < d.L; ++step) {
@@ -380,6 +382,17 @@ __global__ void __launch_bounds__(128) realnvp_kernel(poco_realnvp d) {
         for (int e = threadIdx.x; e < RB * D; e += blockDim.x) inp[e / D][e % D] = z[e / D][e % D] * mask[e % D];
         __syncthreads();
         // layer 0: 2*HID units, warp-cooperative dot products over IN (coalesced weight reads)
+        if (hoisted) {      // D-column part only (D <= 16: one thread per (row, unit)) + the precomputed context part
+            for (int e = threadIdx.x; e < RB * 2 * HID; e += blockDim.x) {
+                const int r = e / (2 * HID), u = e % (2 * HID);
+                const float* net = P + D + (u / HID) * net_sz;
+                const float* wrow = net + (long long)(u % HID) * IN;
+                const int g = min(r0 + r, d.R - 1) / d.ctx_group;
+                float v = d.ctx_part[(long long)g * (d.L * 2 * HID) + (long long)li * 2 * HID + u];      // includes b0
+                for (int i = 0; i < D; ++i) v = fmaf(wrow[i], inp[r][i], v);
+                h0[r][u] = v > 0.f ? v : 0.01f * v;
+            }
+        } else
         for (int u = warp; u < 2 * HID; u += 4) {
             const float* net = P + D + (u / HID) * net_sz;
             const float* wrow = net + (long long)(u % HID) * IN;
@@ -532,7 +545,8 @@ extern "C" int poco_pare_head_run(const poco_pare_head* d, void* stream) {
 
 extern "C" int poco_realnvp_run(const poco_realnvp* d, void* stream) {
     POCO_CHECK(d->x && d->params && d->out && d->R > 0, "bad arguments");
-    POCO_CHECK(d->D <= RMAXD && d->HID <= RMAXH && d->D + d->CTX <= RMAXIN && (d->CTX == 0 || d->ctx), "unsupported flow shape");
+    POCO_CHECK(d->D <= RMAXD && d->HID <= RMAXH && d->D + d->CTX <= RMAXIN && (d->CTX == 0 || d->ctx || d->ctx_part), "unsupported flow shape");
+    POCO_CHECK(!d->ctx_part || (d->CTX > 0 && d->ctx_group >= 1), "ctx_part needs a conditional flow and ctx_group >= 1");
     realnvp_kernel<<<blocks_for(d->R, RB), 128, 0, static_cast<cudaStream_t>(stream)>>>(*d);
     POCO_LAUNCHED();
     return 0;

@@ -166,6 +166,19 @@ def pack_realnvp(sd, prefix='flow_head.flow.'):
     return torch.cat([p.float() for p in parts]).contiguous()
 
 
+def pack_realnvp_ctx(sd, num_rv, prefix='flow_head.flow.'):
+    """the context columns of the first layer of every (coupling layer, s / t net), stacked for ONE GEMM:
+    -> (W [L*2*HID, CTX], b [L*2*HID]) in the (layer, net = s then t, unit) order poco_realnvp.ctx_part uses"""
+    n = sd[prefix + 'mask'].shape[0]
+    ws, bs = [], []
+    for i in range(n):
+        for net in ('s', 't'):
+            w0 = sd[f'{prefix}{net}.{i}.0.weight'].float()
+            ws.append(w0[:, num_rv:])
+            bs.append(sd[f'{prefix}{net}.{i}.0.bias'].float())
+    return torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous()
+
+
 # ------------------------------------------------------------------------------------------------
 # plan builder
 # ------------------------------------------------------------------------------------------------

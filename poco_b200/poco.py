@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import arch
-from .engine import Plan, PlanBuilder, pack_realnvp
+from .engine import Plan, PlanBuilder, pack_realnvp, pack_realnvp_ctx
 from .smpl import make_smpl_stage
 
 SMPL_MEAN_PARAMS = 'data/smpl_mean_params.npz'      # reference: pocolib/core/config.py:37
@@ -442,24 +442,40 @@ class POCO(nn.Module):
         key = ('flow', str(device))
         if key not in self._engines:
             sd = self.state_dict()
-            self._engines[key] = (pack_realnvp(sd).to(device), sd['flow_head.flow.mask'].shape[0])
+            wc = bc = None
+            if self.cond_nflow:
+                wc, bc = (t.to(device) for t in pack_realnvp_ctx(sd, self.num_nf_rv))
+            self._engines[key] = (pack_realnvp(sd).to(device), sd['flow_head.flow.mask'].shape[0], wc, bc)
         return self._engines[key]
 
-    def _flow_run(self, x, ctx, direction):
+    def _flow_run(self, x, ctx, direction, rows_per_ctx=1):
+        """rows_per_ctx: consecutive rows of x that share one row of ctx (24 = the joints of a crop, as nf_head.py:85-101
+        expands the context); the context part of every coupling layer's first linear layer is computed once per
+        context row with ONE GEMM (real_nvp.py:27-31 / :42-46 evaluate it inside every s / t net call)."""
         if not x.is_cuda:
             raise L.PocoError('RealNVP kernels need CUDA tensors')
-        params, nl = self._flow_params(x.device)
+        params, nl, wc, bc = self._flow_params(x.device)
         x = x.float().contiguous()
         R, D = x.shape
         ctxd = ctx.shape[1] if ctx is not None else 0
         ctx = ctx.float().contiguous() if ctx is not None else None
+        s = torch.cuda.current_stream().cuda_stream
+        ctx_part = None
+        if ctx is not None:
+            if ctx.shape[0] * rows_per_ctx < R or wc is None:
+                raise ValueError(f'flow context: {tuple(ctx.shape)} rows x rows_per_ctx={rows_per_ctx} do not cover {R} rows')
+            G = ctx.shape[0]
+            ctx_part = torch.empty(G, wc.shape[0], dtype=torch.float32, device=x.device)
+            L.run_op(L.Linear(ctx.data_ptr(), ctx.stride(0), wc.data_ptr(), bc.data_ptr(), None, 0, ctx_part.data_ptr(),
+                              ctx_part.stride(0), G, ctxd, wc.shape[0], 0), s)
         out = torch.empty(R if direction == 0 else (R, D), dtype=torch.float32, device=x.device)
         z = torch.empty(R, D, dtype=torch.float32, device=x.device) if direction == 0 else None
         ld = torch.empty(R, dtype=torch.float32, device=x.device) if direction == 0 else None
         d = L.RealNVP(x.data_ptr(), ctx.data_ptr() if ctx is not None else None, params.data_ptr(), out.data_ptr(),
                       z.data_ptr() if z is not None else None, ld.data_ptr() if ld is not None else None,
-                      R, D, ctxd, 64, nl, direction)
-        L.run_op(d, torch.cuda.current_stream().cuda_stream)
+                      R, D, ctxd, 64, nl, direction,
+                      ctx_part.data_ptr() if ctx_part is not None else None, rows_per_ctx, 0)
+        L.run_op(d, s)
         return out, z, ld
 
     def flow_context(self, uncert_feat):
@@ -472,18 +488,18 @@ class POCO(nn.Module):
         L.run_op(d, torch.cuda.current_stream().cuda_stream)
         return y
 
-    def flow_log_prob(self, x, ctx):
-        """RealNVP.log_prob (real_nvp.py:55-65)"""
-        return self._flow_run(x, ctx, 0)[0]
+    def flow_log_prob(self, x, ctx, rows_per_ctx=1):
+        """RealNVP.log_prob (real_nvp.py:55-65).  ctx: one row per row of x, or one per `rows_per_ctx` consecutive rows"""
+        return self._flow_run(x, ctx, 0, rows_per_ctx)[0]
 
-    def flow_backward(self, x, ctx):
+    def flow_backward(self, x, ctx, rows_per_ctx=1):
         """RealNVP.backward_p (real_nvp.py:40-53) -> (z, log_det_J)"""
-        _, z, ld = self._flow_run(x, ctx, 0)
+        _, z, ld = self._flow_run(x, ctx, 0, rows_per_ctx)
         return z, ld
 
-    def flow_forward(self, z, ctx):
+    def flow_forward(self, z, ctx, rows_per_ctx=1):
         """RealNVP.forward_p (real_nvp.py:25-38)"""
-        return self._flow_run(z, ctx, 1)[0]
+        return self._flow_run(z, ctx, 1, rows_per_ctx)[0]
 
 
 class _Engine:

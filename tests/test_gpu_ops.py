@@ -238,6 +238,21 @@ def test_realnvp_against_reference_goldens(preset):
     # cond_layer
     uf = torch.from_numpy(gold['uncert_feat']).cuda()
     assert rel_err(m.flow_context(uf).cpu().numpy(), gold['flow_ctx']) < 2e-5
+    # one context row per crop (the 24 joints of a crop share it, nf_head.py:85-101): same numbers as the expanded call
+    per = rows // meta['test_b']
+    ctx1 = torch.from_numpy(gold['flow_ctx']).cuda()
+    lp1 = m.flow_log_prob(x, ctx1, rows_per_ctx=per)
+    fx1 = m.flow_forward(z, ctx1, rows_per_ctx=per)
+    sync_or_die()
+    assert torch.equal(lp1, lp) and torch.equal(fx1, fx)
+    # the un-hoisted kernel path (ctx_part = NULL in the C ABI) still agrees
+    from poco_b200 import _lib as L2
+    params, nl = m._flow_params(x.device)[:2]
+    out = torch.empty(rows, device='cuda')
+    L2.run_op(L2.RealNVP(x.data_ptr(), ctx.data_ptr(), params.data_ptr(), out.data_ptr(), None, None,
+                         rows, x.shape[1], ctx.shape[1], 64, nl, 0, None, 1, 0), stream())
+    sync_or_die()
+    assert rel_err(out.cpu().numpy(), gold['flow_log_prob']) < 2e-5
 
 
 # ------------------------------------------------------------------------------------------------
