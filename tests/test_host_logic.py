@@ -353,3 +353,20 @@ def test_convert_crop_cam_matches_reference_formula():
     sy = c[:, 0] * (1. / (H / b[:, 2]))
     ref = np.stack([sx, sy, ((b[:, 0] - W / 2.) / (W / 2.) / sx) + c[:, 1], ((b[:, 1] - H / 2.) / (H / 2.) / sy) + c[:, 2]]).T
     assert np.allclose(got, ref, rtol=1e-6, atol=1e-6) and got.shape == (7, 4)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) prints one JSON line with the keys the
+    bench contract names; runs the oracle port (or the reference tree when present) on a 1-crop sample"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                        '--cpu-sample', '1'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'crops/sec' and line['unit'] == 'crops/s'
+    assert line['higher_is_better'] is True and line['value'] > 0 and line['gpu_launches'] == 0
+    assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': 'crops/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in line['config'] and 'model' not in line['config']
