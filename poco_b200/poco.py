@@ -234,6 +234,7 @@ class POCO(nn.Module):
     def _invalidate(self):
         self._version += 1
         self._engines.clear()
+        self._sig_tensors = None
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         r = super().load_state_dict(state_dict, strict=strict, **kw)
@@ -373,7 +374,20 @@ class POCO(nn.Module):
         step = 8 if B <= 64 else (32 if B <= 256 else 64)
         return (B + step - 1) // step * step
 
+    def _param_signature(self):
+        """changes whenever a parameter / buffer is replaced or modified in place (torch bumps `_version` on every
+        in-place write): prepared plans hold folded, packed copies of the weights and must not outlive them"""
+        ts = getattr(self, '_sig_tensors', None)
+        if ts is None:      # (the module walk costs ~3 ms for HRNet: done once per invalidation, the sum below ~0.1 ms)
+            ts = self._sig_tensors = list(self.parameters()) + list(self.buffers())
+        return sum(t._version for t in ts)
+
     def _engine(self, B, device):
+        sig = self._param_signature()
+        if sig != getattr(self, '_plans_sig', None):
+            if self._engines:
+                self._invalidate()
+            self._plans_sig = sig
         key = (B, str(device))
         eng = self._engines.pop(key, None)
         if eng is None:

@@ -161,6 +161,21 @@ def test_submodule_load_state_dict_invalidates_prepared_plans():
     assert not m._engines
 
 
+def test_in_place_parameter_updates_invalidate_prepared_plans():
+    """model.head.fc1.weight.data.mul_(2) (or any optimiser step) must not leave forward() on stale packed weights"""
+    m = build_model('cliff_w32')
+    m._build_engine = lambda B, dev: ('plan', B)
+    m._engine(4, torch.device('cpu'))
+    assert len(m._engines) == 1
+    m._engine(4, torch.device('cpu'))
+    assert len(m._engines) == 1                         # unchanged parameters: the plan is reused
+    with torch.no_grad():
+        m.head.deccam.bias.add_(1.0)
+    built = []
+    m._build_engine = lambda B, dev: built.append(B) or ('plan2', B)
+    assert m._engine(4, torch.device('cpu')) == ('plan2', 4) and built == [4]
+
+
 def test_plan_cache_is_bucketed_and_bounded():
     """tester.py:213 calls forward with B = #detections: batch sizes round up to buckets, plans are LRU-evicted"""
     assert [POCO.bucket(b) for b in (1, 5, 8, 9, 16, 17, 64, 65, 100, 256, 257, 2048)] == \
