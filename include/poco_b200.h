@@ -90,6 +90,24 @@ typedef struct poco_conv_chain {
     int32_t* flags;
 } poco_conv_chain;
 
+/* One residual BasicBlock as ONE launch (hrnet.py:42-58 without a downsample branch):
+ *     out = ReLU(BN2(conv2(ReLU(BN1(conv1(in))))) + in),   both convs 3x3 / stride 1 / pad 1, C -> C channels.
+ * The intermediate tensor never leaves the SM: a work unit computes the conv1 tiles that cover its conv2
+ * tiles plus their (W+3)-pixel reach (halo recompute), the first epilogue writes them as fp16 into shared
+ * memory in the operand layout, and conv2's MMAs read them there; the block input is the residual.
+ * C = 32, W + 3 <= 64, fp16 mode only (in.lo == out.lo == NULL); `in` and `out` must not alias.
+ * weight1 / weight2: poco_conv weight format 0 with the BN scale folded, bias1 / bias2: the BN shifts. */
+typedef struct poco_basic_block {
+    poco_act in;
+    poco_act out;
+    const void* weight1;
+    const float* bias1;
+    const void* weight2;
+    const float* bias2;
+    int32_t max_ctas; /* like poco_conv.max_ctas: 0 = all SMs */
+    int32_t pad_;
+} poco_basic_block;
+
 /* batch['img'] f32 NCHW [N,3,H,W] -> planar-8 fp16 with channels padded to 16 (poco.py:100 input) */
 typedef struct poco_pack_image {
     const float* img;
@@ -345,7 +363,8 @@ typedef enum poco_op_kind {
     POCO_OP_CONV_CHAIN = 15,
     POCO_OP_CROP = 16,
     POCO_OP_UNCERT_POST = 17,
-    POCO_OP_SMPL = 18
+    POCO_OP_SMPL = 18,
+    POCO_OP_BASIC_BLOCK = 19
 } poco_op_kind;
 
 typedef struct poco_op {
@@ -355,6 +374,7 @@ typedef struct poco_op {
         poco_pack_image pack_image;
         poco_conv conv;
         poco_conv_chain conv_chain;
+        poco_basic_block basic_block;
         poco_fuse_sum fuse_sum;
         poco_upsample2x upsample2x;
         poco_maxpool maxpool;
@@ -384,6 +404,8 @@ int64_t poco_kernel_launches(void); /* kernels launched by this library since lo
 int poco_run_op(const poco_op* op, void* stream);
 int poco_conv_run(const poco_conv* d, void* stream);
 int poco_conv_chain_run(const poco_conv_chain* d, void* stream);
+int poco_basic_block_run(const poco_basic_block* d, void* stream);
+int poco_basic_block_supported(int32_t C, int32_t H, int32_t W); /* 1 iff poco_basic_block_run takes this geometry */
 int64_t poco_conv_chain_flag_count(const poco_conv_chain* d); /* int32 entries `flags` must hold */
 int poco_pack_image_run(const poco_pack_image* d, void* stream);
 int poco_fuse_sum_run(const poco_fuse_sum* d, void* stream);

@@ -142,7 +142,15 @@ def conv_cost(N, cin, cout, k, Hout, Wout):
 # ------------------------------------------------------------------------------------------------
 def basic_block(b, x, name, cin, cout, free_input=True, s2d_out=None):
     """conv3x3-BN-ReLU, conv3x3-BN, += x, ReLU  (hrnet.py:42-58); HRNet branches never downsample.
-    s2d_out: the block's output also feeds stride-2 convs -> its last conv writes the phase-split copy too"""
+    s2d_out: the block's output also feeds stride-2 convs -> its last conv writes the phase-split copy too.
+    A backend may run the whole block as one launch (PlanBuilder.basic_block_fused: the intermediate stays on the SM)."""
+    fused = getattr(b, 'basic_block_fused', None)
+    if fused is not None and cin == cout and s2d_out is None:
+        o = fused(x, name, cin)
+        if o is not None:
+            if free_input:
+                b.free(x)
+            return o
     y = b.conv_bn(x, name + '.conv1', name + '.bn1', cin, cout, 3)
     o = b.conv_bn(y, name + '.conv2', name + '.bn2', cout, cout, 3, residual=x, s2d=s2d_out)
     b.free(y)

@@ -107,6 +107,7 @@ extern "C" int poco_run_op(const poco_op* op, void* stream) {
         case POCO_OP_CROP: return poco_crop_run(&op->u.crop, stream);
         case POCO_OP_UNCERT_POST: return poco_uncert_post_run(&op->u.uncert_post, stream);
         case POCO_OP_SMPL: return poco_smpl_run(&op->u.smpl, stream);
+        case POCO_OP_BASIC_BLOCK: return poco_basic_block_run(&op->u.basic_block, stream);
         default: break;
     }
     set_error("poco_run_op: unknown op kind " + std::to_string(op->kind));
@@ -121,8 +122,12 @@ extern "C" int poco_plan_create(const poco_op* ops, int32_t n_ops, poco_plan** o
         if (op.kind == POCO_OP_CONV) p->flops += conv_flops(&op.u.conv);
         if (op.kind == POCO_OP_CONV_CHAIN)
             for (int k = 0; k < op.u.conv_chain.n_seg; ++k) p->flops += conv_flops(&op.u.conv_chain.seg[k]);
+        if (op.kind == POCO_OP_BASIC_BLOCK) {
+            const poco_act& a = op.u.basic_block.out;
+            p->flops += 2 * (2ll * a.N * a.H * a.W * a.C * a.C * 9);
+        }
         if (op.kind == POCO_OP_LINEAR) p->flops += 2ll * op.u.linear.M * op.u.linear.I * op.u.linear.O;
-        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_SMPL || op.lane < 0 || op.lane >= kMaxLanes) {
+        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_BASIC_BLOCK || op.lane < 0 || op.lane >= kMaxLanes) {
             delete p;
             set_error("poco_plan_create: unknown op kind " + std::to_string(op.kind));
             return 1;

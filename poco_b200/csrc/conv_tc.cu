@@ -33,15 +33,6 @@ namespace poco {
 
 namespace {
 
-// -DPOCO_MBAR_WATCHDOG: every mbarrier wait gets a 2 s watchdog that reports its source line and traps
-// (bring-up builds only: the bookkeeping in the hot wait loops costs 8-14 % of every conv, measured).
-// The global-memory flag spin of the chain protocol always carries the watchdog.
-#ifdef POCO_MBAR_WATCHDOG
-#define MBAR_WAIT(bar, parity) mbar_wait_tag(bar, parity, __LINE__)
-#else
-#define MBAR_WAIT(bar, parity) mbar_wait(bar, parity)
-#endif
-
 constexpr int kMaxStages = 16;                     // operand stages over both rings (header barrier arrays)
 constexpr int kMaxAccBufs = 8;                     // TMEM accumulator ring (512 columns / n_tile)
 constexpr int kTileM = 128;
@@ -157,62 +148,6 @@ struct Roles {
     static constexpr int kThreads = (kEpiWarp0 + 8) * 32;
 };
 
-
-// Issue every MMA of one shared-memory stage as straight-line code.  The issuing thread is the
-// bottleneck for small N: measured (profiles/r01_mma_issue_rate.csv) the tensor pipe accepts an SS-mode
-// M=128 K=16 MMA every max(N/2, 32 + N/4) cycles (operand fetch at 128 B/clk), but a descriptor that is
-// built in vector registers and moved with R2UR costs the thread ~77 cycles per MMA.  Here every
-// descriptor is `base + compile-time multiple of a uniform stride`, so ptxas keeps the chain in uniform
-// registers: ~3 uniform ALU ops per UTCHMMA.
-__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; }
-
-// POCO_ISSUE_BATCH (round 2): UTCHMMA reads its descriptors from uniform registers and holds them until the tensor pipe
-// dequeues the instruction; a uniform-datapath op that overwrites one of them stalls (short scoreboard) until then.  The
-// lean "3 uniform ops per MMA" chain reused a handful of registers every 2-3 MMAs, so only ~3 MMAs were ever queued and the
-// pipe ran at 60-72 cycles per MMA instead of its 40-64 (ncu source page: 80 % of the issuer's samples were short_sb on
-// UIADD3; tools/mma_bench7.cu reaches the hardware rate with the same operand geometry).  Here the descriptors of a batch
-// of MMAs are materialised in ordinary registers first; ptxas then moves each into its own uniform register pair right
-// before its UTCHMMA, so a whole batch can sit in the queue.  0 = the old uniform chain.
-#ifndef POCO_ISSUE_BATCH
-#define POCO_ISSUE_BATCH 12
-#endif
-template <int TAPS, int KS>
-__device__ __forceinline__ void issue_linear(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, const uint32_t (&sh)[9], uint32_t a_kstep,
-                                             uint32_t b_kstep, uint32_t b_tap, uint32_t desc_hi, uint32_t idesc,
-                                             uint32_t acc0) {
-#if POCO_ISSUE_BATCH > 0
-    constexpr int TOTAL = TAPS * KS;
-    constexpr int BATCH = POCO_ISSUE_BATCH < TOTAL ? POCO_ISSUE_BATCH : TOTAL;
-#pragma unroll
-    for (int j0 = 0; j0 < TOTAL; j0 += BATCH) {
-        uint32_t al[BATCH], bl[BATCH];
-#pragma unroll
-        for (int i = 0; i < BATCH; ++i) {
-            const int j = j0 + i, t = j / KS, k = j % KS;
-            if (j < TOTAL) {
-                al[i] = a_lo + sh[t] + uint32_t(k) * a_kstep;       // sh: where tap t starts inside the landed run
-                bl[i] = b_lo + uint32_t(t) * b_tap + uint32_t(k) * b_kstep;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < BATCH; ++i)
-            if (j0 + i < TOTAL) asm volatile("" : "+r"(al[i]), "+r"(bl[i]));        // all of the batch live in registers here
-#pragma unroll
-        for (int i = 0; i < BATCH; ++i)
-            if (j0 + i < TOTAL) umma_f16(d_tmem, desc64(desc_hi, al[i]), desc64(desc_hi, bl[i]), idesc, (j0 + i) ? 1u : acc0);
-    }
-#else
-#pragma unroll
-    for (int t = 0; t < TAPS; ++t) {
-        const uint32_t at = a_lo + sh[t];
-        const uint32_t bt = b_lo + uint32_t(t) * b_tap;
-#pragma unroll
-        for (int k = 0; k < KS; ++k)
-            umma_f16(d_tmem, desc64(desc_hi, at + uint32_t(k) * a_kstep), desc64(desc_hi, bt + uint32_t(k) * b_kstep), idesc,
-                     (t | k) ? 1u : acc0);
-    }
-#endif
-}
 
 template <int TG>
 __device__ __forceinline__ void issue_gather(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t b_tap,

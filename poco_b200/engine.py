@@ -413,6 +413,32 @@ class PlanBuilder:
         self.conv_log.append((convs[0], x.C, cout, k, stride, x.H, Ho))
         return out
 
+    def basic_block_fused(self, x, name, c, out=None):
+        """BasicBlock `name` (conv1-bn1-ReLU-conv2-bn2, += x, ReLU; hrnet.py:42-58) as ONE poco_basic_block launch when the
+        library takes the geometry (32 channels, W <= 61, fp16 mode); None otherwise (the caller emits two conv_bn ops).
+        POCO_B200_FUSE_BLOCK=0 switches it off."""
+        if (self.conv_impl != 0 or self.split or self.chain is not None or x.C != c or
+                os.environ.get('POCO_B200_FUSE_BLOCK', '1') == '0' or not hasattr(L.lib(), 'poco_basic_block_supported') or
+                not L.lib().poco_basic_block_supported(c, x.H, x.W)):
+            return None
+        sd = self.sd
+        packed = []
+        for cv, bn in ((name + '.conv1', name + '.bn1'), (name + '.conv2', name + '.bn2')):
+            w = sd[cv + '.weight'].cpu()
+            assert tuple(w.shape) == (c, c, 3, 3) and sd.get(cv + '.bias') is None, cv
+            wf, bf = fold_bn(w, None, tuple(sd[bn + s_].cpu() for s_ in ('.weight', '.bias', '.running_mean', '.running_var')))
+            packed += [pack_conv_weight(wf).to(self.device), bf.contiguous().to(self.device)]
+        self.keep += packed
+        if out is None:
+            out = self.act(c, x.H, x.W)
+        assert (out.C, out.H, out.W) == (c, x.H, x.W)
+        d = L.BasicBlock(x.desc(), out.desc(), packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(),
+                         packed[3].data_ptr(), self._share(), 0)
+        self.add(d)
+        self.conv_log.append((name + '.conv1', c, c, 3, 1, x.H, x.H))
+        self.conv_log.append((name + '.conv2', c, c, 3, 1, x.H, x.H))
+        return out
+
     # -- conv chains: consecutive same-geometry convs (the BasicBlocks of an HRNet branch) as ONE launch
     def begin_chain(self):
         assert self.chain is None

@@ -27,7 +27,7 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def run_conv(x, w, bias, stride=1, pad=None, relu=1, residual=None, impl=0, dxn=False, split=False):
+def run_conv(x, w, bias, stride=1, pad=None, relu=1, residual=None, impl=0, dxn=False, split=False, max_ctas=0):
     """x [N,Cin,H,W], w [Cout,Cin,k,k], bias [Cout] (CPU float) -> [N,Cout,Ho,Wo] float (CPU).
     Inputs are rounded to fp16 exactly as the engine does (split=True: to hi + lo fp16 pairs, the parity mode)."""
     dev = 'cuda'
@@ -44,7 +44,7 @@ def run_conv(x, w, bias, stride=1, pad=None, relu=1, residual=None, impl=0, dxn=
     b = bias.to(dev).float().contiguous()
     r = engine.to_planar(residual.to(dev), split=split) if residual is not None else None
     d = L.Conv(a.desc(), o.desc(), wp.data_ptr(), b.data_ptr(), r.ptr if r is not None else None,
-               r.plane_stride if r is not None else 0, k, k, stride, pad, relu, impl, 0, wfmt,
+               r.plane_stride if r is not None else 0, k, k, stride, pad, relu, impl, max_ctas, wfmt,
                r.ptr_lo if r is not None else None)
     L.run_op(d, stream())
     sync_or_die()
@@ -89,3 +89,20 @@ def conv_reference_split(x, w, bias, stride=1, pad=None, relu=1, residual=None):
     if relu == 1:
         y = F.relu(y)
     return y
+
+
+def run_basic_block(x, w1, b1, w2, b2, max_ctas=0):
+    """fused BasicBlock (poco_basic_block): x [N,C,H,W], w1 / w2 [C,C,3,3] (BN folded), b1 / b2 [C] -> [N,C,H,W] float (CPU)"""
+    dev = 'cuda'
+    N, C_, H, W = x.shape
+    a = engine.to_planar(x.to(dev))
+    o = engine.alloc_act(C_, N, H, W, dev)
+    p1, p2 = engine.pack_conv_weight(w1.to(dev).float()), engine.pack_conv_weight(w2.to(dev).float())
+    c1, c2 = b1.to(dev).float().contiguous(), b2.to(dev).float().contiguous()
+    d = L.BasicBlock(a.desc(), o.desc(), p1.data_ptr(), c1.data_ptr(), p2.data_ptr(), c2.data_ptr(), max_ctas, 0)
+    L.run_op(d, stream())
+    sync_or_die()
+    halo = engine.act_view(o)
+    assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
+                 halo[:, :, :, -1].abs().sum()) == 0.0, 'kernel wrote into the zero halo'
+    return engine.from_planar(o).cpu()

@@ -547,3 +547,41 @@ def test_phase_split_only_output_leaves_no_normal_tensor():
         L.run_op(op, stream())
     sync_or_die(30)
     assert rel_err(engine.from_planar(z).cpu().numpy(), engine.from_planar(z2).cpu().numpy()) < CONV_TOL
+
+
+@pytest.mark.parametrize('H,W,N,max_ctas', [(56, 56, 2, 0), (56, 56, 7, 5), (28, 28, 3, 0), (8, 12, 1, 0), (56, 56, 37, 0), (20, 61, 2, 3)])
+def test_basic_block_fused_matches_two_convs(H, W, N, max_ctas):
+    """poco_basic_block (conv1 -> shared memory -> conv2 + input as residual, one launch) against the same block as two
+    poco_conv launches: bit-identical (same MMA order, same fp16 rounding of the intermediate; the two-launch block runs
+    with a CTA budget so that it takes the one-CTA-per-SM flavour -- the two-CTA flavour walks K in 16-channel chunks,
+    another summation order), and against fp32 arithmetic on the fp16-rounded operands (hrnet.py:42-58).  Cases: several units per CTA / one short unit, a CTA
+    budget (plan lanes), crops that straddle unit boundaries, the widest row the kernel takes (W + 3 = 64)."""
+    from gpu_util import run_basic_block
+    assert L.lib().poco_basic_block_supported(32, H, W) == 1
+    g = torch.Generator().manual_seed(H * 100 + N)
+    x = torch.randn(N, 32, H, W, generator=g)
+    w1, w2 = (torch.randn(32, 32, 3, 3, generator=g) * 0.08 for _ in range(2))
+    b1, b2 = (torch.randn(32, generator=g) * 0.2 for _ in range(2))
+    got = run_basic_block(x, w1, b1, w2, b2, max_ctas)
+    mid = run_conv(x, w1, b1, relu=1, max_ctas=148)
+    two = run_conv(mid, w2, b2, relu=1, residual=x, max_ctas=148)
+    assert torch.equal(got, two), float((got - two).abs().max())
+    ref_mid = conv_reference(x, w1, b1, relu=1).half().float()
+    ref = conv_reference(ref_mid, w2, b2, relu=1, residual=x)
+    assert rel_err(got, ref) < CONV_TOL
+
+
+def test_basic_block_rejects_what_it_cannot_fuse():
+    lib = L.lib()
+    assert lib.poco_basic_block_supported(64, 28, 28) == 0 and lib.poco_basic_block_supported(32, 56, 62) == 0
+    a = engine.alloc_act(64, 1, 28, 28, 'cuda')
+    o = engine.alloc_act(64, 1, 28, 28, 'cuda')
+    w = torch.zeros(9 * 8 * 64 * 8, dtype=torch.float16, device='cuda')
+    b = torch.zeros(64, device='cuda')
+    d = L.BasicBlock(a.desc(), o.desc(), w.data_ptr(), b.data_ptr(), w.data_ptr(), b.data_ptr(), 0, 0)
+    with pytest.raises(L.PocoError):
+        L.run_op(d, stream())
+    a32 = engine.alloc_act(32, 1, 8, 8, 'cuda')
+    d = L.BasicBlock(a32.desc(), a32.desc(), w.data_ptr(), b.data_ptr(), w.data_ptr(), b.data_ptr(), 0, 0)
+    with pytest.raises(L.PocoError):        # in-place
+        L.run_op(d, stream())

@@ -1,0 +1,46 @@
+"""fused BasicBlock (poco_basic_block) against the same block as two poco_conv launches, batch 256, CUDA events"""
+import os
+import sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from poco_b200 import _lib as L
+from poco_b200 import engine
+
+B, H = int(sys.argv[1]) if len(sys.argv) > 1 else 256, 56
+dev = 'cuda'
+s = torch.cuda.current_stream().cuda_stream
+a = engine.alloc_act(32, B, H, H, dev)
+engine.act_view(a)[:, :, 1:H + 1, 1:H + 1].normal_()
+m, o = engine.alloc_act(32, B, H, H, dev), engine.alloc_act(32, B, H, H, dev)
+w = [(torch.randn(9, 4, 32, 8, device=dev) * 0.05).half() for _ in range(2)]
+b = [torch.randn(32, device=dev) * 0.1 for _ in range(2)]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timed(fn, reps=10):
+    fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps * 1e3
+
+
+for ctas in (0, 148, 74, 37):
+    fused = L.BasicBlock(a.desc(), o.desc(), w[0].data_ptr(), b[0].data_ptr(), w[1].data_ptr(), b[1].data_ptr(), ctas, 0)
+    c1 = L.Conv(a.desc(), m.desc(), w[0].data_ptr(), b[0].data_ptr(), None, 0, 3, 3, 1, 1, 1, 0, ctas, 0, None)
+    c2 = L.Conv(m.desc(), o.desc(), w[1].data_ptr(), b[1].data_ptr(), a.ptr, a.plane_stride, 3, 3, 1, 1, 1, 0, ctas, 0, None)
+
+    def two():
+        L.run_op(c1, s)
+        L.run_op(c2, s)
+    t2 = timed(two)
+    tf = timed(lambda: L.run_op(fused, s))
+    print(f'batch {B} max_ctas {ctas}: two launches {t2:.1f} us, fused {tf:.1f} us', flush=True)

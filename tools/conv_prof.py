@@ -14,14 +14,15 @@ cin, cout, k, st, H, res, B = (int(v) for v in sys.argv[1:8])
 DBG = [int(x) for x in sys.argv[8].split(',')]
 s = torch.cuda.current_stream().cuda_stream
 Ho = (H + 2 * (k // 2) - k) // st + 1
-a = engine.alloc_act(cin, B, H, H, 'cuda')
+SPLIT = os.environ.get('PROF_SPLIT') == '1'
+a = engine.alloc_act(cin, B, H, H, 'cuda', SPLIT)
 engine.act_view(a)[:, :, 1:H + 1, 1:H + 1].normal_()
-o = engine.alloc_act(cout, B, Ho, Ho, 'cuda')
-r = engine.alloc_act(cout, B, Ho, Ho, 'cuda') if res else None
-w = (torch.randn(k * k, cin // 8, cout, 8, device='cuda') * 0.05).half()
+o = engine.alloc_act(cout, B, Ho, Ho, 'cuda', SPLIT)
+r = engine.alloc_act(cout, B, Ho, Ho, 'cuda', SPLIT) if res else None
+w = (torch.randn((2 if SPLIT else 1) * k * k, cin // 8, cout, 8, device='cuda') * 0.05).half()
 b = torch.zeros(cout, device='cuda')
 d = L.Conv(a.desc(), o.desc(), w.data_ptr(), b.data_ptr(), r.ptr if r else None, r.plane_stride if r else 0,
-           k, k, st, k // 2, 1, 0, 0, 0)
+           k, k, st, k // 2, 1, 0, 0, 0, r.ptr_lo if r else None)
 op = L.make_op(d)
 prof = torch.zeros(16, dtype=torch.int64, device='cuda')
 os.environ['POCO_CONV_PROF'] = str(prof.data_ptr())
