@@ -18,14 +18,15 @@
 // HBM traffic per block: input once + output once (103 MB at batch 256); the kernel is bound by the tensor pipe at
 // its small-N rate (an M = 128, N = 32, K = 16 MMA every 40 cycles: 7 x 18 x 40 = 5040 cycles per unit).
 //
-// Roles (320 threads, one persistent CTA per SM, units dealt round-robin): warp 0 producer (weights once, then the
-// input runs, double buffered), warp 1 issues every MMA in the order C1(0) C1(1) C2(0) C1(2) C2(1) ... so that
-// epilogue 1 of unit u+1 and epilogue 2 of unit u run under the MMAs of their neighbours, warps 2-9 epilogue
+// Roles (352 threads, one persistent CTA per SM, units dealt round-robin): warp 0 producer (weights once, then the
+// input runs, double buffered), warp 1 issues conv1's MMAs and warp 2 conv2's, each unit by unit behind its own
+// barriers, so that the tensor pipe always has the other conv's tiles queued while an epilogue runs; warps 3-10 epilogue
 // (two sets of four TMEM lane groups; a set takes alternate tiles).  TMEM: 2 x (4 + 3) accumulators of 32 columns.
 // mbarriers, each a two-deep ring over the local unit index j (buffer j & 1, use j >> 1):
 //   in_full / in_free (producer <-> C1), acc1_full / acc1_free (C1 <-> epilogue 1), mid_full / mid_free
 //   (epilogue 1 <-> C2), acc2_full / acc2_free (C2 <-> epilogue 2).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -56,7 +57,7 @@ constexpr int kSlab = kC * 16;          // one (tap, 8-channel) weight slab: 32 
 constexpr int kWBytes = 9 * kPlanes * kSlab;        // one conv's weights: 18 KB
 constexpr int kMidPitch = kT1 * kTile * 16;         // one plane of the intermediate: 8 KB
 constexpr int kHeader = 1024;
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;          // producer, two issuers, eight epilogue warps
 constexpr int kTmemCols = 512;          // 2 x (4 + 3) x 32 = 448 used
 
 struct BlockParams {
@@ -72,6 +73,7 @@ struct BlockParams {
     int num_units;
     int in_pitch;                       // bytes between the planes of an input run in shared memory
     int run_bytes;                      // bytes of one input run: (4 * 128 + 2 R) * 16
+    unsigned long long* prof;           // bring-up (POCO_BBLOCK_PROF): per issuer [total, in_full, acc1_free, mid_full, acc2_free, issue, units, ctas]
 };
 
 struct Header {
@@ -141,8 +143,8 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // ============================================================ MMA issuer
+    } else if (warp <= 2) {
+        // ============================================================ MMA issuers: warp 1 conv1, warp 2 conv2
         const uint32_t idesc = umma_idesc_f16(kTile, kC);
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);
         const uint32_t in_lbo = (uint32_t(p.in_pitch) >> 4) << 16, in_kstep = (2u * uint32_t(p.in_pitch)) >> 4;
@@ -153,10 +155,16 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
         for (int t = 0; t < 9; ++t) sh[t] = uint32_t((t / 3 - 1) * Wp + (t % 3 - 1));
         const uint32_t w1_lo = (smem_u32(w_smem) >> 4) | b_lbo, w2_lo = ((smem_u32(w_smem) + kWBytes) >> 4) | b_lbo;
         MBAR_WAIT(smem_u32(&hdr->w_full), 0u);
+        const bool prof = p.prof != nullptr;
+        long long pt[5] = {0, 0, 0, 0, 0}, pt_mark = prof ? clock64() : 0;
+        const long long pt_t0 = pt_mark;
+        auto lap = [&](int k) { if (prof) { const long long t = clock64(); pt[k] += t - pt_mark; pt_mark = t; } };
         auto conv1 = [&](int j) {
             const uint32_t b = uint32_t(j) & 1u, par = (uint32_t(j) >> 1) & 1u;
             MBAR_WAIT(smem_u32(&hdr->in_full[b]), par);
+            lap(0);
             MBAR_WAIT(smem_u32(&hdr->acc1_free[b]), par ^ 1u);
+            lap(1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t a0 = smem_u32(in_smem) + b * uint32_t(in_buf_bytes) + uint32_t(R) * 16u;
@@ -168,11 +176,14 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
                 umma_commit(smem_u32(&hdr->in_free[b]));
             }
             __syncwarp();
+            lap(4);
         };
         auto conv2 = [&](int j) {
             const uint32_t b = uint32_t(j) & 1u, par = (uint32_t(j) >> 1) & 1u;
             MBAR_WAIT(smem_u32(&hdr->mid_full[b]), par);
+            lap(2);
             MBAR_WAIT(smem_u32(&hdr->acc2_free[b]), par ^ 1u);
+            lap(3);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t a0 = smem_u32(mid_smem) + b * uint32_t(mid_buf_bytes) + uint32_t(kLead) * 16u;
@@ -184,15 +195,25 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
                 umma_commit(smem_u32(&hdr->mid_free[b]));
             }
             __syncwarp();
+            lap(4);
         };
-        if (my_units > 0) conv1(0);
-        for (int j = 0; j < my_units; ++j) {
-            if (j + 1 < my_units) conv1(j + 1);
-            conv2(j);
+        // (one warp issuing C1(0) C1(1) C2(0) C1(2) ... spent 47 cycles per MMA against the pipe's 40: two warps, each
+        // with its own waits, keep the queue fed while the other one is between units)
+        if (warp == 1) {
+            for (int j = 0; j < my_units; ++j) conv1(j);
+        } else {
+            for (int j = 0; j < my_units; ++j) conv2(j);
+        }
+        if (prof && lane == 0) {
+            unsigned long long* o = p.prof + (warp - 1) * 8;
+            atomicAdd(o + 0, (unsigned long long)(clock64() - pt_t0));
+            for (int k = 0; k < 5; ++k) atomicAdd(o + 1 + k, (unsigned long long)pt[k]);
+            atomicAdd(o + 6, (unsigned long long)my_units);
+            atomicAdd(o + 7, 1ull);
         }
     } else {
         // ============================================================ epilogue (8 warps)
-        const int ew = warp - 2;
+        const int ew = warp - 3;
         const int set = ew >> 2;                        // tiles alternate between the two sets
         const int lg = warp & 3;                        // TMEM lane group this warp may access
         const int row = lg * 32 + lane;
@@ -338,6 +359,8 @@ extern "C" int poco_basic_block_run(const poco_basic_block* d, void* stream) {
     p.num_units = int((P + kG * kTile - 1) / (kG * kTile));
     p.run_bytes = (kT1 * kTile + 2 * R) * 16;
     p.in_pitch = (p.run_bytes + 127) / 128 * 128;
+    static const char* prof_env = getenv("POCO_BBLOCK_PROF");       // bring-up: device address (decimal) of 16 zeroed uint64 counters
+    p.prof = prof_env ? reinterpret_cast<unsigned long long*>(strtoull(prof_env, nullptr, 10)) : nullptr;
     const size_t smem = size_t(kHeader) + 2 * kWBytes + 2 * size_t(kPlanes) * p.in_pitch + 2 * size_t(kPlanes) * kMidPitch;
     POCO_CHECK(smem <= 227 * 1024, "shared memory");
     static std::once_flag once;

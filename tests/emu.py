@@ -198,7 +198,19 @@ def _op15(self, d):         # conv chain = its segments in order
         self._op2(d.seg[k])
 
 
+def _op19(self, d):         # fused BasicBlock: conv1 -> fp16 intermediate -> conv2 + input as residual
+    i, o = d.in_, d.out
+    c = o.C
+    x = self.act_get(i)
+    ws = [self.flat(w_, torch.float16)[:9 * c * c].view(9, c // 8, c, 8).float().permute(2, 1, 3, 0).reshape(c, c, 3, 3)
+          for w_ in (d.weight1, d.weight2)]
+    bs = [self.flat(b_, torch.float32)[:c] for b_ in (d.bias1, d.bias2)]
+    mid = F.relu(F.conv2d(x, ws[0], bs[0], padding=1)).half().float()      # the kernel keeps it as fp16 in shared memory
+    self.act_set(o, F.relu(F.conv2d(mid, ws[1], bs[1], padding=1) + x))
+
+
 Emu._op15 = _op15
+Emu._op19 = _op19
 Emu._op13 = lambda self, d: None      # fork / join of plan lanes: the interpreter is sequential
 Emu._op14 = lambda self, d: None
 

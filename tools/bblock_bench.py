@@ -16,6 +16,9 @@ m, o = engine.alloc_act(32, B, H, H, dev), engine.alloc_act(32, B, H, H, dev)
 w = [(torch.randn(9, 4, 32, 8, device=dev) * 0.05).half() for _ in range(2)]
 b = [torch.randn(32, device=dev) * 0.1 for _ in range(2)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+prof = torch.zeros(16, dtype=torch.int64, device=dev)
+if os.environ.get('BB_PROF') == '1':
+    os.environ['POCO_BBLOCK_PROF'] = str(prof.data_ptr())
 
 
 def timed(fn, reps=10):
@@ -44,3 +47,12 @@ for ctas in (0, 148, 74, 37):
     t2 = timed(two)
     tf = timed(lambda: L.run_op(fused, s))
     print(f'batch {B} max_ctas {ctas}: two launches {t2:.1f} us, fused {tf:.1f} us', flush=True)
+    if os.environ.get('BB_PROF') == '1':
+        prof.zero_()
+        L.run_op(fused, s)
+        torch.cuda.synchronize()
+        for w_ in range(2):
+            v = prof.tolist()[w_ * 8:w_ * 8 + 8]
+            n = max(1, v[6])
+            print('   conv%d issuer, cycles per unit: total %.0f | wait in_full %.0f acc1_free %.0f mid_full %.0f acc2_free %.0f | issue %.0f   (units/cta %.1f)' %
+                  (w_ + 1, v[0] / n, v[1] / n, v[2] / n, v[3] / n, v[4] / n, v[5] / n, v[6] / max(1, v[7])), flush=True)
