@@ -108,6 +108,25 @@ typedef struct poco_basic_block {
     int32_t pad_;
 } poco_basic_block;
 
+/* The tail of a Bottleneck block as ONE launch (hrnet.py:79-99, resnet.py:100-121):
+ *     out = ReLU(BN3(conv3(ReLU(BN2(conv2(in))))) + residual),   conv2 3x3 / stride 1 / pad 1 (Cmid -> Cmid),
+ * conv3 1x1 (Cmid -> Cout).  conv2's output tile goes through shared memory straight into conv3's MMAs (a 1x1 conv
+ * is pointwise: no halo, no recompute).  Cmid = 64, Cout = 256 (layer1 of the HRNet trunks), fp16 mode only;
+ * `residual` has `out`'s geometry (plane stride res_plane_stride pixels) and must not alias `out`.
+ * weight2 / weight3: poco_conv weight format 0 with the BN scales folded, bias2 / bias3: the BN shifts. */
+typedef struct poco_bottleneck_tail {
+    poco_act in;
+    poco_act out;
+    const void* residual;
+    int64_t res_plane_stride;
+    const void* weight2;
+    const float* bias2;
+    const void* weight3;
+    const float* bias3;
+    int32_t max_ctas; /* like poco_conv.max_ctas: 0 = all SMs */
+    int32_t pad_;
+} poco_bottleneck_tail;
+
 /* batch['img'] f32 NCHW [N,3,H,W] -> planar-8 fp16 with channels padded to 16 (poco.py:100 input) */
 typedef struct poco_pack_image {
     const float* img;
@@ -364,7 +383,8 @@ typedef enum poco_op_kind {
     POCO_OP_CROP = 16,
     POCO_OP_UNCERT_POST = 17,
     POCO_OP_SMPL = 18,
-    POCO_OP_BASIC_BLOCK = 19
+    POCO_OP_BASIC_BLOCK = 19,
+    POCO_OP_BOTTLENECK_TAIL = 20
 } poco_op_kind;
 
 typedef struct poco_op {
@@ -375,6 +395,7 @@ typedef struct poco_op {
         poco_conv conv;
         poco_conv_chain conv_chain;
         poco_basic_block basic_block;
+        poco_bottleneck_tail bottleneck_tail;
         poco_fuse_sum fuse_sum;
         poco_upsample2x upsample2x;
         poco_maxpool maxpool;
@@ -406,6 +427,8 @@ int poco_conv_run(const poco_conv* d, void* stream);
 int poco_conv_chain_run(const poco_conv_chain* d, void* stream);
 int poco_basic_block_run(const poco_basic_block* d, void* stream);
 int poco_basic_block_supported(int32_t C, int32_t H, int32_t W); /* 1 iff poco_basic_block_run takes this geometry */
+int poco_bottleneck_tail_run(const poco_bottleneck_tail* d, void* stream);
+int poco_bottleneck_tail_supported(int32_t Cmid, int32_t Cout, int32_t H, int32_t W);
 int64_t poco_conv_chain_flag_count(const poco_conv_chain* d); /* int32 entries `flags` must hold */
 int poco_pack_image_run(const poco_pack_image* d, void* stream);
 int poco_fuse_sum_run(const poco_fuse_sum* d, void* stream);

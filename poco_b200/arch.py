@@ -165,6 +165,19 @@ def bottleneck(b, x, name, cin, planes, stride=1, downsample=False, free_input=T
     for the strided 1x1 downsample when the previous block wrote one)"""
     cout = planes * 4
     y1 = b.conv_bn(x, name + '.conv1', name + '.bn1', cin, planes, 1)      # (phase-split hand-off to a strided conv2 measured slower on ResNet-50)
+    can_fuse = getattr(b, 'bottleneck_tail_supported', None)
+    if can_fuse is not None and stride == 1 and s2d_out is None and can_fuse(y1, planes, cout):
+        # conv2 -> conv3 + residual as one launch (PlanBuilder.bottleneck_tail_fused: conv2's tile never leaves the SM)
+        r = x
+        if downsample:
+            r = b.conv_bn(x, name + '.downsample.0', name + '.downsample.1', cin, cout, 1, 1, relu=False)
+        o = b.bottleneck_tail_fused(y1, name, planes, cout, r)
+        b.free(y1)
+        if r is not x:
+            b.free(r)
+        if free_input:
+            b.free(x)
+        return o
     y2 = b.conv_bn(y1, name + '.conv2', name + '.bn2', planes, planes, 3, stride)
     b.free(y1)
     r = x

@@ -108,6 +108,7 @@ extern "C" int poco_run_op(const poco_op* op, void* stream) {
         case POCO_OP_UNCERT_POST: return poco_uncert_post_run(&op->u.uncert_post, stream);
         case POCO_OP_SMPL: return poco_smpl_run(&op->u.smpl, stream);
         case POCO_OP_BASIC_BLOCK: return poco_basic_block_run(&op->u.basic_block, stream);
+        case POCO_OP_BOTTLENECK_TAIL: return poco_bottleneck_tail_run(&op->u.bottleneck_tail, stream);
         default: break;
     }
     set_error("poco_run_op: unknown op kind " + std::to_string(op->kind));
@@ -126,8 +127,12 @@ extern "C" int poco_plan_create(const poco_op* ops, int32_t n_ops, poco_plan** o
             const poco_act& a = op.u.basic_block.out;
             p->flops += 2 * (2ll * a.N * a.H * a.W * a.C * a.C * 9);
         }
+        if (op.kind == POCO_OP_BOTTLENECK_TAIL) {
+            const poco_bottleneck_tail& t = op.u.bottleneck_tail;
+            p->flops += 2ll * t.out.N * t.out.H * t.out.W * (int64_t(t.in.C) * t.in.C * 9 + int64_t(t.in.C) * t.out.C);
+        }
         if (op.kind == POCO_OP_LINEAR) p->flops += 2ll * op.u.linear.M * op.u.linear.I * op.u.linear.O;
-        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_BASIC_BLOCK || op.lane < 0 || op.lane >= kMaxLanes) {
+        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_BOTTLENECK_TAIL || op.lane < 0 || op.lane >= kMaxLanes) {
             delete p;
             set_error("poco_plan_create: unknown op kind " + std::to_string(op.kind));
             return 1;

@@ -439,6 +439,32 @@ class PlanBuilder:
         self.conv_log.append((name + '.conv2', c, c, 3, 1, x.H, x.H))
         return out
 
+    def bottleneck_tail_supported(self, y1, planes, cout):
+        """True when conv2 (3x3) -> conv3 (1x1) + residual of a Bottleneck runs as one poco_bottleneck_tail launch
+        (64 -> 64 -> 256 channels, fp16 mode).  POCO_B200_FUSE_TAIL=0 switches it off."""
+        return (self.conv_impl == 0 and not self.split and self.chain is None and y1.C == planes and
+                os.environ.get('POCO_B200_FUSE_TAIL', '1') != '0' and hasattr(L.lib(), 'poco_bottleneck_tail_supported') and
+                bool(L.lib().poco_bottleneck_tail_supported(planes, cout, y1.H, y1.W)))
+
+    def bottleneck_tail_fused(self, y1, name, planes, cout, residual):
+        """conv2-bn2-ReLU-conv3-bn3, += residual, ReLU of Bottleneck `name` (hrnet.py:88-99) on conv1's output y1"""
+        sd = self.sd
+        packed = []
+        for cv, bn, ci, co, k in ((name + '.conv2', name + '.bn2', planes, planes, 3), (name + '.conv3', name + '.bn3', planes, cout, 1)):
+            w = sd[cv + '.weight'].cpu()
+            assert tuple(w.shape) == (co, ci, k, k) and sd.get(cv + '.bias') is None, cv
+            wf, bf = fold_bn(w, None, tuple(sd[bn + s_].cpu() for s_ in ('.weight', '.bias', '.running_mean', '.running_var')))
+            packed += [pack_conv_weight(wf).to(self.device), bf.contiguous().to(self.device)]
+        self.keep += packed
+        out = self.act(cout, y1.H, y1.W)
+        assert (residual.C, residual.H, residual.W) == (cout, y1.H, y1.W) and residual.ptr != out.ptr
+        d = L.BottleneckTail(y1.desc(), out.desc(), residual.ptr, residual.plane_stride, packed[0].data_ptr(), packed[1].data_ptr(),
+                             packed[2].data_ptr(), packed[3].data_ptr(), self._share(), 0)
+        self.add(d)
+        self.conv_log.append((name + '.conv2', planes, planes, 3, 1, y1.H, y1.H))
+        self.conv_log.append((name + '.conv3', planes, cout, 1, 1, y1.H, y1.H))
+        return out
+
     # -- conv chains: consecutive same-geometry convs (the BasicBlocks of an HRNet branch) as ONE launch
     def begin_chain(self):
         assert self.chain is None

@@ -209,8 +209,20 @@ def _op19(self, d):         # fused BasicBlock: conv1 -> fp16 intermediate -> co
     self.act_set(o, F.relu(F.conv2d(mid, ws[1], bs[1], padding=1) + x))
 
 
+def _op20(self, d):         # fused Bottleneck tail: conv2 3x3 -> fp16 intermediate -> conv3 1x1 + residual
+    i, o = d.in_, d.out
+    cm, co = i.C, o.C
+    w2 = self.flat(d.weight2, torch.float16)[:9 * cm * cm].view(9, cm // 8, cm, 8).float().permute(2, 1, 3, 0).reshape(cm, cm, 3, 3)
+    w3 = self.flat(d.weight3, torch.float16)[:cm * co].view(1, cm // 8, co, 8).float().permute(2, 1, 3, 0).reshape(co, cm, 1, 1)
+    b2, b3 = self.flat(d.bias2, torch.float32)[:cm], self.flat(d.bias3, torch.float32)[:co]
+    mid = F.relu(F.conv2d(self.act_get(i), w2, b2, padding=1)).half().float()
+    r = L.Act(d.residual, d.res_plane_stride, co, o.N, o.H, o.W, None)
+    self.act_set(o, F.relu(F.conv2d(mid, w3, b3) + self.act_get(r)))
+
+
 Emu._op15 = _op15
 Emu._op19 = _op19
+Emu._op20 = _op20
 Emu._op13 = lambda self, d: None      # fork / join of plan lanes: the interpreter is sequential
 Emu._op14 = lambda self, d: None
 

@@ -106,3 +106,23 @@ def run_basic_block(x, w1, b1, w2, b2, max_ctas=0):
     assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
                  halo[:, :, :, -1].abs().sum()) == 0.0, 'kernel wrote into the zero halo'
     return engine.from_planar(o).cpu()
+
+
+def run_bottleneck_tail(x, w2, b2, w3, b3, residual, max_ctas=0):
+    """fused Bottleneck tail (poco_bottleneck_tail): x [N,64,H,W], w2 [64,64,3,3], w3 [256,64,1,1] (BN folded),
+    residual [N,256,H,W] -> [N,256,H,W] float (CPU)"""
+    dev = 'cuda'
+    N, Cm, H, W = x.shape
+    Co = w3.shape[0]
+    a = engine.to_planar(x.to(dev))
+    r = engine.to_planar(residual.to(dev))
+    o = engine.alloc_act(Co, N, H, W, dev)
+    p2, p3 = engine.pack_conv_weight(w2.to(dev).float()), engine.pack_conv_weight(w3.to(dev).float())
+    c2, c3 = b2.to(dev).float().contiguous(), b3.to(dev).float().contiguous()
+    d = L.BottleneckTail(a.desc(), o.desc(), r.ptr, r.plane_stride, p2.data_ptr(), c2.data_ptr(), p3.data_ptr(), c3.data_ptr(), max_ctas, 0)
+    L.run_op(d, stream())
+    sync_or_die()
+    halo = engine.act_view(o)
+    assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
+                 halo[:, :, :, -1].abs().sum()) == 0.0, 'kernel wrote into the zero halo'
+    return engine.from_planar(o).cpu()

@@ -585,3 +585,25 @@ def test_basic_block_rejects_what_it_cannot_fuse():
     d = L.BasicBlock(a32.desc(), a32.desc(), w.data_ptr(), b.data_ptr(), w.data_ptr(), b.data_ptr(), 0, 0)
     with pytest.raises(L.PocoError):        # in-place
         L.run_op(d, stream())
+
+
+@pytest.mark.parametrize('H,W,N,max_ctas', [(56, 56, 2, 0), (56, 56, 5, 7), (28, 28, 3, 0), (8, 12, 1, 0), (56, 56, 19, 0)])
+def test_bottleneck_tail_fused_matches_two_convs(H, W, N, max_ctas):
+    """poco_bottleneck_tail (3x3 conv -> shared memory -> 1x1 conv + residual, one launch; hrnet.py:88-99) against the
+    two poco_conv launches it replaces (same fp16 rounding of the intermediate; the 1x1 conv accumulates its four K steps
+    in the same order, the 3x3 in the one-CTA flavour's order) and against fp32 arithmetic on the fp16-rounded operands."""
+    from gpu_util import run_bottleneck_tail
+    assert L.lib().poco_bottleneck_tail_supported(64, 256, H, W) == 1
+    g = torch.Generator().manual_seed(H * 100 + N)
+    x = torch.randn(N, 64, H, W, generator=g)
+    res = torch.randn(N, 256, H, W, generator=g)
+    w2 = torch.randn(64, 64, 3, 3, generator=g) * 0.06
+    w3 = torch.randn(256, 64, 1, 1, generator=g) * 0.15
+    b2, b3 = torch.randn(64, generator=g) * 0.2, torch.randn(256, generator=g) * 0.2
+    got = run_bottleneck_tail(x, w2, b2, w3, b3, res, max_ctas)
+    mid = run_conv(x, w2, b2, relu=1, max_ctas=148)
+    two = run_conv(mid, w3, b3, relu=1, residual=res, max_ctas=148)
+    ref_mid = conv_reference(x, w2, b2, relu=1).half().float()
+    ref = conv_reference(ref_mid, w3, b3, relu=1, residual=res)
+    assert rel_err(got, ref) < CONV_TOL
+    assert rel_err(got, two) < 2e-3 and float((got != two).float().mean()) < 0.01, float((got != two).float().mean())
