@@ -12,6 +12,14 @@
 // 3x3 conv's MMAs (9 taps x 4 K steps, N = 64), warp 2 the 1x1 conv's (4 K steps per N = 128 half), warps 3-10
 // epilogue: two sets of four TMEM lane groups; set s owns columns [32 s, 32 s + 32) of the first accumulator and
 // half s of the second.  TMEM: 2 x 64 + 2 x 128 columns.  The kernel is bound by its 822 MB of output + residual traffic.
+//
+// Measured while tuning (batch 256, 45.5 tiles per CTA, clock64 laps inside the epilogue warps, tools/btail_bench.py of the
+// time): a tile takes ~8200 cycles whatever the role layout -- 218 us per launch = 4.2 TB/s of algorithmic traffic, DRAM
+// 51 % busy (ncu).  Not kept: requesting tile j + 1's residual rows while tile j is written (231 us); ONE issuer warp in
+// the order S2(j), S1(j + 2) (238 us); four issuer warps taking turns so that no single SM sub-partition hosts every
+// tcgen05.mma (231 us).  That last experiment did show that the epilogue warps which share a sub-partition with the
+// issuing warp are the slow ones (5700 against 3800 cycles of epilogue 2 per tile, and the slow lane group moves with
+// the issuer warp): their tcgen05.ld queue behind the MMA batches issued next to them.
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -221,37 +229,35 @@ __global__ void __launch_bounds__(kThreads, 1) bottleneck_tail_kernel(const Tail
                 mbar_arrive(smem_u32(&hdr->mid_full[b]));
             }
         };
-        // The residual rows (16 planes x 16 B per lane) of tile j + 1 are requested while tile j is being written: each
-        // register is reloaded right after its value has been consumed, so the L2 / HBM latency runs under the rest of
-        // this tile's epilogue and the next tile's first epilogue instead of in front of every tile (it cost ~1 us of
-        // the 4.8 us a tile took when the loads were issued at the top of epilogue 2).
-        uint4 res[16];
         auto res_ptr = [&](long long q, int pl) {
             return reinterpret_cast<const uint4*>(p.res + ((long long)(set * 16 + pl) * p.res_plane + q) * 8);
         };
         const long long q_first = (long long)blockIdx.x * kTile + row;
-        {
-            const bool k0 = my_units > 0 && interior_of(q_first);
-#pragma unroll
-            for (int pl = 0; pl < 16; ++pl) res[pl] = k0 ? __ldg(res_ptr(q_first, pl)) : make_uint4(0, 0, 0, 0);
-        }
         auto epilogue2 = [&](int j) {                   // this warp: output channels [128 set, 128 set + 128) of its 32 rows
             const uint32_t upar = uint32_t(j) & 1u;
             const long long q = q_first + (long long)j * gridDim.x * kTile;
-            const long long qn = q + (long long)gridDim.x * kTile;         // this CTA's next tile
             const bool keep = interior_of(q);
-            const bool keep_next = j + 1 < my_units && interior_of(qn);
+            // the residual rows of all 16 planes are requested before the wait: they arrive under the MMAs
+            uint4 res[16];
+#pragma unroll
+            for (int pl = 0; pl < 16; ++pl) res[pl] = keep ? __ldg(res_ptr(q, pl)) : make_uint4(0, 0, 0, 0);
             MBAR_WAIT(smem_u32(&hdr->acc2_full[set]), upar);
             tc_fence_after();
             __half* outp = p.out + ((long long)(set * 16) * p.out_plane + q) * 8;
+            // accumulator columns 32 at a time (4 output planes); the TMEM load of the next 32 is in flight during the math
+            uint32_t va[32], vb[32];
+            const uint32_t taddr0 = tmem_base + acc2_col(uint32_t(set)) + lane_sel;
+            tmem_ld16(taddr0, va);
+            tmem_ld16(taddr0 + 16, va + 16);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {               // 32 accumulator columns = 4 output planes at a time
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + acc2_col(uint32_t(set)) + uint32_t(c * 32) + lane_sel;
-                tmem_ld16(taddr, v);
-                tmem_ld16(taddr + 16, v + 16);
+            for (int c = 0; c < 4; ++c) {
+                uint32_t* v = (c & 1) ? vb : va;
+                uint32_t* vn = (c & 1) ? va : vb;
                 tmem_ld_wait();
-                if (c == 3) {                           // the accumulator half is drained: the next tile's MMAs may overwrite it
+                if (c < 3) {
+                    tmem_ld16(taddr0 + uint32_t((c + 1) * 32), vn);
+                    tmem_ld16(taddr0 + uint32_t((c + 1) * 32 + 16), vn + 16);
+                } else {                // the accumulator half is drained: the next tile's MMAs may overwrite it
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&hdr->acc2_free[set]));
@@ -259,7 +265,6 @@ __global__ void __launch_bounds__(kThreads, 1) bottleneck_tail_kernel(const Tail
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl) {
                     const uint4 r4 = res[c * 4 + pl];
-                    res[c * 4 + pl] = keep_next ? __ldg(res_ptr(qn, c * 4 + pl)) : make_uint4(0, 0, 0, 0);
                     const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
                     const float* bs = hdr->bias3 + set * 128 + c * 32 + pl * 8;
                     float f[8];

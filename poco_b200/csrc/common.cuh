@@ -94,6 +94,27 @@ __device__ __forceinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, int
     }
 }
 
+// Wait of a role that shares its SM sub-partition with busy warps (producer / MMA-issuer warps next to epilogue
+// warps): try_wait with a suspend-time hint parks the warp in hardware until the phase completes (or the hint expires)
+// instead of spinning through the issue slots of its neighbours.
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    unsigned long long t0 = 0;
+    while (!ok) {
+        if ((++spins & 1023u) == 0u) {          // (an iteration parks for up to 20 us: this is seconds of waiting)
+            if (t0 == 0) t0 = global_timer_ns();
+            spin_timeout(-1, t0);
+        }
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(20000u)
+            : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // async copies
 // ---------------------------------------------------------------------------------------------
