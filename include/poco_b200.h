@@ -95,7 +95,8 @@ typedef struct poco_conv_chain {
  * The intermediate tensor never leaves the SM: a work unit computes the conv1 tiles that cover its conv2
  * tiles plus their (W+3)-pixel reach (halo recompute), the first epilogue writes them as fp16 into shared
  * memory in the operand layout, and conv2's MMAs read them there; the block input is the residual.
- * C = 32, W + 3 <= 64, fp16 mode only (in.lo == out.lo == NULL); `in` and `out` must not alias.
+ * C = 32 or 64 with W + 3 <= 64 (poco_basic_block_supported), fp16 mode only (in.lo == out.lo == NULL); `in` and
+ * `out` must not alias.
  * weight1 / weight2: poco_conv weight format 0 with the BN scale folded, bias1 / bias2: the BN shifts. */
 typedef struct poco_basic_block {
     poco_act in;

@@ -1,7 +1,7 @@
 // poco_b200 -- one residual BasicBlock as ONE tcgen05 launch (sm_100a):
 //     out = ReLU(BN2(conv2(ReLU(BN1(conv1(in))))) + in)          (hrnet.py:42-58, downsample is None)
-// for the 32-channel, 56x56 branch of the HRNet modules (hrnet.py:140-186): 64 of the 311 conv launches of a
-// POCO-CLIFF / HRNet-W32 forward.  As two poco_conv launches a block pays the fixed launch gap + pipeline fill twice,
+// for the 32-channel 56x56 and the 64-channel 28x28 branches of the HRNet modules (hrnet.py:140-186): 128 of the 311
+// conv launches of a POCO-CLIFF / HRNet-W32 forward.  (Described for C = 32; the 64-channel flavour is at the end.)  As two poco_conv launches a block pays the fixed launch gap + pipeline fill twice,
 // writes the intermediate tensor to HBM, reads it back with a second halo, and reads the block input a second time as
 // the residual (257 MB of HBM traffic per block at batch 256).  Here the intermediate never leaves the SM:
 //
@@ -25,6 +25,13 @@
 // mbarriers, each a two-deep ring over the local unit index j (buffer j & 1, use j >> 1):
 //   in_full / in_free (producer <-> C1), acc1_full / acc1_free (C1 <-> epilogue 1), mid_full / mid_free
 //   (epilogue 1 <-> C2), acc2_full / acc2_free (C2 <-> epilogue 2).
+//
+// C = 64 (template flavour <64, 1, 1>): both weight tensors take 144 KB, so a unit is ONE conv2 tile (G = 1, two conv1
+// tiles: 1.5x the MMAs of the two-launch block) and the input run and the intermediate have ONE shared-memory buffer each
+// (the accumulators stay double buffered).  The tensor pipe then idles only while epilogue 1 runs between C1(u) and
+// C2(u): the next input run lands under C2(u), C1(u + 1) follows C2(u) directly.  Measured at batch 256, 28x28: 61.8 us
+// against 58.7 us for the two launches (6400-6700 cycles per unit for 5184 cycles of MMAs; even at the pipe's rate the
+// recompute leaves ~5 us), so the plan does not use this flavour by default (POCO_B200_FUSE_BLOCK64=1).
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -47,18 +54,24 @@ int sm_count() {
     return n;
 }
 
-constexpr int kC = 32;                  // channels (= N of every MMA)
-constexpr int kPlanes = kC / 8;
-constexpr int kG = 3;                   // conv2 tiles per unit
-constexpr int kT1 = kG + 1;             // conv1 tiles per unit
 constexpr int kTile = 128;
 constexpr int kLead = 64;               // conv1 starts this many pixels before the unit's first output pixel (>= W + 3)
-constexpr int kSlab = kC * 16;          // one (tap, 8-channel) weight slab: 32 output channels x 16 B
-constexpr int kWBytes = 9 * kPlanes * kSlab;        // one conv's weights: 18 KB
-constexpr int kMidPitch = kT1 * kTile * 16;         // one plane of the intermediate: 8 KB
 constexpr int kHeader = 1024;
-constexpr int kThreads = 352;          // producer, two issuers, eight epilogue warps
-constexpr int kTmemCols = 512;          // 2 x (4 + 3) x 32 = 448 used
+constexpr int kThreads = 352;           // producer, two issuers, eight epilogue warps
+constexpr int kTmemCols = 512;
+
+// C channels (= N of every MMA), G conv2 tiles per unit (G + 1 conv1 tiles), NBUF shared-memory buffers for the input
+// run and for the intermediate
+template <int C, int G, int NBUF>
+struct Cfg {
+    static constexpr int kPlanes = C / 8;
+    static constexpr int kT1 = G + 1;
+    static constexpr int kSlab = C * 16;                    // one (tap, 8-channel) weight slab: C output channels x 16 B
+    static constexpr int kWBytes = 9 * kPlanes * kSlab;     // one conv's weights
+    static constexpr int kMidPitch = kT1 * kTile * 16;      // one plane of the intermediate
+    static constexpr int kChunks = C / 32;                  // epilogue work items (32 accumulator columns) per tile
+    static_assert(2 * (kT1 + G) * C <= kTmemCols, "accumulators do not fit in TMEM");
+};
 
 struct BlockParams {
     const __half* in;
@@ -72,7 +85,7 @@ struct BlockParams {
     int P;                              // N * (H + 2) * (W + 2)
     int num_units;
     int in_pitch;                       // bytes between the planes of an input run in shared memory
-    int run_bytes;                      // bytes of one input run: (4 * 128 + 2 R) * 16
+    int run_bytes;                      // bytes of one input run: ((G + 1) * 128 + 2 R) * 16
     unsigned long long* prof;           // bring-up (POCO_BBLOCK_PROF): per issuer [total, in_full, acc1_free, mid_full, acc2_free, issue, units, ctas]
 };
 
@@ -81,23 +94,31 @@ struct Header {
     unsigned long long w_full;
     uint32_t tmem_base;
     uint32_t pad_;
-    float bias[2][kC];
+    float bias[2][64];
 };
 static_assert(sizeof(Header) <= kHeader, "header too large");
 
+template <int C, int G, int NBUF>
 __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockParams p) {
+    using K = Cfg<C, G, NBUF>;
+    constexpr int kPlanes = K::kPlanes, kT1 = K::kT1, kWBytes = K::kWBytes, kMidPitch = K::kMidPitch, kChunks = K::kChunks;
     extern __shared__ __align__(1024) uint8_t smem[];
     Header* hdr = reinterpret_cast<Header*>(smem);
-    uint8_t* w_smem = smem + kHeader;                               // [conv][tap][plane][32][8]
-    uint8_t* in_smem = w_smem + 2 * kWBytes;                        // [2][plane][run]
+    uint8_t* w_smem = smem + kHeader;                               // [conv][tap][plane][C][8]
+    uint8_t* in_smem = w_smem + 2 * kWBytes;                        // [NBUF][plane][run]
     const int in_buf_bytes = kPlanes * p.in_pitch;
-    uint8_t* mid_smem = in_smem + 2 * in_buf_bytes;                 // [2][plane][512 pixels]
+    uint8_t* mid_smem = in_smem + NBUF * in_buf_bytes;              // [NBUF][plane][(G + 1) * 128 pixels]
     constexpr int mid_buf_bytes = kPlanes * kMidPitch;
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int Wp = p.W + 2, HpWp = (p.H + 2) * Wp, R = Wp + 1;
     const int my_units = (p.num_units - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+    // ring positions of this CTA's j-th unit: shared-memory buffers (NBUF deep) and accumulators (two deep)
+    auto sbuf = [](int j) { return NBUF == 2 ? uint32_t(j) & 1u : 0u; };
+    auto spar = [](int j) { return (NBUF == 2 ? uint32_t(j) >> 1 : uint32_t(j)) & 1u; };
+    auto abuf = [](int j) { return uint32_t(j) & 1u; };
+    auto apar = [](int j) { return (uint32_t(j) >> 1) & 1u; };
 
     if (threadIdx.x < 16) {
         unsigned long long* bars = hdr->in_full;                    // the sixteen ring barriers are contiguous
@@ -106,9 +127,9 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
         mbar_init(smem_u32(bars + threadIdx.x), count);
     }
     if (threadIdx.x == 16) mbar_init(smem_u32(&hdr->w_full), 1);
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * kC) {
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * C) {
         const int i = threadIdx.x - 64;
-        hdr->bias[i / kC][i % kC] = (i < kC ? p.b1 : p.b2)[i % kC];
+        hdr->bias[i / C][i % C] = (i < C ? p.b1 : p.b2)[i % C];
     }
     mbar_fence_init();
     if (warp == 1) tmem_alloc(smem_u32(&hdr->tmem_base), kTmemCols);
@@ -116,8 +137,8 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
-    auto acc1_col = [&](uint32_t b, int t) { return (b * kT1 + uint32_t(t)) * uint32_t(kC); };
-    auto acc2_col = [&](uint32_t b, int g) { return (2u * kT1 + b * kG + uint32_t(g)) * uint32_t(kC); };
+    auto acc1_col = [&](uint32_t b, int t) { return (b * kT1 + uint32_t(t)) * uint32_t(C); };
+    auto acc2_col = [&](uint32_t b, int g) { return (2u * kT1 + b * G + uint32_t(g)) * uint32_t(C); };
 
     if (warp == 0) {
         // ============================================================ producer
@@ -129,13 +150,13 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
         }
         __syncwarp();
         for (int j = 0; j < my_units; ++j) {
-            const uint32_t b = uint32_t(j) & 1u, par = (uint32_t(j) >> 1) & 1u;
+            const uint32_t b = sbuf(j), par = spar(j);
             const long long unit = (long long)blockIdx.x + (long long)j * gridDim.x;
-            MBAR_WAIT(smem_u32(&hdr->in_free[b]), par ^ 1u);        // C1 of the unit two back has retired
+            MBAR_WAIT(smem_u32(&hdr->in_free[b]), par ^ 1u);        // C1 of the unit that last used this buffer has retired
             if (elect_one()) {
                 const uint32_t bar = smem_u32(&hdr->in_full[b]);
                 mbar_arrive_expect_tx(bar, uint32_t(kPlanes) * uint32_t(p.run_bytes));
-                const long long q0 = unit * (kG * kTile) - kLead - R;       // (>= -8 KB guard, see the launcher)
+                const long long q0 = unit * (G * kTile) - kLead - R;        // (>= -8 KB guard, see the launcher)
                 const __half* src = p.in + q0 * 8;
                 const uint32_t dst = smem_u32(in_smem) + b * uint32_t(in_buf_bytes);
                 for (int pl = 0; pl < kPlanes; ++pl, src += p.in_plane * 8)
@@ -145,11 +166,11 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
         }
     } else if (warp <= 2) {
         // ============================================================ MMA issuers: warp 1 conv1, warp 2 conv2
-        const uint32_t idesc = umma_idesc_f16(kTile, kC);
+        const uint32_t idesc = umma_idesc_f16(kTile, C);
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);
         const uint32_t in_lbo = (uint32_t(p.in_pitch) >> 4) << 16, in_kstep = (2u * uint32_t(p.in_pitch)) >> 4;
         constexpr uint32_t mid_lbo = (uint32_t(kMidPitch) >> 4) << 16, mid_kstep = (2u * uint32_t(kMidPitch)) >> 4;
-        constexpr uint32_t b_lbo = (uint32_t(kSlab) >> 4) << 16, b_kstep = (2u * kSlab) >> 4, b_tap = (uint32_t(kPlanes) * kSlab) >> 4;
+        constexpr uint32_t b_lbo = (uint32_t(K::kSlab) >> 4) << 16, b_kstep = (2u * K::kSlab) >> 4, b_tap = (uint32_t(kPlanes) * K::kSlab) >> 4;
         uint32_t sh[9];
 #pragma unroll
         for (int t = 0; t < 9; ++t) sh[t] = uint32_t((t / 3 - 1) * Wp + (t % 3 - 1));
@@ -160,39 +181,39 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
         const long long pt_t0 = pt_mark;
         auto lap = [&](int k) { if (prof) { const long long t = clock64(); pt[k] += t - pt_mark; pt_mark = t; } };
         auto conv1 = [&](int j) {
-            const uint32_t b = uint32_t(j) & 1u, par = (uint32_t(j) >> 1) & 1u;
-            MBAR_WAIT(smem_u32(&hdr->in_full[b]), par);
+            const uint32_t sb = sbuf(j), ab = abuf(j);
+            MBAR_WAIT(smem_u32(&hdr->in_full[sb]), spar(j));
             lap(0);
-            MBAR_WAIT(smem_u32(&hdr->acc1_free[b]), par ^ 1u);
+            MBAR_WAIT(smem_u32(&hdr->acc1_free[ab]), apar(j) ^ 1u);
             lap(1);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t a0 = smem_u32(in_smem) + b * uint32_t(in_buf_bytes) + uint32_t(R) * 16u;
+                const uint32_t a0 = smem_u32(in_smem) + sb * uint32_t(in_buf_bytes) + uint32_t(R) * 16u;
 #pragma unroll
                 for (int t = 0; t < kT1; ++t)
-                    issue_linear<9, 2>(tmem_base + acc1_col(b, t), ((a0 + uint32_t(t) * (kTile * 16u)) >> 4) | in_lbo, w1_lo, sh,
-                                       in_kstep, b_kstep, b_tap, desc_hi, idesc, 0u);
-                umma_commit(smem_u32(&hdr->acc1_full[b]));
-                umma_commit(smem_u32(&hdr->in_free[b]));
+                    issue_linear<9, C / 16>(tmem_base + acc1_col(ab, t), ((a0 + uint32_t(t) * (kTile * 16u)) >> 4) | in_lbo, w1_lo, sh,
+                                            in_kstep, b_kstep, b_tap, desc_hi, idesc, 0u);
+                umma_commit(smem_u32(&hdr->acc1_full[ab]));
+                umma_commit(smem_u32(&hdr->in_free[sb]));
             }
             __syncwarp();
             lap(4);
         };
         auto conv2 = [&](int j) {
-            const uint32_t b = uint32_t(j) & 1u, par = (uint32_t(j) >> 1) & 1u;
-            MBAR_WAIT(smem_u32(&hdr->mid_full[b]), par);
+            const uint32_t sb = sbuf(j), ab = abuf(j);
+            MBAR_WAIT(smem_u32(&hdr->mid_full[sb]), spar(j));
             lap(2);
-            MBAR_WAIT(smem_u32(&hdr->acc2_free[b]), par ^ 1u);
+            MBAR_WAIT(smem_u32(&hdr->acc2_free[ab]), apar(j) ^ 1u);
             lap(3);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t a0 = smem_u32(mid_smem) + b * uint32_t(mid_buf_bytes) + uint32_t(kLead) * 16u;
+                const uint32_t a0 = smem_u32(mid_smem) + sb * uint32_t(mid_buf_bytes) + uint32_t(kLead) * 16u;
 #pragma unroll
-                for (int g = 0; g < kG; ++g)
-                    issue_linear<9, 2>(tmem_base + acc2_col(b, g), ((a0 + uint32_t(g) * (kTile * 16u)) >> 4) | mid_lbo, w2_lo, sh,
-                                       mid_kstep, b_kstep, b_tap, desc_hi, idesc, 0u);
-                umma_commit(smem_u32(&hdr->acc2_full[b]));
-                umma_commit(smem_u32(&hdr->mid_free[b]));
+                for (int g = 0; g < G; ++g)
+                    issue_linear<9, C / 16>(tmem_base + acc2_col(ab, g), ((a0 + uint32_t(g) * (kTile * 16u)) >> 4) | mid_lbo, w2_lo, sh,
+                                            mid_kstep, b_kstep, b_tap, desc_hi, idesc, 0u);
+                umma_commit(smem_u32(&hdr->acc2_full[ab]));
+                umma_commit(smem_u32(&hdr->mid_free[sb]));
             }
             __syncwarp();
             lap(4);
@@ -213,8 +234,9 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
         }
     } else {
         // ============================================================ epilogue (8 warps)
+        // Work item = 32 accumulator columns (4 planes) of one tile; the items of a unit are dealt alternately to the two sets.
         const int ew = warp - 3;
-        const int set = ew >> 2;                        // tiles alternate between the two sets
+        const int set = ew >> 2;
         const int lg = warp & 3;                        // TMEM lane group this warp may access
         const int row = lg * 32 + lane;
         const uint32_t lane_sel = uint32_t(lg * 32) << 16;
@@ -225,26 +247,28 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
             return q >= 0 && q < p.P && yy >= 1u && yy <= uint32_t(p.H) && xx >= 1u && xx <= uint32_t(p.W);
         };
         auto epilogue1 = [&](int j) {
-            const uint32_t b = uint32_t(j) & 1u, par = (uint32_t(j) >> 1) & 1u;
+            const uint32_t sb = sbuf(j), ab = abuf(j);
             const long long unit = (long long)blockIdx.x + (long long)j * gridDim.x;
-            const long long qm = unit * (kG * kTile) - kLead;               // pixel of row 0 of conv1 tile 0
-            MBAR_WAIT(smem_u32(&hdr->acc1_full[b]), par);
-            MBAR_WAIT(smem_u32(&hdr->mid_free[b]), par ^ 1u);               // C2 of the unit two back no longer reads the buffer
+            const long long qm = unit * (G * kTile) - kLead;                // pixel of row 0 of conv1 tile 0
+            MBAR_WAIT(smem_u32(&hdr->acc1_full[ab]), apar(j));
+            MBAR_WAIT(smem_u32(&hdr->mid_free[sb]), spar(j) ^ 1u);          // C2 of the unit that last read this buffer has retired
             tc_fence_after();
-            uint8_t* mid = mid_smem + b * mid_buf_bytes;
-            for (int t = set; t < kT1; t += 2) {
-                uint32_t v[kC];
-                const uint32_t taddr = tmem_base + acc1_col(b, t) + lane_sel;
+            uint8_t* mid = mid_smem + sb * mid_buf_bytes;
+            for (int it = set; it < kT1 * kChunks; it += 2) {
+                const int t = it / kChunks, ch = it % kChunks;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + acc1_col(ab, t) + uint32_t(ch * 32) + lane_sel;
                 tmem_ld16(taddr, v);
                 tmem_ld16(taddr + 16, v + 16);
                 const bool keep = interior_of(qm + t * kTile + row);
                 tmem_ld_wait();
-                uint8_t* dst = mid + (t * kTile + row) * 16;
+                uint8_t* dst = mid + (ch * 4) * kMidPitch + (t * kTile + row) * 16;
+                const float* bs = hdr->bias[0] + ch * 32;
 #pragma unroll
-                for (int pl = 0; pl < kPlanes; ++pl) {
+                for (int pl = 0; pl < 4; ++pl) {
                     float f[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = keep ? fmaxf(__uint_as_float(v[pl * 8 + i]) + hdr->bias[0][pl * 8 + i], 0.f) : 0.f;
+                    for (int i = 0; i < 8; ++i) f[i] = keep ? fmaxf(__uint_as_float(v[pl * 8 + i]) + bs[pl * 8 + i], 0.f) : 0.f;
                     uint4 o4;
                     o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
                     o4.z = pack_half2(f[4], f[5]); o4.w = pack_half2(f[6], f[7]);
@@ -255,48 +279,50 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
             fence_proxy_async_smem();               // these generic-proxy stores are read by tcgen05.mma (async proxy)
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(smem_u32(&hdr->acc1_free[b]));
-                mbar_arrive(smem_u32(&hdr->mid_full[b]));
+                mbar_arrive(smem_u32(&hdr->acc1_free[ab]));
+                mbar_arrive(smem_u32(&hdr->mid_full[sb]));
             }
         };
         auto epilogue2 = [&](int j) {
-            const uint32_t b = uint32_t(j) & 1u, par = (uint32_t(j) >> 1) & 1u;
+            const uint32_t ab = abuf(j);
             const long long unit = (long long)blockIdx.x + (long long)j * gridDim.x;
-            const long long q0 = unit * (kG * kTile) + row;
-            const int g0 = (set + j) & 1;                                   // the set with two tiles alternates per unit
+            const long long q0 = unit * (G * kTile) + row;
+            constexpr int kItems = G * kChunks;                             // 3 (C = 32, G = 3) or 2 (C = 64, G = 1)
+            const int i0 = (kItems & 1) ? ((set + j) & 1) : set;            // an odd count: the set with the extra item alternates per unit
             // the residual = the block input at the output pixel: issued before the wait, it arrives under the MMAs
-            uint4 res[2][kPlanes];
+            uint4 res[2][4];
             bool keep[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const int g = g0 + 2 * k;
-                keep[k] = g < kG && interior_of(q0 + g * kTile);
+                const int it = i0 + 2 * k, g = it / kChunks, ch = it % kChunks;
+                keep[k] = it < kItems && interior_of(q0 + g * kTile);
 #pragma unroll
-                for (int pl = 0; pl < kPlanes; ++pl)
-                    res[k][pl] = keep[k] ? __ldg(reinterpret_cast<const uint4*>(p.in + ((long long)pl * p.in_plane + q0 + g * kTile) * 8))
+                for (int pl = 0; pl < 4; ++pl)
+                    res[k][pl] = keep[k] ? __ldg(reinterpret_cast<const uint4*>(p.in + ((long long)(ch * 4 + pl) * p.in_plane + q0 + g * kTile) * 8))
                                          : make_uint4(0, 0, 0, 0);
             }
-            MBAR_WAIT(smem_u32(&hdr->acc2_full[b]), par);
+            MBAR_WAIT(smem_u32(&hdr->acc2_full[ab]), apar(j));
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const int g = g0 + 2 * k;
-                if (g >= kG) break;
-                uint32_t v[kC];
-                const uint32_t taddr = tmem_base + acc2_col(b, g) + lane_sel;
+                const int it = i0 + 2 * k, g = it / kChunks, ch = it % kChunks;
+                if (it >= kItems) break;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + acc2_col(ab, g) + uint32_t(ch * 32) + lane_sel;
                 tmem_ld16(taddr, v);
                 tmem_ld16(taddr + 16, v + 16);
                 tmem_ld_wait();
-                __half* outp = p.out + (q0 + g * kTile) * 8;
+                __half* outp = p.out + ((long long)(ch * 4) * p.out_plane + q0 + g * kTile) * 8;
+                const float* bs = hdr->bias[1] + ch * 32;
 #pragma unroll
-                for (int pl = 0; pl < kPlanes; ++pl) {
+                for (int pl = 0; pl < 4; ++pl) {
                     const uint32_t rr[4] = {res[k][pl].x, res[k][pl].y, res[k][pl].z, res[k][pl].w};
                     float f[8];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float2 r2 = unpack_half2(rr[i]);
-                        f[2 * i] = fmaxf(__uint_as_float(v[pl * 8 + 2 * i]) + hdr->bias[1][pl * 8 + 2 * i] + r2.x, 0.f);
-                        f[2 * i + 1] = fmaxf(__uint_as_float(v[pl * 8 + 2 * i + 1]) + hdr->bias[1][pl * 8 + 2 * i + 1] + r2.y, 0.f);
+                        f[2 * i] = fmaxf(__uint_as_float(v[pl * 8 + 2 * i]) + bs[pl * 8 + 2 * i] + r2.x, 0.f);
+                        f[2 * i + 1] = fmaxf(__uint_as_float(v[pl * 8 + 2 * i + 1]) + bs[pl * 8 + 2 * i + 1] + r2.y, 0.f);
                     }
                     if (keep[k]) {
                         uint4 o4;
@@ -308,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&hdr->acc2_free[b]));
+            if (lane == 0) mbar_arrive(smem_u32(&hdr->acc2_free[ab]));
         };
         for (int j = 0; j < my_units; ++j) {
             epilogue1(j);
@@ -321,6 +347,24 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+template <int C, int G, int NBUF>
+int launch_block(const poco_basic_block* d, BlockParams p, cudaStream_t stream) {
+    using K = Cfg<C, G, NBUF>;
+    const int R = d->in.W + 3;
+    p.num_units = (p.P + G * kTile - 1) / (G * kTile);
+    p.run_bytes = (K::kT1 * kTile + 2 * R) * 16;
+    p.in_pitch = (p.run_bytes + 127) / 128 * 128;
+    const size_t smem = size_t(kHeader) + 2 * K::kWBytes + size_t(NBUF) * K::kPlanes * p.in_pitch + size_t(NBUF) * K::kPlanes * K::kMidPitch;
+    POCO_CHECK(smem <= 227 * 1024, "shared memory");
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(basic_block_kernel<C, G, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    const int budget = d->max_ctas > 0 ? std::min(d->max_ctas, sm_count()) : sm_count();
+    const int grid = std::max(1, std::min(p.num_units, budget));
+    basic_block_kernel<C, G, NBUF><<<grid, kThreads, smem, stream>>>(p);
+    POCO_LAUNCHED();
+    return 0;
+}
+
 }  // namespace
 
 }  // namespace poco
@@ -328,9 +372,16 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
 using namespace poco;
 
 extern "C" int poco_basic_block_supported(int32_t C, int32_t H, int32_t W) {
-    // (a unit's input run starts kLead + R pixels before its first output pixel and ends kT1 * 128 - kLead + R pixels after
-    // it, R = W + 3: both ends of the tensor must stay inside the activation guard)
-    return C == kC && H >= 1 && W >= 1 && W + 3 <= kLead && (kT1 * kTile - kLead + W + 3) * 16 <= POCO_ACT_GUARD_BYTES;
+    // A unit's input run starts kLead + R pixels before its first output pixel and ends (G + 1) * 128 - kLead + R pixels
+    // after it, R = W + 3: both ends of the tensor must stay inside the activation guard.  C = 64: the two weight tensors
+    // (144 KB) leave room for one input run and one intermediate of two tiles only if the rows are short.
+    if (H < 1 || W < 1 || W + 3 > kLead) return 0;
+    if (C == 32) return (4 * kTile - kLead + W + 3) * 16 <= POCO_ACT_GUARD_BYTES;
+    if (C == 64) {
+        const int in_pitch = ((2 * kTile + 2 * (W + 3)) * 16 + 127) / 128 * 128;
+        return kHeader + 2 * Cfg<64, 1, 1>::kWBytes + 8 * in_pitch + 8 * Cfg<64, 1, 1>::kMidPitch <= 227 * 1024;
+    }
+    return 0;
 }
 
 extern "C" int poco_basic_block_run(const poco_basic_block* d, void* stream) {
@@ -338,13 +389,12 @@ extern "C" int poco_basic_block_run(const poco_basic_block* d, void* stream) {
     if (check_act(d->in, "in") || check_act(d->out, "out")) return 1;
     const poco_act &in = d->in, &out = d->out;
     POCO_CHECK(in.C == out.C && in.N == out.N && in.H == out.H && in.W == out.W, "basic block: in and out must share one geometry");
-    POCO_CHECK(poco_basic_block_supported(in.C, in.H, in.W), "basic block: only 32 channels with W + 3 <= 64 run fused");
+    POCO_CHECK(poco_basic_block_supported(in.C, in.H, in.W), "basic block: only 32 channels (W + 3 <= 64) or 64 channels (short rows) run fused");
     POCO_CHECK(in.lo == nullptr && out.lo == nullptr, "basic block: fp16 mode only");
     POCO_CHECK(in.data != out.data, "basic block: in and out must not alias");
     POCO_CHECK(d->weight1 && d->weight2 && d->bias1 && d->bias2, "null weight / bias");
     const int64_t P = int64_t(in.N) * (in.H + 2) * (in.W + 2);
     POCO_CHECK(P + 4096 < (int64_t(1) << 31), "tensor too large");
-    const int R = in.W + 3;
     BlockParams p{};
     p.in = static_cast<const __half*>(in.data);
     p.out = static_cast<__half*>(out.data);
@@ -356,18 +406,8 @@ extern "C" int poco_basic_block_run(const poco_basic_block* d, void* stream) {
     p.out_plane = out.plane_stride;
     p.H = in.H; p.W = in.W;
     p.P = int(P);
-    p.num_units = int((P + kG * kTile - 1) / (kG * kTile));
-    p.run_bytes = (kT1 * kTile + 2 * R) * 16;
-    p.in_pitch = (p.run_bytes + 127) / 128 * 128;
     static const char* prof_env = getenv("POCO_BBLOCK_PROF");       // bring-up: device address (decimal) of 16 zeroed uint64 counters
     p.prof = prof_env ? reinterpret_cast<unsigned long long*>(strtoull(prof_env, nullptr, 10)) : nullptr;
-    const size_t smem = size_t(kHeader) + 2 * kWBytes + 2 * size_t(kPlanes) * p.in_pitch + 2 * size_t(kPlanes) * kMidPitch;
-    POCO_CHECK(smem <= 227 * 1024, "shared memory");
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(basic_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-    const int budget = d->max_ctas > 0 ? std::min(d->max_ctas, sm_count()) : sm_count();
-    const int grid = std::max(1, std::min(p.num_units, budget));
-    basic_block_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
-    POCO_LAUNCHED();
-    return 0;
+    if (in.C == 64) return launch_block<64, 1, 1>(d, p, static_cast<cudaStream_t>(stream));
+    return launch_block<32, 3, 2>(d, p, static_cast<cudaStream_t>(stream));
 }

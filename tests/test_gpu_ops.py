@@ -551,19 +551,22 @@ def test_phase_split_only_output_leaves_no_normal_tensor():
     assert rel_err(engine.from_planar(z).cpu().numpy(), engine.from_planar(z2).cpu().numpy()) < CONV_TOL
 
 
-@pytest.mark.parametrize('H,W,N,max_ctas', [(56, 56, 2, 0), (56, 56, 7, 5), (28, 28, 3, 0), (8, 12, 1, 0), (56, 56, 37, 0), (20, 61, 2, 3)])
-def test_basic_block_fused_matches_two_convs(H, W, N, max_ctas):
+@pytest.mark.parametrize('C,H,W,N,max_ctas', [(32, 56, 56, 2, 0), (32, 56, 56, 7, 5), (32, 28, 28, 3, 0), (32, 8, 12, 1, 0), (32, 56, 56, 37, 0),
+                                              (32, 20, 61, 2, 3), (64, 28, 28, 3, 0), (64, 28, 28, 9, 5), (64, 14, 20, 2, 0), (64, 56, 56, 2, 0),
+                                              (64, 28, 28, 40, 0)])
+def test_basic_block_fused_matches_two_convs(C, H, W, N, max_ctas):
     """poco_basic_block (conv1 -> shared memory -> conv2 + input as residual, one launch) against the same block as two
     poco_conv launches: bit-identical (same MMA order, same fp16 rounding of the intermediate; the two-launch block runs
     with a CTA budget so that it takes the one-CTA-per-SM flavour -- the two-CTA flavour walks K in 16-channel chunks,
     another summation order), and against fp32 arithmetic on the fp16-rounded operands (hrnet.py:42-58).  Cases: several units per CTA / one short unit, a CTA
-    budget (plan lanes), crops that straddle unit boundaries, the widest row the kernel takes (W + 3 = 64)."""
+    budget (plan lanes), crops that straddle unit boundaries, the widest row the kernel takes (W + 3 = 64); the
+    64-channel flavour (one conv2 tile per unit, single shared-memory buffers)."""
     from gpu_util import run_basic_block
-    assert L.lib().poco_basic_block_supported(32, H, W) == 1
+    assert L.lib().poco_basic_block_supported(C, H, W) == 1
     g = torch.Generator().manual_seed(H * 100 + N)
-    x = torch.randn(N, 32, H, W, generator=g)
-    w1, w2 = (torch.randn(32, 32, 3, 3, generator=g) * 0.08 for _ in range(2))
-    b1, b2 = (torch.randn(32, generator=g) * 0.2 for _ in range(2))
+    x = torch.randn(N, C, H, W, generator=g)
+    w1, w2 = (torch.randn(C, C, 3, 3, generator=g) * (0.08 if C == 32 else 0.06) for _ in range(2))
+    b1, b2 = (torch.randn(C, generator=g) * 0.2 for _ in range(2))
     got = run_basic_block(x, w1, b1, w2, b2, max_ctas)
     mid = run_conv(x, w1, b1, relu=1, max_ctas=148)
     two = run_conv(mid, w2, b2, relu=1, residual=x, max_ctas=148)
@@ -575,11 +578,12 @@ def test_basic_block_fused_matches_two_convs(H, W, N, max_ctas):
 
 def test_basic_block_rejects_what_it_cannot_fuse():
     lib = L.lib()
-    assert lib.poco_basic_block_supported(64, 28, 28) == 0 and lib.poco_basic_block_supported(32, 56, 62) == 0
-    a = engine.alloc_act(64, 1, 28, 28, 'cuda')
-    o = engine.alloc_act(64, 1, 28, 28, 'cuda')
-    w = torch.zeros(9 * 8 * 64 * 8, dtype=torch.float16, device='cuda')
-    b = torch.zeros(64, device='cuda')
+    assert lib.poco_basic_block_supported(128, 14, 14) == 0 and lib.poco_basic_block_supported(32, 56, 62) == 0
+    assert lib.poco_basic_block_supported(48, 56, 56) == 0 and lib.poco_basic_block_supported(64, 28, 62) == 0
+    a = engine.alloc_act(128, 1, 14, 14, 'cuda')
+    o = engine.alloc_act(128, 1, 14, 14, 'cuda')
+    w = torch.zeros(9 * 16 * 128 * 8, dtype=torch.float16, device='cuda')
+    b = torch.zeros(128, device='cuda')
     d = L.BasicBlock(a.desc(), o.desc(), w.data_ptr(), b.data_ptr(), w.data_ptr(), b.data_ptr(), 0, 0)
     with pytest.raises(L.PocoError):
         L.run_op(d, stream())

@@ -7,14 +7,16 @@ import torch
 from poco_b200 import _lib as L
 from poco_b200 import engine
 
-B, H = int(sys.argv[1]) if len(sys.argv) > 1 else 256, 56
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+CH = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+H = int(sys.argv[3]) if len(sys.argv) > 3 else (56 if CH == 32 else 28)
 dev = 'cuda'
 s = torch.cuda.current_stream().cuda_stream
-a = engine.alloc_act(32, B, H, H, dev)
+a = engine.alloc_act(CH, B, H, H, dev)
 engine.act_view(a)[:, :, 1:H + 1, 1:H + 1].normal_()
-m, o = engine.alloc_act(32, B, H, H, dev), engine.alloc_act(32, B, H, H, dev)
-w = [(torch.randn(9, 4, 32, 8, device=dev) * 0.05).half() for _ in range(2)]
-b = [torch.randn(32, device=dev) * 0.1 for _ in range(2)]
+m, o = engine.alloc_act(CH, B, H, H, dev), engine.alloc_act(CH, B, H, H, dev)
+w = [(torch.randn(9, CH // 8, CH, 8, device=dev) * 0.05).half() for _ in range(2)]
+b = [torch.randn(CH, device=dev) * 0.1 for _ in range(2)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 prof = torch.zeros(16, dtype=torch.int64, device=dev)
 if os.environ.get('BB_PROF') == '1':
@@ -46,7 +48,7 @@ for ctas in (0, 148, 74, 37):
         L.run_op(c2, s)
     t2 = timed(two)
     tf = timed(lambda: L.run_op(fused, s))
-    print(f'batch {B} max_ctas {ctas}: two launches {t2:.1f} us, fused {tf:.1f} us', flush=True)
+    print(f'{CH} ch {H}x{H} batch {B} max_ctas {ctas}: two launches {t2:.1f} us, fused {tf:.1f} us', flush=True)
     if os.environ.get('BB_PROF') == '1':
         prof.zero_()
         L.run_op(fused, s)
