@@ -128,6 +128,25 @@ typedef struct poco_bottleneck_tail {
     int32_t pad_;
 } poco_bottleneck_tail;
 
+/* The BasicBlocks of one low-resolution HRNet branch as ONE launch with the crop resident in shared memory
+ * (hrnet.py:42-58 x n_blocks inside HighResolutionModule._make_one_branch, hrnet.py:140-186):
+ *     x <- ReLU(BN2(conv2(ReLU(BN1(conv1(x))))) + x)   n_blocks times,   every conv 3x3 / stride 1 / pad 1, C -> C.
+ * A work unit is one crop: its padded image is at most two 128-pixel tiles and all C channels fit in shared memory, so
+ * the activations of all 2 * n_blocks convs never leave the SM (no halo recompute, no HBM hand-off between convs); only
+ * the weights stream out of L2.  C = 128 and (H + 2) * (W + 2) <= 256 (poco_branch_supported: the 14x14 branch of
+ * HRNet-W32), fp16 mode only (in.lo == out.lo == NULL); `out` may alias `in`.
+ * weight[2b] / weight[2b + 1]: conv1 / conv2 of block b in poco_conv weight format 0 with the BN scale folded,
+ * bias[...]: the BN shifts. */
+#define POCO_MAX_BRANCH_BLOCKS 4
+typedef struct poco_branch {
+    poco_act in;
+    poco_act out;
+    const void* weight[2 * POCO_MAX_BRANCH_BLOCKS];
+    const float* bias[2 * POCO_MAX_BRANCH_BLOCKS];
+    int32_t n_blocks;
+    int32_t max_ctas; /* like poco_conv.max_ctas: 0 = all SMs */
+} poco_branch;
+
 /* batch['img'] f32 NCHW [N,3,H,W] -> planar-8 fp16 with channels padded to 16 (poco.py:100 input) */
 typedef struct poco_pack_image {
     const float* img;
@@ -385,7 +404,8 @@ typedef enum poco_op_kind {
     POCO_OP_UNCERT_POST = 17,
     POCO_OP_SMPL = 18,
     POCO_OP_BASIC_BLOCK = 19,
-    POCO_OP_BOTTLENECK_TAIL = 20
+    POCO_OP_BOTTLENECK_TAIL = 20,
+    POCO_OP_BRANCH = 21
 } poco_op_kind;
 
 typedef struct poco_op {
@@ -397,6 +417,7 @@ typedef struct poco_op {
         poco_conv_chain conv_chain;
         poco_basic_block basic_block;
         poco_bottleneck_tail bottleneck_tail;
+        poco_branch branch;
         poco_fuse_sum fuse_sum;
         poco_upsample2x upsample2x;
         poco_maxpool maxpool;
@@ -430,6 +451,8 @@ int poco_basic_block_run(const poco_basic_block* d, void* stream);
 int poco_basic_block_supported(int32_t C, int32_t H, int32_t W); /* 1 iff poco_basic_block_run takes this geometry */
 int poco_bottleneck_tail_run(const poco_bottleneck_tail* d, void* stream);
 int poco_bottleneck_tail_supported(int32_t Cmid, int32_t Cout, int32_t H, int32_t W);
+int poco_branch_run(const poco_branch* d, void* stream);
+int poco_branch_supported(int32_t C, int32_t H, int32_t W, int32_t n_blocks); /* 1 iff poco_branch_run takes this geometry */
 int64_t poco_conv_chain_flag_count(const poco_conv_chain* d); /* int32 entries `flags` must hold */
 int poco_pack_image_run(const poco_pack_image* d, void* stream);
 int poco_fuse_sum_run(const poco_fuse_sum* d, void* stream);

@@ -14,8 +14,9 @@ ACT_GUARD_BYTES = 8192
 
 OP_PACK_IMAGE, OP_CONV, OP_FUSE_SUM, OP_UPSAMPLE2X, OP_MAXPOOL, OP_AVGPOOL, OP_UNPACK, OP_LINEAR, \
     OP_COPY2D, OP_ROT6D, OP_PARE_HEAD, OP_REALNVP, OP_FORK, OP_JOIN, OP_CONV_CHAIN, OP_CROP, OP_UNCERT_POST, OP_SMPL, \
-    OP_BASIC_BLOCK, OP_BOTTLENECK_TAIL = range(1, 21)
+    OP_BASIC_BLOCK, OP_BOTTLENECK_TAIL, OP_BRANCH = range(1, 22)
 MAX_CHAIN = 8
+MAX_BRANCH_BLOCKS = 4
 SMPL_JOINTS, SMPL_BETAS, SMPL_SCRATCH_FLOATS, SMPL_DIR_ROWS = 24, 10, 580, 224
 
 
@@ -46,6 +47,11 @@ class BottleneckTail(C.Structure):
     _fields_ = [('in_', Act), ('out', Act), ('residual', C.c_void_p), ('res_plane_stride', C.c_int64),
                 ('weight2', C.c_void_p), ('bias2', C.c_void_p), ('weight3', C.c_void_p), ('bias3', C.c_void_p),
                 ('max_ctas', C.c_int32), ('pad_', C.c_int32)]
+
+
+class Branch(C.Structure):
+    _fields_ = [('in_', Act), ('out', Act), ('weight', C.c_void_p * (2 * MAX_BRANCH_BLOCKS)),
+                ('bias', C.c_void_p * (2 * MAX_BRANCH_BLOCKS)), ('n_blocks', C.c_int32), ('max_ctas', C.c_int32)]
 
 
 class PackImage(C.Structure):
@@ -143,7 +149,7 @@ class Sync(C.Structure):
 
 class _OpU(C.Union):
     _fields_ = [('pack_image', PackImage), ('conv', Conv), ('conv_chain', ConvChain), ('basic_block', BasicBlock), ('bottleneck_tail', BottleneckTail),
-                ('fuse_sum', FuseSum), ('upsample2x', Upsample2x),
+                ('branch', Branch), ('fuse_sum', FuseSum), ('upsample2x', Upsample2x),
                 ('maxpool', MaxPool), ('avgpool', AvgPool), ('unpack', Unpack), ('linear', Linear),
                 ('copy2d', Copy2d), ('rot6d', Rot6d), ('pare_head', PareHead), ('realnvp', RealNVP), ('sync', Sync),
                 ('crop', Crop), ('uncert_post', UncertPost), ('smpl', Smpl)]
@@ -158,18 +164,18 @@ _FIELD_OF_KIND = {OP_PACK_IMAGE: 'pack_image', OP_CONV: 'conv', OP_FUSE_SUM: 'fu
                   OP_UNPACK: 'unpack', OP_LINEAR: 'linear', OP_COPY2D: 'copy2d', OP_ROT6D: 'rot6d',
                   OP_PARE_HEAD: 'pare_head', OP_REALNVP: 'realnvp', OP_FORK: 'sync', OP_JOIN: 'sync',
                   OP_CONV_CHAIN: 'conv_chain', OP_CROP: 'crop', OP_UNCERT_POST: 'uncert_post', OP_SMPL: 'smpl',
-                  OP_BASIC_BLOCK: 'basic_block', OP_BOTTLENECK_TAIL: 'bottleneck_tail'}
+                  OP_BASIC_BLOCK: 'basic_block', OP_BOTTLENECK_TAIL: 'bottleneck_tail', OP_BRANCH: 'branch'}
 _KIND_OF_TYPE = {PackImage: OP_PACK_IMAGE, Conv: OP_CONV, FuseSum: OP_FUSE_SUM, Upsample2x: OP_UPSAMPLE2X,
                  MaxPool: OP_MAXPOOL, AvgPool: OP_AVGPOOL, Unpack: OP_UNPACK, Linear: OP_LINEAR,
                  Copy2d: OP_COPY2D, Rot6d: OP_ROT6D, PareHead: OP_PARE_HEAD, RealNVP: OP_REALNVP,
                  ConvChain: OP_CONV_CHAIN, Crop: OP_CROP, UncertPost: OP_UNCERT_POST, Smpl: OP_SMPL,
-                 BasicBlock: OP_BASIC_BLOCK, BottleneckTail: OP_BOTTLENECK_TAIL}
+                 BasicBlock: OP_BASIC_BLOCK, BottleneckTail: OP_BOTTLENECK_TAIL, Branch: OP_BRANCH}
 
 # every symbol include/poco_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     'poco_version', 'poco_last_error', 'poco_device_check', 'poco_kernel_launches', 'poco_run_op',
     'poco_conv_run', 'poco_conv_chain_run', 'poco_conv_chain_flag_count', 'poco_basic_block_run', 'poco_basic_block_supported',
-    'poco_bottleneck_tail_run', 'poco_bottleneck_tail_supported', 'poco_pack_image_run', 'poco_fuse_sum_run', 'poco_upsample2x_run', 'poco_maxpool_run',
+    'poco_bottleneck_tail_run', 'poco_bottleneck_tail_supported', 'poco_branch_run', 'poco_branch_supported', 'poco_pack_image_run', 'poco_fuse_sum_run', 'poco_upsample2x_run', 'poco_maxpool_run',
     'poco_avgpool_run', 'poco_unpack_run', 'poco_linear_run', 'poco_copy2d_run', 'poco_rot6d_run',
     'poco_pare_head_run', 'poco_realnvp_run', 'poco_crop_run', 'poco_uncert_post_run', 'poco_smpl_run', 'poco_pare_scratch_floats',
     'poco_plan_create', 'poco_plan_run', 'poco_plan_num_ops', 'poco_plan_flops', 'poco_plan_destroy',
@@ -204,6 +210,8 @@ def lib():
             L.poco_basic_block_supported.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         if hasattr(L, 'poco_bottleneck_tail_supported'):
             L.poco_bottleneck_tail_supported.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        if hasattr(L, 'poco_branch_supported'):
+            L.poco_branch_supported.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.poco_run_op.argtypes = [C.POINTER(Op), C.c_void_p]
         L.poco_plan_create.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p)]
         L.poco_plan_run.argtypes = [C.c_void_p, C.c_void_p]

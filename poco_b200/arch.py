@@ -227,13 +227,29 @@ def hr_module(b, xs, name, chans, out0=None):
     SMs proportional to its work (the 14x14 / 7x7 branches cannot fill 148 SMs on their own)."""
     nb = len(xs)
     N = b.N
-    b.fork([8 * conv_cost(N, chans[i], chans[i], 3, xs[i].H, xs[i].W) for i in range(nb)])
+    import os
+    # The branch's eight convs share one geometry and CAN run as one persistent chained launch
+    # (POCO_B200_CHAIN_MIN_C, off by default: see chain_policy).
+    chain_on = [chain_policy(chans[i], N, getattr(b, 'latency_mode', False)) for i in range(nb)]
+    # A backend may run the four blocks as ONE launch with the crop resident in shared memory (PlanBuilder.branch_fused:
+    # the 128-channel 14x14 branch); not when the last block must also write a phase-split copy.
+    fusable = getattr(b, 'branch_fusable', None)
+    resident = [fusable is not None and not chain_on[i] and not (nb - 1 - i >= 2) and fusable(chans[i], xs[i].H, xs[i].W, 4)
+                for i in range(nb)]
+    # (a resident branch needs about half the SM time of its eight separate launches: tools/branch_bench.py)
+    rcost = float(os.environ.get('POCO_B200_BRANCH_COST', '0.5'))
+    b.fork([8 * conv_cost(N, chans[i], chans[i], 3, xs[i].H, xs[i].W) * (rcost if resident[i] else 1.0) for i in range(nb)])
     for i in range(nb):
         b.set_lane(i)
         x = xs[i]
-        # The branch's eight convs share one geometry and CAN run as one persistent chained launch
-        # (POCO_B200_CHAIN_MIN_C, off by default: see chain_policy).
-        chained = chain_policy(chans[i], N, getattr(b, 'latency_mode', False))
+        chained = chain_on[i]
+        if resident[i]:
+            o = b.branch_fused(x, [f'{name}.branches.{i}.{k}' for k in range(4)], chans[i])
+            if o is not None:
+                if o is not x:
+                    b.free(x)
+                xs[i] = o
+                continue
         if chained:
             b.begin_chain()
         for k in range(4):

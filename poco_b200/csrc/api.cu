@@ -109,6 +109,7 @@ extern "C" int poco_run_op(const poco_op* op, void* stream) {
         case POCO_OP_SMPL: return poco_smpl_run(&op->u.smpl, stream);
         case POCO_OP_BASIC_BLOCK: return poco_basic_block_run(&op->u.basic_block, stream);
         case POCO_OP_BOTTLENECK_TAIL: return poco_bottleneck_tail_run(&op->u.bottleneck_tail, stream);
+        case POCO_OP_BRANCH: return poco_branch_run(&op->u.branch, stream);
         default: break;
     }
     set_error("poco_run_op: unknown op kind " + std::to_string(op->kind));
@@ -132,7 +133,11 @@ extern "C" int poco_plan_create(const poco_op* ops, int32_t n_ops, poco_plan** o
             p->flops += 2ll * t.out.N * t.out.H * t.out.W * (int64_t(t.in.C) * t.in.C * 9 + int64_t(t.in.C) * t.out.C);
         }
         if (op.kind == POCO_OP_LINEAR) p->flops += 2ll * op.u.linear.M * op.u.linear.I * op.u.linear.O;
-        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_BOTTLENECK_TAIL || op.lane < 0 || op.lane >= kMaxLanes) {
+        if (op.kind == POCO_OP_BRANCH) {
+            const poco_act& a = op.u.branch.out;
+            p->flops += 2 * op.u.branch.n_blocks * (2ll * a.N * a.H * a.W * a.C * a.C * 9);
+        }
+        if (op.kind < POCO_OP_PACK_IMAGE || op.kind > POCO_OP_BRANCH || op.lane < 0 || op.lane >= kMaxLanes) {
             delete p;
             set_error("poco_plan_create: unknown op kind " + std::to_string(op.kind));
             return 1;

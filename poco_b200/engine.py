@@ -441,6 +441,37 @@ class PlanBuilder:
         self.conv_log.append((name + '.conv2', c, c, 3, 1, x.H, x.H))
         return out
 
+    def branch_fusable(self, c, H, W, n_blocks):
+        """would branch_fused take n_blocks BasicBlocks of c channels at H x W?  (arch.hr_module also asks for the lane costs)"""
+        return (self.conv_impl == 0 and not self.split and self.chain is None and n_blocks <= L.MAX_BRANCH_BLOCKS and
+                os.environ.get('POCO_B200_FUSE_BRANCH', '1') != '0' and hasattr(L.lib(), 'poco_branch_supported') and
+                bool(L.lib().poco_branch_supported(c, H, W, n_blocks)))
+
+    def branch_fused(self, x, names, c):
+        """the BasicBlocks `names` of one HRNet branch (hrnet.py:42-58 x4, hrnet.py:140-186) as ONE poco_branch launch with
+        the crop resident in shared memory, in place (out aliases x), when the library takes the geometry (128 channels,
+        padded crop <= 256 pixels, fp16 mode); None otherwise.  POCO_B200_FUSE_BRANCH=0 switches it off."""
+        if x.C != c or not self.branch_fusable(c, x.H, x.W, len(names)):
+            return None
+        sd = self.sd
+        d = L.Branch()
+        d.in_ = x.desc()
+        d.out = x.desc()
+        for i, name in enumerate(names):
+            for j, (cv, bn) in enumerate(((name + '.conv1', name + '.bn1'), (name + '.conv2', name + '.bn2'))):
+                w = sd[cv + '.weight'].cpu()
+                assert tuple(w.shape) == (c, c, 3, 3) and sd.get(cv + '.bias') is None, cv
+                wf, bf = fold_bn(w, None, tuple(sd[bn + s_].cpu() for s_ in ('.weight', '.bias', '.running_mean', '.running_var')))
+                wp, bp = pack_conv_weight(wf).to(self.device), bf.contiguous().to(self.device)
+                self.keep += [wp, bp]
+                d.weight[2 * i + j] = wp.data_ptr()
+                d.bias[2 * i + j] = bp.data_ptr()
+                self.conv_log.append((cv, c, c, 3, 1, x.H, x.H))
+        d.n_blocks = len(names)
+        d.max_ctas = self._share()
+        self.add(d)
+        return x
+
     def bottleneck_tail_supported(self, y1, planes, cout):
         """True when conv2 (3x3) -> conv3 (1x1) + residual of a Bottleneck runs as one poco_bottleneck_tail launch
         (64 -> 64 -> 256 channels, fp16 mode).  POCO_B200_FUSE_TAIL=0 switches it off."""

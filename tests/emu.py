@@ -220,7 +220,21 @@ def _op20(self, d):         # fused Bottleneck tail: conv2 3x3 -> fp16 intermedi
     self.act_set(o, F.relu(F.conv2d(mid, w3, b3) + self.act_get(r)))
 
 
+def _op21(self, d):         # resident branch: n_blocks BasicBlocks, every hand-off an fp16 tensor in shared memory
+    i, o = d.in_, d.out
+    c = o.C
+    x = self.act_get(i)
+    for blk in range(d.n_blocks):
+        ws = [self.flat(d.weight[2 * blk + j], torch.float16)[:9 * c * c].view(9, c // 8, c, 8).float().permute(2, 1, 3, 0).reshape(c, c, 3, 3)
+              for j in range(2)]
+        bs = [self.flat(d.bias[2 * blk + j], torch.float32)[:c] for j in range(2)]
+        mid = F.relu(F.conv2d(x, ws[0], bs[0], padding=1)).half().float()
+        x = F.relu(F.conv2d(mid, ws[1], bs[1], padding=1) + x).half().float()
+    self.act_set(o, x)
+
+
 Emu._op15 = _op15
+Emu._op21 = _op21
 Emu._op19 = _op19
 Emu._op20 = _op20
 Emu._op13 = lambda self, d: None      # fork / join of plan lanes: the interpreter is sequential

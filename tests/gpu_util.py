@@ -108,6 +108,28 @@ def run_basic_block(x, w1, b1, w2, b2, max_ctas=0):
     return engine.from_planar(o).cpu()
 
 
+def run_branch(x, ws, bs, max_ctas=0, in_place=True):
+    """resident branch (poco_branch): x [N,128,H,W], ws / bs: 2 * n_blocks conv weights [C,C,3,3] (BN folded) / shifts [C]
+    -> [N,C,H,W] float (CPU)"""
+    dev = 'cuda'
+    N, C_, H, W = x.shape
+    a = engine.to_planar(x.to(dev))
+    o = a if in_place else engine.alloc_act(C_, N, H, W, dev)
+    keep = []
+    d = L.Branch()
+    d.in_, d.out = a.desc(), o.desc()
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        keep += [engine.pack_conv_weight(w.to(dev).float()), b.to(dev).float().contiguous()]
+        d.weight[i], d.bias[i] = keep[-2].data_ptr(), keep[-1].data_ptr()
+    d.n_blocks, d.max_ctas = len(ws) // 2, max_ctas
+    L.run_op(d, stream())
+    sync_or_die()
+    halo = engine.act_view(o)
+    assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
+                 halo[:, :, :, -1].abs().sum()) == 0.0, 'kernel wrote into the zero halo'
+    return engine.from_planar(o).cpu()
+
+
 def run_bottleneck_tail(x, w2, b2, w3, b3, residual, max_ctas=0):
     """fused Bottleneck tail (poco_bottleneck_tail): x [N,64,H,W], w2 [64,64,3,3], w3 [256,64,1,1] (BN folded),
     residual [N,256,H,W] -> [N,256,H,W] float (CPU)"""

@@ -593,6 +593,59 @@ def test_basic_block_rejects_what_it_cannot_fuse():
         L.run_op(d, stream())
 
 
+@pytest.mark.parametrize('H,W,N,blocks,max_ctas,in_place', [(14, 14, 3, 4, 0, True), (14, 14, 9, 4, 4, True), (14, 14, 2, 1, 0, False),
+                                                            (14, 14, 5, 2, 2, False), (7, 7, 4, 4, 0, True), (6, 20, 3, 3, 0, True),
+                                                            (14, 14, 200, 4, 0, True)])
+def test_branch_resident_matches_separate_convs(H, W, N, blocks, max_ctas, in_place):
+    """poco_branch (the BasicBlocks of an HRNet branch in one launch, crop resident in shared memory; hrnet.py:42-58 x4,
+    hrnet.py:140-186) against the same blocks as poco_conv launches (same fp16 rounding points: every conv1 output and
+    every block output; the streamed poco_conv walks K in another order, so equal to one fp16 rounding per hand-off) and
+    against fp32 arithmetic on the fp16-rounded operands.  Cases: several crops per CTA with a CTA budget (plan lanes),
+    one block, in place and out of place, a crop of one tile (7x7), a non-square crop that does not fill its two tiles,
+    more crops than SMs."""
+    from gpu_util import run_branch
+    C = 128
+    assert L.lib().poco_branch_supported(C, H, W, blocks) == 1
+    g = torch.Generator().manual_seed(H * 100 + N)
+    x = torch.randn(N, C, H, W, generator=g)
+    ws = [torch.randn(C, C, 3, 3, generator=g) * 0.04 for _ in range(2 * blocks)]
+    bs = [torch.randn(C, generator=g) * 0.2 for _ in range(2 * blocks)]
+    got = run_branch(x, ws, bs, max_ctas, in_place)
+    sep, ref = x.half().float(), x.half().float()
+    for k in range(blocks):
+        if N <= 16:
+            mid = run_conv(sep, ws[2 * k], bs[2 * k], relu=1)
+            sep = run_conv(mid, ws[2 * k + 1], bs[2 * k + 1], relu=1, residual=sep)
+        ref_mid = conv_reference(ref, ws[2 * k], bs[2 * k], relu=1).half().float()
+        ref = conv_reference(ref_mid, ws[2 * k + 1], bs[2 * k + 1], relu=1, residual=ref).half().float()
+    assert rel_err(got, ref) < 2 * CONV_TOL, rel_err(got, ref)
+    if N <= 16:
+        assert rel_err(got, sep) < 2 * CONV_TOL, rel_err(got, sep)
+    # a crop's result does not depend on the batch it travels in or on the CTA that ran it
+    if N >= 3:
+        alone = run_branch(x[2:3], ws, bs, 0, in_place)
+        assert torch.equal(alone, got[2:3])
+
+
+def test_branch_rejects_what_it_cannot_run():
+    lib = L.lib()
+    assert lib.poco_branch_supported(64, 14, 14, 4) == 0 and lib.poco_branch_supported(128, 28, 28, 4) == 0
+    assert lib.poco_branch_supported(128, 14, 14, 5) == 0 and lib.poco_branch_supported(128, 14, 14, 0) == 0
+    a = engine.alloc_act(128, 1, 28, 28, 'cuda')
+    w = torch.zeros(9 * 16 * 128 * 8, dtype=torch.float16, device='cuda')
+    b = torch.zeros(128, device='cuda')
+    d = L.Branch()
+    d.in_, d.out, d.n_blocks = a.desc(), a.desc(), 1
+    d.weight[0] = d.weight[1] = w.data_ptr()
+    d.bias[0] = d.bias[1] = b.data_ptr()
+    with pytest.raises(L.PocoError):        # the crop does not fit
+        L.run_op(d, stream())
+    a14 = engine.alloc_act(128, 1, 14, 14, 'cuda')
+    d.in_, d.out, d.n_blocks = a14.desc(), a14.desc(), 2
+    with pytest.raises(L.PocoError):        # null weights of the second block
+        L.run_op(d, stream())
+
+
 @pytest.mark.parametrize('H,W,N,max_ctas', [(56, 56, 2, 0), (56, 56, 5, 7), (28, 28, 3, 0), (8, 12, 1, 0), (56, 56, 19, 0)])
 def test_bottleneck_tail_fused_matches_two_convs(H, W, N, max_ctas):
     """poco_bottleneck_tail (3x3 conv -> shared memory -> 1x1 conv + residual, one launch; hrnet.py:88-99) against the

@@ -43,7 +43,7 @@ def test_ctypes_layout_matches_header_field_by_field(tmp_path):
     if shutil.which('gcc') is None:
         pytest.skip('gcc not available')
     pairs = [('poco_act', _lib.Act), ('poco_conv', _lib.Conv), ('poco_conv_chain', _lib.ConvChain),
-             ('poco_basic_block', _lib.BasicBlock), ('poco_bottleneck_tail', _lib.BottleneckTail),
+             ('poco_basic_block', _lib.BasicBlock), ('poco_bottleneck_tail', _lib.BottleneckTail), ('poco_branch', _lib.Branch),
              ('poco_pack_image', _lib.PackImage), ('poco_fuse_sum', _lib.FuseSum), ('poco_upsample2x', _lib.Upsample2x),
              ('poco_maxpool', _lib.MaxPool), ('poco_avgpool', _lib.AvgPool), ('poco_unpack', _lib.Unpack),
              ('poco_linear', _lib.Linear), ('poco_copy2d', _lib.Copy2d), ('poco_rot6d', _lib.Rot6d),
@@ -62,7 +62,8 @@ def test_ctypes_layout_matches_header_field_by_field(tmp_path):
     for m, v in (('POCO_MAX_FUSE_INPUTS', _lib.MAX_FUSE_INPUTS), ('POCO_MAX_CHAIN', _lib.MAX_CHAIN),
                  ('POCO_ACT_GUARD_BYTES', _lib.ACT_GUARD_BYTES), ('POCO_SMPL_SCRATCH_FLOATS', _lib.SMPL_SCRATCH_FLOATS),
                  ('POCO_SMPL_DIR_ROWS', _lib.SMPL_DIR_ROWS), ('POCO_OP_SMPL', _lib.OP_SMPL), ('POCO_OP_CONV_CHAIN', _lib.OP_CONV_CHAIN),
-                 ('POCO_OP_BASIC_BLOCK', _lib.OP_BASIC_BLOCK), ('POCO_OP_BOTTLENECK_TAIL', _lib.OP_BOTTLENECK_TAIL)):
+                 ('POCO_OP_BASIC_BLOCK', _lib.OP_BASIC_BLOCK), ('POCO_OP_BOTTLENECK_TAIL', _lib.OP_BOTTLENECK_TAIL),
+                 ('POCO_OP_BRANCH', _lib.OP_BRANCH), ('POCO_MAX_BRANCH_BLOCKS', _lib.MAX_BRANCH_BLOCKS)):
         lines.append(f'printf("%zu\\n", (size_t){m});')
         expect.append((m, v))
     lines += ['return 0; }']
@@ -83,7 +84,7 @@ def test_every_op_rejects_malformed_descriptors_before_touching_the_gpu():
     lib = _lib.lib()
     kinds = [_lib.PackImage, _lib.Conv, _lib.ConvChain, _lib.FuseSum, _lib.Upsample2x, _lib.MaxPool, _lib.AvgPool,
              _lib.Unpack, _lib.Linear, _lib.Copy2d, _lib.Rot6d, _lib.PareHead, _lib.RealNVP, _lib.Crop, _lib.UncertPost,
-             _lib.Smpl, _lib.BasicBlock, _lib.BottleneckTail]
+             _lib.Smpl, _lib.BasicBlock, _lib.BottleneckTail, _lib.Branch]
     assert {_lib._KIND_OF_TYPE[t] for t in kinds} == set(_lib._KIND_OF_TYPE.values())
     n0 = _lib.kernel_launches()
     for t in kinds:
