@@ -351,7 +351,22 @@ def hrnet_pose(b, img, width=32, prefix='backbone.'):
     ys = hrnet_trunk(b, img, widths, prefix=prefix, final_out0=out0)
     feats = holder['feats']             # branch 0 of the last module already landed in its first channels
     c0 = widths[0]
+    # The three up-sampling chains are independent.  POCO_B200_OUT_LANES=1 runs them as concurrent lanes, the longest
+    # (256 channels, three steps) on the lane with the highest stream priority, so that the HBM-bound upsample kernels
+    # and the short convs of the other two fill in around its tensor-bound convs.
+    import os
+    lanes = os.environ.get('POCO_B200_OUT_LANES', '0') == '1' and hasattr(b, 'fork') and getattr(b, 'use_lanes', False)
+    if lanes:
+        def chain_cost(br):
+            h, c = ys[br].H, 0
+            for k in range(br):
+                h *= 2
+                c += conv_cost(b.N, widths[br], widths[br], 3, h, h) + b.N * h * h * widths[br] // 2
+            return c
+        b.fork([chain_cost(br) for br in (1, 2, 3)])
     for br in range(1, 4):
+        if lanes:
+            b.set_lane(br - 1)
         t = ys[br]
         for k in range(br):
             u = b.upsample2x(t)
@@ -362,6 +377,8 @@ def hrnet_pose(b, img, width=32, prefix='backbone.'):
                           out=feats.channels(c0, c0 + widths[br]) if last else None)
             b.free(u)
         c0 += widths[br]
+    if lanes:
+        b.join()
     if b.mode == 'spec':
         b.param_only_conv(prefix + 'final_layer', widths[0], 24, 1)      # present in checkpoints, never executed
     return feats
