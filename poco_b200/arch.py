@@ -238,7 +238,12 @@ def hr_module(b, xs, name, chans, out0=None):
                 for i in range(nb)]
     # (a resident branch needs about half the SM time of its eight separate launches: tools/branch_bench.py)
     rcost = float(os.environ.get('POCO_B200_BRANCH_COST', '0.5'))
-    b.fork([8 * conv_cost(N, chans[i], chans[i], 3, xs[i].H, xs[i].W) * (rcost if resident[i] else 1.0) for i in range(nb)])
+    # (and a fused 64-channel block ~0.85 of its two launches: tools/bblock_bench.py; a block writing a phase-split copy is not fused)
+    fusable64 = getattr(b, 'basic_block_fusable', None)
+    c64 = float(os.environ.get('POCO_B200_BLOCK64_COST', '0.85'))
+    scale = [rcost if resident[i] else (c64 if (chans[i] == 64 and fusable64 is not None and not chain_on[i] and
+                                                fusable64(64, xs[i].H, xs[i].W)) else 1.0) for i in range(nb)]
+    b.fork([8 * conv_cost(N, chans[i], chans[i], 3, xs[i].H, xs[i].W) * scale[i] for i in range(nb)])
     for i in range(nb):
         b.set_lane(i)
         x = xs[i]

@@ -31,7 +31,8 @@
 // (the accumulators stay double buffered).  The tensor pipe then idles only while epilogue 1 runs between C1(u) and
 // C2(u): the next input run lands under C2(u), C1(u + 1) follows C2(u) directly.  Measured at batch 256, 28x28: 61.8 us
 // against 58.7 us for the two launches (6400-6700 cycles per unit for 5184 cycles of MMAs; even at the pipe's rate the
-// recompute leaves ~5 us), so the plan does not use this flavour by default (POCO_B200_FUSE_BLOCK64=1).
+// recompute leaves ~5 us).  The plan's 64-channel blocks run on bblock64_tc.cu instead (conv2's weights streamed, two conv2
+// tiles per unit); this flavour remains behind POCO_B200_BLOCK64_RESIDENT=1 and for rows too long for that kernel.
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -378,6 +379,7 @@ extern "C" int poco_basic_block_supported(int32_t C, int32_t H, int32_t W) {
     if (H < 1 || W < 1 || W + 3 > kLead) return 0;
     if (C == 32) return (4 * kTile - kLead + W + 3) * 16 <= POCO_ACT_GUARD_BYTES;
     if (C == 64) {
+        if (basic_block64_supported(H, W)) return 1;        // (bblock64_tc.cu)
         const int in_pitch = ((2 * kTile + 2 * (W + 3)) * 16 + 127) / 128 * 128;
         return kHeader + 2 * Cfg<64, 1, 1>::kWBytes + 8 * in_pitch + 8 * Cfg<64, 1, 1>::kMidPitch <= 227 * 1024;
     }
@@ -408,6 +410,10 @@ extern "C" int poco_basic_block_run(const poco_basic_block* d, void* stream) {
     p.P = int(P);
     static const char* prof_env = getenv("POCO_BBLOCK_PROF");       // bring-up: device address (decimal) of 16 zeroed uint64 counters
     p.prof = prof_env ? reinterpret_cast<unsigned long long*>(strtoull(prof_env, nullptr, 10)) : nullptr;
+    // 64 channels: the flavour with conv2's weights streamed (bblock64_tc.cu: two conv2 tiles per unit); POCO_B200_BLOCK64_RESIDENT=1
+    // keeps both weight tensors resident and runs one conv2 tile per unit (slower, see the header)
+    static const bool resident64 = getenv("POCO_B200_BLOCK64_RESIDENT") != nullptr;
+    if (in.C == 64 && !resident64 && basic_block64_supported(in.H, in.W)) return basic_block64_launch(d, static_cast<cudaStream_t>(stream));
     if (in.C == 64) return launch_block<64, 1, 1>(d, p, static_cast<cudaStream_t>(stream));
     return launch_block<32, 3, 2>(d, p, static_cast<cudaStream_t>(stream));
 }

@@ -45,5 +45,7 @@ int conv_tc_launch(const poco_conv* d, cudaStream_t s);
 int conv_tc_launch_chain(const poco_conv* segs, int n_segs, int32_t* flags, cudaStream_t s);
 int conv_ref_launch(const poco_conv* d, cudaStream_t s);
 int64_t conv_flops(const poco_conv* d);
+int basic_block64_supported(int H, int W);                                  // bblock64_tc.cu: 64 channels, conv2's weights streamed
+int basic_block64_launch(const poco_basic_block* d, cudaStream_t s);
 
 }  // namespace poco

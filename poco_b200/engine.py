@@ -413,15 +413,19 @@ class PlanBuilder:
         self.conv_log.append((convs[0], x.C, cout, k, stride, x.H, Ho))
         return out
 
+    def basic_block_fusable(self, c, H, W):
+        """would basic_block_fused take a block of c channels at H x W?  (arch.hr_module also asks for the lane costs)"""
+        return (self.conv_impl == 0 and not self.split and self.chain is None and
+                os.environ.get('POCO_B200_FUSE_BLOCK', '1') != '0' and hasattr(L.lib(), 'poco_basic_block_supported') and
+                bool(L.lib().poco_basic_block_supported(c, H, W)) and
+                not (c == 64 and os.environ.get('POCO_B200_FUSE_BLOCK64', '1') == '0'))
+
     def basic_block_fused(self, x, name, c, out=None):
         """BasicBlock `name` (conv1-bn1-ReLU-conv2-bn2, += x, ReLU; hrnet.py:42-58) as ONE poco_basic_block launch when the
         library takes the geometry (32 or 64 channels, W <= 61, fp16 mode); None otherwise (the caller emits two conv_bn ops).
-        POCO_B200_FUSE_BLOCK=0 switches it off.  The 64-channel flavour is opt-in (POCO_B200_FUSE_BLOCK64=1): with one conv2
-        tile per unit it does 1.5x the MMAs and measured 61.8 us against 58.7 us for the two launches at batch 256."""
-        if (self.conv_impl != 0 or self.split or self.chain is not None or x.C != c or
-                os.environ.get('POCO_B200_FUSE_BLOCK', '1') == '0' or not hasattr(L.lib(), 'poco_basic_block_supported') or
-                not L.lib().poco_basic_block_supported(c, x.H, x.W) or
-                (c == 64 and os.environ.get('POCO_B200_FUSE_BLOCK64', '0') != '1')):
+        POCO_B200_FUSE_BLOCK=0 switches it off, POCO_B200_FUSE_BLOCK64=0 only the 64-channel flavour (conv2's weights streamed,
+        csrc/bblock64_tc.cu: 53 us against 60 us for the two launches at batch 256)."""
+        if x.C != c or not self.basic_block_fusable(c, x.H, x.W):
             return None
         sd = self.sd
         packed = []

@@ -53,6 +53,14 @@ for ctas in (0, 148, 74, 37):
         prof.zero_()
         L.run_op(fused, s)
         torch.cuda.synchronize()
+        if CH == 64 and not os.environ.get('POCO_B200_BLOCK64_RESIDENT'):       # bblock64_tc.cu: another counter layout
+            v = prof.tolist()
+            n = max(1, v[6])
+            print('   conv1 issuer, cycles per unit: total %.0f | wait in_full %.0f acc1_free %.0f | issue %.0f   (units/cta %.1f)' %
+                  (v[0] / n, v[1] / n, v[2] / n, v[4] / n, v[6] / max(1, v[7])), flush=True)
+            print('   conv2 issuer, cycles per unit: total %.0f | wait mid_full %.0f acc2_free %.0f w2_full %.0f | issue %.0f' %
+                  (v[8] / n, v[9] / n, v[10] / n, v[11] / n, v[12] / n), flush=True)
+            continue
         for w_ in range(2):
             v = prof.tolist()[w_ * 8:w_ * 8 + 8]
             n = max(1, v[6])
