@@ -119,10 +119,13 @@ def conv_cost(N, cin, cout, k, Hout, Wout):
     Re-weighting them from the measured lane end times of the HR modules (tools/region_times.py: in eager replay
     the 256-channel lane of a stage-4 module ends at 1.00 ms, the 32-channel one at 0.73 ms) did NOT improve the
     captured-graph step (A/B: 20.18 k vs 20.13-20.19 k crops/s, more aggressive weights 19.3-19.7 k), so they
-    stay.  POCO_B200_COST="c32,c64,c128,c256" overrides them."""
+    stay.  Round 2, after the fused block kernels and the prioritised lanes: the 256-channel 7x7 lane ends the four-branch
+    modules (0.80 ms against 0.60-0.65 for the others, tools/region_times.py) because its eight dependent launches queue
+    behind the other lanes' long-lived persistent CTAs; c256 260 -> 400 gives it a larger share: 10.74 -> 10.65 ms per
+    step (A/B twice on one box; 550: the same).  POCO_B200_COST="c32,c64,c128,c256" overrides them."""
     import os
     env = os.environ.get('POCO_B200_COST')
-    c32, c64, c128, c256 = [float(v) for v in env.split(',')] if env else (105.0, 105.0, 170.0, 260.0)
+    c32, c64, c128, c256 = [float(v) for v in env.split(',')] if env else (105.0, 105.0, 170.0, 400.0)
     tiles = -(-N * (Hout + 2) * (Wout + 2) // 128)
     n_tile = min(cout, 256)
     streamed = k * k * cin * n_tile * 2 > 112 * 1024
