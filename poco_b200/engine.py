@@ -266,6 +266,8 @@ class PlanBuilder:
         if self.shares is None:
             return 0
         sc = float(os.environ.get('POCO_B200_SHARE_SCALE', '2'))
+        if self.lane > 0:       # (the side lanes run on higher-priority streams: POCO_B200_SIDE_SCALE lets them ask for more)
+            sc = float(os.environ.get('POCO_B200_SIDE_SCALE', sc))
         if self.chain is not None:      # chained launches spin on each other's tile flags: all their CTAs must be resident
             sc = min(sc, 1.0) if sc > 0 else 1.0
         return 0 if sc <= 0 else max(1, min(self.num_sms, int(round(self.shares[self.lane] * sc))))

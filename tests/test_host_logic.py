@@ -263,6 +263,50 @@ def test_schedule_replay_matches_reference(preset):
     assert eng.plan.flops > 0
 
 
+def test_fused_kernel_support_predicates():
+    """poco_basic_block_supported / poco_bottleneck_tail_supported / poco_branch_supported are pure host functions: which
+    geometries the fused kernels take (include/poco_b200.h); everything else falls back to separate poco_conv launches"""
+    lib = _lib.lib()
+    assert lib.poco_basic_block_supported(32, 56, 56) == 1 and lib.poco_basic_block_supported(32, 56, 61) == 1
+    assert lib.poco_basic_block_supported(32, 56, 62) == 0 and lib.poco_basic_block_supported(48, 56, 56) == 0
+    assert lib.poco_basic_block_supported(64, 28, 28) == 1 and lib.poco_basic_block_supported(64, 56, 56) == 1
+    assert lib.poco_basic_block_supported(64, 28, 62) == 0 and lib.poco_basic_block_supported(128, 14, 14) == 0
+    assert lib.poco_bottleneck_tail_supported(64, 256, 56, 56) == 1 and lib.poco_bottleneck_tail_supported(128, 512, 28, 28) == 0
+    assert lib.poco_branch_supported(128, 14, 14, 4) == 1 and lib.poco_branch_supported(128, 7, 7, 1) == 1
+    assert lib.poco_branch_supported(128, 6, 20, 3) == 1 and lib.poco_branch_supported(128, 15, 15, 4) == 0     # 17 * 17 > 256
+    assert lib.poco_branch_supported(64, 14, 14, 4) == 0 and lib.poco_branch_supported(256, 7, 7, 4) == 0
+    assert lib.poco_branch_supported(128, 14, 14, 5) == 0 and lib.poco_branch_supported(128, 14, 14, 0) == 0
+
+
+def test_plan_fuses_blocks_in_fp16_mode_only(monkeypatch):
+    """the HRNet-W32 plan: 25 + 29 BasicBlocks (32 / 64 channels; the blocks that also write a phase-split copy stay
+    separate), the four Bottleneck tails of layer1 and the seven 128-channel branches run as fused launches in fp16 mode;
+    the parity mode and the POCO_B200_FUSE_* = 0 switches use separate convs; either way every conv of the network is
+    accounted for in conv_log"""
+    def kinds(m):
+        eng = m._build_engine(2, torch.device('cpu'))
+        c = {}
+        for op in eng.plan.ops:
+            c[op.kind] = c.get(op.kind, 0) + 1
+        return c, len(eng.plan.conv_log)
+    m = build_model('cliff_w32')
+    c, n_convs = kinds(m)
+    assert (c.get(_lib.OP_BASIC_BLOCK), c.get(_lib.OP_BOTTLENECK_TAIL), c.get(_lib.OP_BRANCH)) == (54, 4, 7)
+    assert c[_lib.OP_CONV] + 2 * 54 + 2 * 4 + 8 * 7 == n_convs
+    for var in ('POCO_B200_FUSE_BLOCK', 'POCO_B200_FUSE_TAIL', 'POCO_B200_FUSE_BRANCH'):
+        monkeypatch.setenv(var, '0')
+    c0, n0 = kinds(build_model('cliff_w32'))
+    assert n0 == n_convs == c0[_lib.OP_CONV] and not any(k in c0 for k in (_lib.OP_BASIC_BLOCK, _lib.OP_BOTTLENECK_TAIL, _lib.OP_BRANCH))
+    for var in ('POCO_B200_FUSE_BLOCK', 'POCO_B200_FUSE_TAIL', 'POCO_B200_FUSE_BRANCH'):
+        monkeypatch.delenv(var)
+    monkeypatch.setenv('POCO_B200_FUSE_BLOCK64', '0')
+    c64, _ = kinds(build_model('cliff_w32'))
+    assert c64.get(_lib.OP_BASIC_BLOCK) == 25 and c64.get(_lib.OP_BRANCH) == 7
+    monkeypatch.delenv('POCO_B200_FUSE_BLOCK64')
+    cs, ns = kinds(build_model('cliff_w32', precision='split'))
+    assert ns == n_convs == cs[_lib.OP_CONV] and _lib.OP_BRANCH not in cs and _lib.OP_BASIC_BLOCK not in cs
+
+
 def test_buffer_pool_keeps_zero_halo():
     """pool reuse never hands a buffer to a tensor of different spatial geometry"""
     b = engine.PlanBuilder({}, 2, 'cpu')

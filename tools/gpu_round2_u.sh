@@ -1,0 +1,18 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+run() { echo "== $*"; env "$@" timeout 150 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-other-mode 2> gpurun_out/bench_var.err | python -c "
+import sys, json
+for l in sys.stdin:
+    l = l.strip()
+    if l.startswith('{'):
+        d = json.loads(l); print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'launches', d['launches_per_forward'])
+"; }
+run X=1
+run POCO_B200_SIDE_SCALE=3
+run POCO_B200_SIDE_SCALE=4
+run POCO_B200_SIDE_SCALE=3 POCO_B200_SHARE_SCALE=1.5
+run POCO_B200_SIDE_SCALE=4 POCO_B200_SHARE_SCALE=1
+run POCO_B200_SIDE_SCALE=2.5 POCO_B200_SHARE_SCALE=1.5
+run X=2
+run POCO_B200_SIDE_SCALE=3
