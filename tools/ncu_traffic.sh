@@ -40,12 +40,16 @@ lin = [v for v in per.values() if 'conv_tc_kernel<0' in v['name']]
 gat = [v for v in per.values() if 'conv_tc_kernel<1' in v['name']]
 def avg(vs, k): return sum(v[k] for v in vs) / max(1, len(vs))
 sha = hashlib.sha256(open('poco_b200/libpoco_b200.so', 'rb').read()).hexdigest()[:16]
+import sys
+sys.path.insert(0, '.')
+import bench
+src_sha = bench.source_hash()
 out = {'kernel': 'conv_tc_linear', 'launches_captured': len(lin),
        'dram_bytes_per_launch': round(avg(lin, 'dram__bytes_read.sum') + avg(lin, 'dram__bytes_write.sum')),
        'dram_read_bytes_per_launch': round(avg(lin, 'dram__bytes_read.sum')), 'dram_write_bytes_per_launch': round(avg(lin, 'dram__bytes_write.sum')),
        'avg_launch_us_under_ncu': round(avg(lin, 'gpu__time_duration.sum'), 2),
        'gather': {'launches_captured': len(gat), 'dram_bytes_per_launch': round(avg(gat, 'dram__bytes_read.sum') + avg(gat, 'dram__bytes_write.sum'))},
-       'lib_sha256_16': sha, 'command': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:conv_tc python bench.py --steps 2 --warmup 3 (cliff_w32, 256 crops, fp16; all conv launches of the eager + graph-capture forwards)'}
+       'lib_sha256_16': sha, 'src_sha256_16': src_sha, 'command': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:conv_tc python bench.py --steps 2 --warmup 3 (cliff_w32, 256 crops, fp16; all conv launches of the eager + graph-capture forwards)'}
 # the fused kernels of the same forward (one launch = a whole block / branch)
 for key, pat in (('basic_block_tc', 'basic_block'), ('bottleneck_tail_tc', 'bottleneck_tail'), ('branch_tc', 'branch_kernel')):
     vs = [v for v in per.values() if pat in v['name']]
