@@ -22,7 +22,8 @@
 // activations, so the next conv's first stages are already there when its input is), warps 1 / 2 issue the MMAs of
 // tile 0 / tile 1 (M = 128, N = 128: four K = 16 MMAs per stage and tile, 64 cycles each), warps 3-10 epilogue (four TMEM
 // lane groups per tile).  Within a crop the convs are strictly sequential, so the tensor pipe idles while an epilogue
-// runs (~10 % of a conv); across CTAs nothing is shared but the weights in L2.
+// runs (~3000 of 12700 cycles per conv, measured: two epilogue warps per scheduler cannot hide their tcgen05.ld / LDS
+// latencies -- it is not the TMEM read rate, tools/tmem_ld_bench.cu); across CTAs nothing is shared but the weights in L2.
 // mbarriers: w_full / w_empty[5] (producer <-> both issuers), x_full / x_free (crop landed / crop finished),
 // acc_full[2] (issuer -> its tile's epilogue warps), tile_ready[2] (a tile's epilogue warps -> issuers: its rows of MID or X
 // are written, its accumulator drained).  The two tiles share every weight stage but not their pace: the ring lets one

@@ -7,11 +7,14 @@
 // operand layout, the 1x1 conv -- pointwise, so no halo and no recompute -- reads it there as two N = 128 halves, and
 // epilogue 2 adds shift3 and the 256-channel residual and writes the output planes.
 //
-// Roles (352 threads, one persistent CTA per SM, tiles dealt round-robin): warp 0 producer (both weight tensors once,
+// Roles (96 + 128 kSets threads, one persistent CTA per SM, tiles dealt round-robin): warp 0 producer (both weight tensors once,
 // then one bulk copy per input plane and tile: the tile plus its (W+3)-pixel reach, double buffered), warp 1 issues the
-// 3x3 conv's MMAs (9 taps x 4 K steps, N = 64), warp 2 the 1x1 conv's (4 K steps per N = 128 half), warps 3-10
-// epilogue: two sets of four TMEM lane groups; set s owns columns [32 s, 32 s + 32) of the first accumulator and
-// half s of the second.  TMEM: 2 x 64 + 2 x 128 columns.  The kernel is bound by its 822 MB of output + residual traffic.
+// 3x3 conv's MMAs (9 taps x 4 K steps, N = 64), warp 2 the 1x1 conv's (4 K steps per N = 128 half), then 4 * kSets
+// epilogue warps: kSets sets of four TMEM lane groups; set s owns columns [64 s / kSets, ...) of the first accumulator and
+// output channels [256 s / kSets, ...) of the second.  TMEM: 2 x 64 + 2 x 128 columns.  The kernel is bound by its 822 MB of
+// output + residual traffic -- and by the latency of its epilogues: with FOUR sets (16 epilogue warps, 88 registers, one
+// TMEM buffer per thread) instead of two (150 registers, double buffered) a launch takes 203 instead of 220 us at batch 256
+// (4.55 TB/s; the whole step 10.70 -> 10.58 ms, A/B twice on one box).
 //
 // Measured while tuning (batch 256, 45.5 tiles per CTA, clock64 laps inside the epilogue warps, tools/btail_bench.py of the
 // time): a tile takes ~8200 cycles whatever the role layout -- 218 us per launch = 4.2 TB/s of algorithmic traffic, DRAM
@@ -52,7 +55,17 @@ constexpr int kW2Bytes = 9 * kPm * kSlab2;          // 72 KB
 constexpr int kW3Bytes = kPm * kSlab3;              // 32 KB
 constexpr int kMidPitch = kTile * 16;               // one plane of the intermediate tile: 2 KB
 constexpr int kHeader = 2048;
-constexpr int kThreads = 352;
+// epilogue warp sets (four TMEM lane groups each).  The epilogues are latency-bound, not TMEM-bound (tools/tmem_ld_bench.cu:
+// a 32-column tcgen05.ld takes ~190 cycles, eight warps with several loads in flight read > 600 B/clk): with two sets a
+// scheduler holds two epilogue warps and cannot hide their tcgen05.ld / LDS / LDG latencies, four sets give it four.
+#ifndef POCO_TAIL_SETS
+#define POCO_TAIL_SETS 4
+#endif
+constexpr int kSets = POCO_TAIL_SETS;                   // 2 or 4
+static_assert(kSets == 2 || kSets == 4, "POCO_TAIL_SETS");
+constexpr int kThreads = 96 + 128 * kSets;              // producer, two issuers, 4 * kSets epilogue warps
+constexpr int kCols1 = kCm / kSets;                     // epilogue 1: accumulator columns per set (32 or 16)
+constexpr int kCols2 = kCo / kSets;                     // epilogue 2: output channels per set (128 or 64)
 constexpr int kTmemCols = 512;          // 2 x 64 + 2 x 128 = 384 used
 
 struct TailParams {
@@ -99,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) bottleneck_tail_kernel(const Tail
     if (threadIdx.x < 16) {
         unsigned long long* bars = hdr->in_full;                    // the sixteen ring barriers are contiguous
         const int which = threadIdx.x >> 1;                         // 0 in_full 1 in_free 2 acc1_full 3 acc1_free 4 mid_full 5 mid_free 6 acc2_full 7 acc2_free
-        const uint32_t count = (which == 3 || which == 4) ? 8u : (which == 7 ? 4u : 1u);    // all epilogue warps / the four warps of a set / one commit
+        const uint32_t count = (which == 3 || which == 4) ? uint32_t(4 * kSets) : (which == 7 ? uint32_t(2 * kSets) : 1u);    // all epilogue warps / the warps of an accumulator half / one commit
         mbar_init(smem_u32(bars + threadIdx.x), count);
     }
     if (threadIdx.x == 16) mbar_init(smem_u32(&hdr->w_full), 1);
@@ -187,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) bottleneck_tail_kernel(const Tail
             }
         }
     } else {
-        // ============================================================ epilogue (8 warps)
+        // ============================================================ epilogue (4 * kSets warps)
         const int ew = warp - 3;
         const int set = ew >> 2;
         const int lg = warp & 3;                        // TMEM lane group this warp may access
@@ -198,24 +211,24 @@ __global__ void __launch_bounds__(kThreads, 1) bottleneck_tail_kernel(const Tail
             const uint32_t yy = rem / uint32_t(Wp), xx = rem - yy * uint32_t(Wp);
             return q < p.P && yy >= 1u && yy <= uint32_t(p.H) && xx >= 1u && xx <= uint32_t(p.W);
         };
-        auto epilogue1 = [&](int j) {                   // this warp: columns [32 set, 32 set + 32) of its 32 rows
+        auto epilogue1 = [&](int j) {                   // this warp: columns [kCols1 set, kCols1 set + kCols1) of its 32 rows
             const uint32_t b = uint32_t(j) & 1u, par = (uint32_t(j) >> 1) & 1u;
             const long long unit = (long long)blockIdx.x + (long long)j * gridDim.x;
             MBAR_WAIT(smem_u32(&hdr->acc1_full[b]), par);
             MBAR_WAIT(smem_u32(&hdr->mid_free[b]), par ^ 1u);
             tc_fence_after();
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + acc1_col(b) + uint32_t(set * 32) + lane_sel;
-            tmem_ld16(taddr, v);
-            tmem_ld16(taddr + 16, v + 16);
+            uint32_t v[kCols1];
+            const uint32_t taddr = tmem_base + acc1_col(b) + uint32_t(set * kCols1) + lane_sel;
+#pragma unroll
+            for (int c = 0; c < kCols1; c += 16) tmem_ld16(taddr + uint32_t(c), v + c);
             const bool keep = interior_of(unit * kTile + row);
             tmem_ld_wait();
-            uint8_t* dst = mid_smem + b * mid_buf_bytes + (set * 4) * kMidPitch + row * 16;
+            uint8_t* dst = mid_smem + b * mid_buf_bytes + (set * (kCols1 / 8)) * kMidPitch + row * 16;
 #pragma unroll
-            for (int pl = 0; pl < 4; ++pl) {
+            for (int pl = 0; pl < kCols1 / 8; ++pl) {
                 float f[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = keep ? fmaxf(__uint_as_float(v[pl * 8 + i]) + hdr->bias2[set * 32 + pl * 8 + i], 0.f) : 0.f;
+                for (int i = 0; i < 8; ++i) f[i] = keep ? fmaxf(__uint_as_float(v[pl * 8 + i]) + hdr->bias2[set * kCols1 + pl * 8 + i], 0.f) : 0.f;
                 uint4 o4;
                 o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
                 o4.z = pack_half2(f[4], f[5]); o4.w = pack_half2(f[6], f[7]);
@@ -229,44 +242,55 @@ __global__ void __launch_bounds__(kThreads, 1) bottleneck_tail_kernel(const Tail
                 mbar_arrive(smem_u32(&hdr->mid_full[b]));
             }
         };
+        constexpr int kPl2 = kCols2 / 8;                // output planes per set (16 or 8)
         auto res_ptr = [&](long long q, int pl) {
-            return reinterpret_cast<const uint4*>(p.res + ((long long)(set * 16 + pl) * p.res_plane + q) * 8);
+            return reinterpret_cast<const uint4*>(p.res + ((long long)(set * kPl2 + pl) * p.res_plane + q) * 8);
         };
         const long long q_first = (long long)blockIdx.x * kTile + row;
-        auto epilogue2 = [&](int j) {                   // this warp: output channels [128 set, 128 set + 128) of its 32 rows
+        const int half = (set * kCols2) / 128;          // which N = 128 accumulator half this set reads
+        auto epilogue2 = [&](int j) {                   // this warp: output channels [kCols2 set, kCols2 set + kCols2) of its 32 rows
             const uint32_t upar = uint32_t(j) & 1u;
             const long long q = q_first + (long long)j * gridDim.x * kTile;
             const bool keep = interior_of(q);
-            // the residual rows of all 16 planes are requested before the wait: they arrive under the MMAs
-            uint4 res[16];
+            // the residual rows of all planes are requested before the wait: they arrive under the MMAs
+            uint4 res[kPl2];
 #pragma unroll
-            for (int pl = 0; pl < 16; ++pl) res[pl] = keep ? __ldg(res_ptr(q, pl)) : make_uint4(0, 0, 0, 0);
-            MBAR_WAIT(smem_u32(&hdr->acc2_full[set]), upar);
+            for (int pl = 0; pl < kPl2; ++pl) res[pl] = keep ? __ldg(res_ptr(q, pl)) : make_uint4(0, 0, 0, 0);
+            MBAR_WAIT(smem_u32(&hdr->acc2_full[half]), upar);
             tc_fence_after();
-            __half* outp = p.out + ((long long)(set * 16) * p.out_plane + q) * 8;
+            __half* outp = p.out + ((long long)(set * kPl2) * p.out_plane + q) * 8;
             // accumulator columns 32 at a time (4 output planes); the TMEM load of the next 32 is in flight during the math
-            uint32_t va[32], vb[32];
-            const uint32_t taddr0 = tmem_base + acc2_col(uint32_t(set)) + lane_sel;
+            // (two sets: the next load is in flight during the math of this one; four sets leave a thread 104 registers, so one
+            //  buffer, and the other three warps of the scheduler cover the load)
+            constexpr bool kDouble = kSets == 2;
+            uint32_t va[32], vb[kDouble ? 32 : 1];
+            const uint32_t taddr0 = tmem_base + acc2_col(uint32_t(half)) + uint32_t((set * kCols2) % 128) + lane_sel;
             tmem_ld16(taddr0, va);
             tmem_ld16(taddr0 + 16, va + 16);
+            constexpr int kChunks = kCols2 / 32;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t* v = (c & 1) ? vb : va;
-                uint32_t* vn = (c & 1) ? va : vb;
+            for (int c = 0; c < kChunks; ++c) {
+                uint32_t* v = (kDouble && (c & 1)) ? vb : va;
+                uint32_t* vn = (kDouble && !(c & 1)) ? vb : va;
+                if (!kDouble && c > 0) {
+                    tmem_ld16(taddr0 + uint32_t(c * 32), va);
+                    tmem_ld16(taddr0 + uint32_t(c * 32 + 16), va + 16);
+                }
                 tmem_ld_wait();
-                if (c < 3) {
+                if (kDouble && c < kChunks - 1) {
                     tmem_ld16(taddr0 + uint32_t((c + 1) * 32), vn);
                     tmem_ld16(taddr0 + uint32_t((c + 1) * 32 + 16), vn + 16);
-                } else {                // the accumulator half is drained: the next tile's MMAs may overwrite it
+                }
+                if (c == kChunks - 1) {     // this set's columns are drained: once every set of the half has arrived, the next tile's MMAs may overwrite it
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&hdr->acc2_free[set]));
+                    if (lane == 0) mbar_arrive(smem_u32(&hdr->acc2_free[half]));
                 }
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl) {
                     const uint4 r4 = res[c * 4 + pl];
                     const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
-                    const float* bs = hdr->bias3 + set * 128 + c * 32 + pl * 8;
+                    const float* bs = hdr->bias3 + set * kCols2 + c * 32 + pl * 8;
                     float f[8];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
