@@ -107,6 +107,9 @@ typedef struct poco_basic_block {
     const float* bias2;
     int32_t max_ctas; /* like poco_conv.max_ctas: 0 = all SMs */
     int32_t pad_;
+    poco_act out_s2d; /* data NULL: none.  Else a second output like poco_conv.out_s2d: the phase-split form of `out`
+                       * (4*C channels, H/2 x W/2, H and W even) for the stride-2 fuse convs that read this block
+                       * (hrnet.py:213-240); C = 32 only */
 } poco_basic_block;
 
 /* The tail of a Bottleneck block as ONE launch (hrnet.py:79-99, resnet.py:100-121):

@@ -40,7 +40,7 @@ class ConvChain(C.Structure):
 
 class BasicBlock(C.Structure):
     _fields_ = [('in_', Act), ('out', Act), ('weight1', C.c_void_p), ('bias1', C.c_void_p), ('weight2', C.c_void_p),
-                ('bias2', C.c_void_p), ('max_ctas', C.c_int32), ('pad_', C.c_int32)]
+                ('bias2', C.c_void_p), ('max_ctas', C.c_int32), ('pad_', C.c_int32), ('out_s2d', Act)]
 
 
 class BottleneckTail(C.Structure):

@@ -148,8 +148,8 @@ def basic_block(b, x, name, cin, cout, free_input=True, s2d_out=None):
     s2d_out: the block's output also feeds stride-2 convs -> its last conv writes the phase-split copy too.
     A backend may run the whole block as one launch (PlanBuilder.basic_block_fused: the intermediate stays on the SM)."""
     fused = getattr(b, 'basic_block_fused', None)
-    if fused is not None and cin == cout and s2d_out is None:
-        o = fused(x, name, cin)
+    if fused is not None and cin == cout:
+        o = fused(x, name, cin, s2d=s2d_out)
         if o is not None:
             if free_input:
                 b.free(x)

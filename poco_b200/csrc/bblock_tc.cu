@@ -88,6 +88,9 @@ struct BlockParams {
     int in_pitch;                       // bytes between the planes of an input run in shared memory
     int run_bytes;                      // bytes of one input run: ((G + 1) * 128 + 2 R) * 16
     unsigned long long* prof;           // bring-up (POCO_BBLOCK_PROF): per issuer [total, in_full, acc1_free, mid_full, acc2_free, issue, units, ctas]
+    __half* s2d_out;                    // second output: phase-split copy of `out` (poco_basic_block.out_s2d), or nullptr
+    long long s2d_plane;                // its plane stride (pixels)
+    int s2d_Wp, s2d_HpWp;               // its padded row pitch / padded pixels per crop
 };
 
 struct Header {
@@ -293,10 +296,17 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
             // the residual = the block input at the output pixel: issued before the wait, it arrives under the MMAs
             uint4 res[2][4];
             bool keep[2];
+            long long s2d_off[2] = {0, 0};      // this row's pixel in the phase-split second output (plane 0 of its phase)
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int it = i0 + 2 * k, g = it / kChunks, ch = it % kChunks;
                 keep[k] = it < kItems && interior_of(q0 + g * kTile);
+                if (p.s2d_out != nullptr && keep[k]) {
+                    const uint32_t q = uint32_t(q0 + g * kTile), n_crop = q / uint32_t(HpWp), rem = q - n_crop * uint32_t(HpWp);
+                    const uint32_t y = rem / uint32_t(Wp) - 1u, x = rem % uint32_t(Wp) - 1u;
+                    s2d_off[k] = ((long long)(((y & 1u) * 2u + (x & 1u)) * uint32_t(kPlanes)) * p.s2d_plane + (long long)n_crop * p.s2d_HpWp +
+                                  ((y >> 1) + 1u) * uint32_t(p.s2d_Wp) + (x >> 1) + 1u) * 8;
+                }
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl)
                     res[k][pl] = keep[k] ? __ldg(reinterpret_cast<const uint4*>(p.in + ((long long)(ch * 4 + pl) * p.in_plane + q0 + g * kTile) * 8))
@@ -330,6 +340,8 @@ __global__ void __launch_bounds__(kThreads, 1) basic_block_kernel(const BlockPar
                         o4.x = pack_half2(f[0], f[1]); o4.y = pack_half2(f[2], f[3]);
                         o4.z = pack_half2(f[4], f[5]); o4.w = pack_half2(f[6], f[7]);
                         *reinterpret_cast<uint4*>(outp + (long long)pl * p.out_plane * 8) = o4;
+                        if (p.s2d_out != nullptr)       // the same pixel in the phase-split copy (feeds the stride-2 fuse convs)
+                            *reinterpret_cast<uint4*>(p.s2d_out + s2d_off[k] + (long long)(ch * 4 + pl) * p.s2d_plane * 8) = o4;
                     }
                 }
             }
@@ -394,6 +406,13 @@ extern "C" int poco_basic_block_run(const poco_basic_block* d, void* stream) {
     POCO_CHECK(poco_basic_block_supported(in.C, in.H, in.W), "basic block: only 32 channels (W + 3 <= 64) or 64 channels (short rows) run fused");
     POCO_CHECK(in.lo == nullptr && out.lo == nullptr, "basic block: fp16 mode only");
     POCO_CHECK(in.data != out.data, "basic block: in and out must not alias");
+    if (d->out_s2d.data != nullptr) {
+        const poco_act& s2 = d->out_s2d;
+        if (check_act(s2, "out_s2d")) return 1;
+        POCO_CHECK(in.C == 32 && out.H % 2 == 0 && out.W % 2 == 0 && s2.C == 4 * out.C && s2.N == out.N && s2.H == out.H / 2 &&
+                       s2.W == out.W / 2 && s2.lo == nullptr,
+                   "basic block out_s2d: 32 channels only; 4 C channels at half the (even) output resolution");
+    }
     POCO_CHECK(d->weight1 && d->weight2 && d->bias1 && d->bias2, "null weight / bias");
     const int64_t P = int64_t(in.N) * (in.H + 2) * (in.W + 2);
     POCO_CHECK(P + 4096 < (int64_t(1) << 31), "tensor too large");
@@ -408,6 +427,10 @@ extern "C" int poco_basic_block_run(const poco_basic_block* d, void* stream) {
     p.out_plane = out.plane_stride;
     p.H = in.H; p.W = in.W;
     p.P = int(P);
+    p.s2d_out = static_cast<__half*>(d->out_s2d.data);
+    p.s2d_plane = d->out_s2d.plane_stride;
+    p.s2d_Wp = d->out_s2d.W + 2;
+    p.s2d_HpWp = (d->out_s2d.H + 2) * (d->out_s2d.W + 2);
     static const char* prof_env = getenv("POCO_BBLOCK_PROF");       // bring-up: device address (decimal) of 16 zeroed uint64 counters
     p.prof = prof_env ? reinterpret_cast<unsigned long long*>(strtoull(prof_env, nullptr, 10)) : nullptr;
     // 64 channels: the flavour with conv2's weights streamed (bblock64_tc.cu: two conv2 tiles per unit); POCO_B200_BLOCK64_RESIDENT=1

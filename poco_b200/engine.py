@@ -422,13 +422,16 @@ class PlanBuilder:
                 bool(L.lib().poco_basic_block_supported(c, H, W)) and
                 not (c == 64 and os.environ.get('POCO_B200_FUSE_BLOCK64', '1') == '0'))
 
-    def basic_block_fused(self, x, name, c, out=None):
+    def basic_block_fused(self, x, name, c, out=None, s2d=None):
         """BasicBlock `name` (conv1-bn1-ReLU-conv2-bn2, += x, ReLU; hrnet.py:42-58) as ONE poco_basic_block launch when the
         library takes the geometry (32 or 64 channels, W <= 61, fp16 mode); None otherwise (the caller emits two conv_bn ops).
         POCO_B200_FUSE_BLOCK=0 switches it off, POCO_B200_FUSE_BLOCK64=0 only the 64-channel flavour (conv2's weights streamed,
         csrc/bblock64_tc.cu: 53 us against 60 us for the two launches at batch 256)."""
         if x.C != c or not self.basic_block_fusable(c, x.H, x.W):
             return None
+        want_s2d = bool(s2d) and self.use_s2d
+        if want_s2d and (s2d != 'dual' or c != 32 or x.H % 2 or x.W % 2 or os.environ.get('POCO_B200_FUSE_BLOCK_S2D', '1') == '0'):
+            return None     # (the phase-split second output exists for the 32-channel flavour only: two conv launches instead)
         sd = self.sd
         packed = []
         for cv, bn in ((name + '.conv1', name + '.bn1'), (name + '.conv2', name + '.bn2')):
@@ -442,6 +445,9 @@ class PlanBuilder:
         assert (out.C, out.H, out.W) == (c, x.H, x.W)
         d = L.BasicBlock(x.desc(), out.desc(), packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(),
                          packed[3].data_ptr(), self._share(), 0)
+        if want_s2d:        # the block's output also feeds stride-2 fuse convs: epilogue 2 writes the phase-split copy as well
+            out.s2d = self.act(4 * c, x.H // 2, x.W // 2)
+            d.out_s2d = out.s2d.desc()
         self.add(d)
         self.conv_log.append((name + '.conv1', c, c, 3, 1, x.H, x.H))
         self.conv_log.append((name + '.conv2', c, c, 3, 1, x.H, x.H))

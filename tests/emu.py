@@ -206,7 +206,10 @@ def _op19(self, d):         # fused BasicBlock: conv1 -> fp16 intermediate -> co
           for w_ in (d.weight1, d.weight2)]
     bs = [self.flat(b_, torch.float32)[:c] for b_ in (d.bias1, d.bias2)]
     mid = F.relu(F.conv2d(x, ws[0], bs[0], padding=1)).half().float()      # the kernel keeps it as fp16 in shared memory
-    self.act_set(o, F.relu(F.conv2d(mid, ws[1], bs[1], padding=1) + x))
+    y = F.relu(F.conv2d(mid, ws[1], bs[1], padding=1) + x)
+    self.act_set(o, y)
+    if d.out_s2d.data:
+        self.act_set(d.out_s2d, space_to_depth(y))
 
 
 def _op20(self, d):         # fused Bottleneck tail: conv2 3x3 -> fp16 intermediate -> conv3 1x1 + residual

@@ -91,8 +91,9 @@ def conv_reference_split(x, w, bias, stride=1, pad=None, relu=1, residual=None):
     return y
 
 
-def run_basic_block(x, w1, b1, w2, b2, max_ctas=0):
-    """fused BasicBlock (poco_basic_block): x [N,C,H,W], w1 / w2 [C,C,3,3] (BN folded), b1 / b2 [C] -> [N,C,H,W] float (CPU)"""
+def run_basic_block(x, w1, b1, w2, b2, max_ctas=0, s2d=False):
+    """fused BasicBlock (poco_basic_block): x [N,C,H,W], w1 / w2 [C,C,3,3] (BN folded), b1 / b2 [C] -> [N,C,H,W] float (CPU);
+    s2d=True: also the phase-split second output [N,4C,H/2,W/2] -> (out, out_s2d)"""
     dev = 'cuda'
     N, C_, H, W = x.shape
     a = engine.to_planar(x.to(dev))
@@ -100,11 +101,18 @@ def run_basic_block(x, w1, b1, w2, b2, max_ctas=0):
     p1, p2 = engine.pack_conv_weight(w1.to(dev).float()), engine.pack_conv_weight(w2.to(dev).float())
     c1, c2 = b1.to(dev).float().contiguous(), b2.to(dev).float().contiguous()
     d = L.BasicBlock(a.desc(), o.desc(), p1.data_ptr(), c1.data_ptr(), p2.data_ptr(), c2.data_ptr(), max_ctas, 0)
+    o2 = None
+    if s2d:
+        o2 = engine.alloc_act(4 * C_, N, H // 2, W // 2, dev)
+        d.out_s2d = o2.desc()
     L.run_op(d, stream())
     sync_or_die()
-    halo = engine.act_view(o)
-    assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
-                 halo[:, :, :, -1].abs().sum()) == 0.0, 'kernel wrote into the zero halo'
+    for t in (o, o2) if s2d else (o,):
+        halo = engine.act_view(t)
+        assert float(halo[:, :, 0].abs().sum() + halo[:, :, -1].abs().sum() + halo[:, :, :, 0].abs().sum() +
+                     halo[:, :, :, -1].abs().sum()) == 0.0, 'kernel wrote into the zero halo'
+    if s2d:
+        return engine.from_planar(o).cpu(), engine.from_planar(o2).cpu()
     return engine.from_planar(o).cpu()
 
 

@@ -576,6 +576,24 @@ def test_basic_block_fused_matches_two_convs(C, H, W, N, max_ctas):
     assert rel_err(got, ref) < CONV_TOL
 
 
+@pytest.mark.parametrize('H,W,N,max_ctas', [(56, 56, 3, 0), (28, 28, 5, 3), (8, 12, 2, 0)])
+def test_basic_block_fused_writes_the_phase_split_copy(H, W, N, max_ctas):
+    """poco_basic_block.out_s2d: the fused 32-channel block writes its output a second time in phase-split form
+    (channel ((y & 1) * 2 + (x & 1)) * C + c of pixel (y / 2, x / 2)) for the stride-2 fuse convs (hrnet.py:213-240):
+    the normal output is unchanged bit for bit and the copy is exactly its space-to-depth"""
+    import emu
+    from gpu_util import run_basic_block
+    C = 32
+    g = torch.Generator().manual_seed(H + N)
+    x = torch.randn(N, C, H, W, generator=g)
+    w1, w2 = (torch.randn(C, C, 3, 3, generator=g) * 0.08 for _ in range(2))
+    b1, b2 = (torch.randn(C, generator=g) * 0.2 for _ in range(2))
+    plain = run_basic_block(x, w1, b1, w2, b2, max_ctas)
+    out, copy = run_basic_block(x, w1, b1, w2, b2, max_ctas, s2d=True)
+    assert torch.equal(out, plain)
+    assert torch.equal(copy, emu.space_to_depth(out))
+
+
 def test_basic_block_rejects_what_it_cannot_fuse():
     lib = L.lib()
     assert lib.poco_basic_block_supported(128, 14, 14) == 0 and lib.poco_basic_block_supported(32, 56, 62) == 0

@@ -279,8 +279,9 @@ def test_fused_kernel_support_predicates():
 
 
 def test_plan_fuses_blocks_in_fp16_mode_only(monkeypatch):
-    """the HRNet-W32 plan: 25 + 29 BasicBlocks (32 / 64 channels; the blocks that also write a phase-split copy stay
-    separate), the four Bottleneck tails of layer1 and the seven 128-channel branches run as fused launches in fp16 mode;
+    """the HRNet-W32 plan: 32 + 29 BasicBlocks (all 32-channel blocks, seven of them also writing the phase-split copy; the
+    64-channel blocks except the three that write such a copy), the four Bottleneck tails of layer1 and the seven
+    128-channel branches run as fused launches in fp16 mode;
     the parity mode and the POCO_B200_FUSE_* = 0 switches use separate convs; either way every conv of the network is
     accounted for in conv_log"""
     def kinds(m):
@@ -291,8 +292,8 @@ def test_plan_fuses_blocks_in_fp16_mode_only(monkeypatch):
         return c, len(eng.plan.conv_log)
     m = build_model('cliff_w32')
     c, n_convs = kinds(m)
-    assert (c.get(_lib.OP_BASIC_BLOCK), c.get(_lib.OP_BOTTLENECK_TAIL), c.get(_lib.OP_BRANCH)) == (54, 4, 7)
-    assert c[_lib.OP_CONV] + 2 * 54 + 2 * 4 + 8 * 7 == n_convs
+    assert (c.get(_lib.OP_BASIC_BLOCK), c.get(_lib.OP_BOTTLENECK_TAIL), c.get(_lib.OP_BRANCH)) == (61, 4, 7)
+    assert c[_lib.OP_CONV] + 2 * 61 + 2 * 4 + 8 * 7 == n_convs
     for var in ('POCO_B200_FUSE_BLOCK', 'POCO_B200_FUSE_TAIL', 'POCO_B200_FUSE_BRANCH'):
         monkeypatch.setenv(var, '0')
     c0, n0 = kinds(build_model('cliff_w32'))
@@ -301,8 +302,11 @@ def test_plan_fuses_blocks_in_fp16_mode_only(monkeypatch):
         monkeypatch.delenv(var)
     monkeypatch.setenv('POCO_B200_FUSE_BLOCK64', '0')
     c64, _ = kinds(build_model('cliff_w32'))
-    assert c64.get(_lib.OP_BASIC_BLOCK) == 25 and c64.get(_lib.OP_BRANCH) == 7
+    assert c64.get(_lib.OP_BASIC_BLOCK) == 32 and c64.get(_lib.OP_BRANCH) == 7
     monkeypatch.delenv('POCO_B200_FUSE_BLOCK64')
+    monkeypatch.setenv('POCO_B200_FUSE_BLOCK_S2D', '0')
+    assert kinds(build_model('cliff_w32'))[0].get(_lib.OP_BASIC_BLOCK) == 54
+    monkeypatch.delenv('POCO_B200_FUSE_BLOCK_S2D')
     cs, ns = kinds(build_model('cliff_w32', precision='split'))
     assert ns == n_convs == cs[_lib.OP_CONV] and _lib.OP_BRANCH not in cs and _lib.OP_BASIC_BLOCK not in cs
 
