@@ -247,7 +247,10 @@ def hr_module(b, xs, name, chans, out0=None):
     scale = [rcost if resident[i] else (c64 if (chans[i] == 64 and fusable64 is not None and not chain_on[i] and
                                                 fusable64(64, xs[i].H, xs[i].W)) else 1.0) for i in range(nb)]
     b.fork([8 * conv_cost(N, chans[i], chans[i], 3, xs[i].H, xs[i].W) * scale[i] for i in range(nb)])
-    for i in range(nb):
+    # emission order of the lanes = creation order of their graph nodes: POCO_B200_LANE_ORDER=rev enqueues the low-resolution
+    # branches (dependent chains of short launches, the lanes that end a module) before the 32-channel lane's long kernels
+    order = list(range(nb))[::-1] if os.environ.get('POCO_B200_LANE_ORDER', 'fwd') == 'rev' else list(range(nb))
+    for i in order:
         b.set_lane(i)
         x = xs[i]
         chained = chain_on[i]
@@ -284,8 +287,8 @@ def hr_module(b, xs, name, chans, out0=None):
                 c += conv_cost(N, chans[j], co, 3, dims[j][0] >> (k + 1), dims[j][1] >> (k + 1)) * 2   # gather mode
         return c + N * dims[i][0] * dims[i][1] * chans[i] // 4          # + the element-wise sum
     b.fork([fuse_cost(i) for i in range(nb)])
-    outs = []
-    for i in range(nb):
+    outs = [None] * nb
+    for i in (order if os.environ.get('POCO_B200_LANE_ORDER_FUSE', '0') == '1' else range(nb)):
         b.set_lane(i)
         ups = []
         for j in range(i + 1, nb):      # 1x1 conv + BN at low resolution; nearest upsample folded into the sum
@@ -313,7 +316,7 @@ def hr_module(b, xs, name, chans, out0=None):
             o = acc
         for z, _ in ups:
             b.free(z)
-        outs.append(o)
+        outs[i] = o
     b.join()
     for x in xs:
         b.free(x)

@@ -1,0 +1,16 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+run() { echo "== $*"; env "$@" timeout 150 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-other-mode 2> gpurun_out/bench_var.err | python -c "
+import sys, json
+for l in sys.stdin:
+    l = l.strip()
+    if l.startswith('{'):
+        d = json.loads(l); print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'launches', d['launches_per_forward'], d['parity_err']['pred_pose'])
+"; }
+run X=1
+run POCO_B200_LANE_ORDER=rev
+run POCO_B200_LANE_ORDER=rev POCO_B200_LANE_ORDER_FUSE=1
+run X=2
+run POCO_B200_LANE_ORDER=rev
+run POCO_B200_LANE_ORDER=rev POCO_B200_LANE_ORDER_FUSE=1
