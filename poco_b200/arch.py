@@ -223,21 +223,19 @@ def chain_policy(channels, N=256, latency_mode=False):
     return bool(latency_mode) and N <= 16
 
 
-def hr_module(b, xs, name, chans, out0=None):
-    """HighResolutionModule: 4 BasicBlocks per branch, then the multi-resolution fuse
-    (hrnet.py:188-266).  Inputs are consumed (freed).  The branches, and afterwards the per-output
-    fuse chains, are independent: they are emitted as concurrent plan lanes, each with a share of the
-    SMs proportional to its work (the 14x14 / 7x7 branches cannot fill 148 SMs on their own)."""
-    nb = len(xs)
-    N = b.N
+def _branch_phase(b, xs, dims, name, chans):
+    """the four BasicBlocks of every branch of one HighResolutionModule (hrnet.py:140-186):
+    -> (per-lane costs, emit(i)); emit(i) emits branch i on xs[i] in the current lane and stores its output in xs[i]"""
     import os
+    nb = len(chans)
+    N = b.N
     # The branch's eight convs share one geometry and CAN run as one persistent chained launch
     # (POCO_B200_CHAIN_MIN_C, off by default: see chain_policy).
     chain_on = [chain_policy(chans[i], N, getattr(b, 'latency_mode', False)) for i in range(nb)]
     # A backend may run the four blocks as ONE launch with the crop resident in shared memory (PlanBuilder.branch_fused:
     # the 128-channel 14x14 branch); not when the last block must also write a phase-split copy.
     fusable = getattr(b, 'branch_fusable', None)
-    resident = [fusable is not None and not chain_on[i] and not (nb - 1 - i >= 2) and fusable(chans[i], xs[i].H, xs[i].W, 4)
+    resident = [fusable is not None and not chain_on[i] and not (nb - 1 - i >= 2) and fusable(chans[i], dims[i][0], dims[i][1], 4)
                 for i in range(nb)]
     # (a resident branch needs about half the SM time of its eight separate launches: tools/branch_bench.py)
     rcost = float(os.environ.get('POCO_B200_BRANCH_COST', '0.5'))
@@ -245,13 +243,10 @@ def hr_module(b, xs, name, chans, out0=None):
     fusable64 = getattr(b, 'basic_block_fusable', None)
     c64 = float(os.environ.get('POCO_B200_BLOCK64_COST', '0.85'))
     scale = [rcost if resident[i] else (c64 if (chans[i] == 64 and fusable64 is not None and not chain_on[i] and
-                                                fusable64(64, xs[i].H, xs[i].W)) else 1.0) for i in range(nb)]
-    b.fork([8 * conv_cost(N, chans[i], chans[i], 3, xs[i].H, xs[i].W) * scale[i] for i in range(nb)])
-    # emission order of the lanes = creation order of their graph nodes: POCO_B200_LANE_ORDER=rev enqueues the low-resolution
-    # branches (dependent chains of short launches, the lanes that end a module) before the 32-channel lane's long kernels
-    order = list(range(nb))[::-1] if os.environ.get('POCO_B200_LANE_ORDER', 'fwd') == 'rev' else list(range(nb))
-    for i in order:
-        b.set_lane(i)
+                                                fusable64(64, dims[i][0], dims[i][1])) else 1.0) for i in range(nb)]
+    costs = [8 * conv_cost(N, chans[i], chans[i], 3, dims[i][0], dims[i][1]) * scale[i] for i in range(nb)]
+
+    def emit(i):
         x = xs[i]
         chained = chain_on[i]
         if resident[i]:
@@ -260,7 +255,7 @@ def hr_module(b, xs, name, chans, out0=None):
                 if o is not x:
                     b.free(x)
                 xs[i] = o
-                continue
+                return o
         if chained:
             b.begin_chain()
         for k in range(4):
@@ -272,10 +267,15 @@ def hr_module(b, xs, name, chans, out0=None):
         if chained:
             b.end_chain(groups=chain_groups(i, nb))
         xs[i] = x
-    b.join()
-    if nb == 1:
-        return xs
-    dims = [(x.H, x.W) for x in xs]
+        return x
+    return costs, emit
+
+
+def _fuse_phase(b, xs, dims, name, chans, out0=None):
+    """the multi-resolution fuse of one HighResolutionModule (hrnet.py:213-266): -> (per-lane costs, emit(i)); emit(i) emits
+    output i from the branch outputs xs in the current lane and returns it (xs stay allocated: the caller frees them)"""
+    nb = len(chans)
+    N = b.N
 
     def fuse_cost(i):
         c = 0
@@ -286,10 +286,8 @@ def hr_module(b, xs, name, chans, out0=None):
                 co = chans[i] if k == i - j - 1 else chans[j]
                 c += conv_cost(N, chans[j], co, 3, dims[j][0] >> (k + 1), dims[j][1] >> (k + 1)) * 2   # gather mode
         return c + N * dims[i][0] * dims[i][1] * chans[i] // 4          # + the element-wise sum
-    b.fork([fuse_cost(i) for i in range(nb)])
-    outs = [None] * nb
-    for i in (order if os.environ.get('POCO_B200_LANE_ORDER_FUSE', '0') == '1' else range(nb)):
-        b.set_lane(i)
+
+    def emit(i):
         ups = []
         for j in range(i + 1, nb):      # 1x1 conv + BN at low resolution; nearest upsample folded into the sum
             z = b.conv_bn(xs[j], f'{name}.fuse_layers.{i}.{j}.0', f'{name}.fuse_layers.{i}.{j}.1',
@@ -316,11 +314,85 @@ def hr_module(b, xs, name, chans, out0=None):
             o = acc
         for z, _ in ups:
             b.free(z)
-        outs[i] = o
+        return o
+    return [fuse_cost(i) for i in range(nb)], emit
+
+
+def _lane_order(nb):
+    """emission order of the lanes = creation order of their graph nodes: POCO_B200_LANE_ORDER=rev enqueues the low-resolution
+    branches (dependent chains of short launches, the lanes that end a module) before the 32-channel lane's long kernels
+    (measured slightly slower: not the default)"""
+    import os
+    return list(range(nb))[::-1] if os.environ.get('POCO_B200_LANE_ORDER', 'fwd') == 'rev' else list(range(nb))
+
+
+def hr_module(b, xs, name, chans, out0=None):
+    """HighResolutionModule: 4 BasicBlocks per branch, then the multi-resolution fuse
+    (hrnet.py:188-266).  Inputs are consumed (freed).  The branches, and afterwards the per-output
+    fuse chains, are independent: they are emitted as concurrent plan lanes, each with a share of the
+    SMs proportional to its work (the 14x14 / 7x7 branches cannot fill 148 SMs on their own)."""
+    import os
+    nb = len(xs)
+    dims = [(x.H, x.W) for x in xs]
+    costs, emit = _branch_phase(b, xs, dims, name, chans)
+    b.fork(costs)
+    for i in _lane_order(nb):
+        b.set_lane(i)
+        emit(i)
+    b.join()
+    if nb == 1:
+        return xs
+    costs, emit = _fuse_phase(b, xs, dims, name, chans, out0)
+    b.fork(costs)
+    outs = [None] * nb
+    for i in (_lane_order(nb) if os.environ.get('POCO_B200_LANE_ORDER_FUSE', '0') == '1' else range(nb)):
+        b.set_lane(i)
+        outs[i] = emit(i)
     b.join()
     for x in xs:
         b.free(x)
     return outs
+
+
+def hr_stage(b, xs, names, chans, out0=None):
+    """The HighResolutionModules `names` of one HRNet stage (hrnet.py:386-412) with the fuse of module m and the branches of
+    module m + 1 in ONE fork / join region: branch i of the next module reads fuse output i only, so lane i runs
+    fuse_i(m) -> branch_i(m + 1) without waiting for the other lanes; only the fuse needs every branch, i.e. a real join.
+    One barrier per module instead of two (POCO_B200_MERGE_PHASES, see hrnet_trunk).  out0: see hr_module (last module)."""
+    nb = len(xs)
+    dims = [(x.H, x.W) for x in xs]
+    set_shares = getattr(b, 'set_shares', None)        # (PlanBuilder: SM shares of the ops emitted next, per sub-phase)
+    bcosts, bemit = _branch_phase(b, xs, dims, names[0], chans)
+    b.fork(bcosts)
+    for i in range(nb):
+        b.set_lane(i)
+        bemit(i)
+    b.join()
+    for m, name in enumerate(names):
+        last = m == len(names) - 1
+        fcosts, femit = _fuse_phase(b, xs, dims, name, chans, out0 if last else None)
+        outs = [None] * nb
+        if last:
+            b.fork(fcosts)
+            for i in range(nb):
+                b.set_lane(i)
+                outs[i] = femit(i)
+        else:
+            bcosts, bemit = _branch_phase(b, outs, dims, names[m + 1], chans)
+            b.fork([f + c for f, c in zip(fcosts, bcosts)])
+            for i in range(nb):
+                b.set_lane(i)
+                if set_shares is not None:
+                    set_shares(fcosts)
+                outs[i] = femit(i)
+                if set_shares is not None:
+                    set_shares(bcosts)
+                bemit(i)                    # (runs on outs[i] and replaces it)
+        b.join()
+        for x in xs:
+            b.free(x)
+        xs = outs
+    return xs
 
 
 def hrnet_trunk(b, img, widths, H=224, W=224, prefix='backbone.', final_out0=None):
@@ -343,6 +415,11 @@ def hrnet_trunk(b, img, widths, H=224, W=224, prefix='backbone.', final_out0=Non
         new = b.conv_bn(ys[-1], f'{p}transition{st - 1}.{nbr - 1}.0.0', f'{p}transition{st - 1}.{nbr - 1}.0.1',
                         widths[nbr - 2], widths[nbr - 1], 3, 2)
         ys = ys + [new]
+        import os
+        if os.environ.get('POCO_B200_MERGE_PHASES', '0') == '1' and nbr > 1:
+            ys = hr_stage(b, ys, [f'{p}stage{st}.{m}' for m in range(n_modules[st])], widths[:nbr],
+                          out0=final_out0(ys[0].H, ys[0].W) if (st == 4 and final_out0 is not None) else None)
+            continue
         for m in range(n_modules[st]):
             last = st == 4 and m == n_modules[st] - 1 and final_out0 is not None
             ys = hr_module(b, ys, f'{p}stage{st}.{m}', widths[:nbr],

@@ -279,16 +279,27 @@ class PlanBuilder:
         if not self.use_lanes:
             return
         n = len(costs)
-        tot = float(sum(costs)) or 1.0
-        shares = [max(4, int(round(self.num_sms * c / tot))) for c in costs]
-        while sum(shares) > self.num_sms:
-            shares[shares.index(max(shares))] -= 1
-        self.shares = shares
+        self.shares = self.shares_for(costs)
         self.ops.append(L.make_op(L.Sync(n), lane=0, kind=L.OP_FORK))
         for (lane, H, W), lst in list(self.free_pool.items()):     # everything free now is safe for any lane
             if lane == 0 and lst:
                 self.free_pool.setdefault(('fork', H, W), []).extend(lst)
                 lst.clear()
+
+    def shares_for(self, costs):
+        """SM share per lane for relative `costs` (every lane at least 4 SMs, together at most all of them)"""
+        tot = float(sum(costs)) or 1.0
+        shares = [max(4, int(round(self.num_sms * c / tot))) for c in costs]
+        while sum(shares) > self.num_sms:
+            shares[shares.index(max(shares))] -= 1
+        return shares
+
+    def set_shares(self, costs):
+        """inside a fork: the ops emitted next take their CTA budgets from these costs (arch.hr_stage: a lane's fuse ops and
+        its next-module branch ops share one fork / join region but not one cost profile)"""
+        if self.use_lanes and self.shares is not None:
+            assert len(costs) == len(self.shares)
+            self.shares = self.shares_for(costs)
 
     def set_lane(self, k):
         if not self.use_lanes:
