@@ -311,6 +311,40 @@ def test_plan_fuses_blocks_in_fp16_mode_only(monkeypatch):
     assert ns == n_convs == cs[_lib.OP_CONV] and _lib.OP_BRANCH not in cs and _lib.OP_BASIC_BLOCK not in cs
 
 
+@pytest.mark.parametrize('env', [{'POCO_B200_MERGE_PHASES': '1'}, {'POCO_B200_LANE_ORDER': 'rev', 'POCO_B200_LANE_ORDER_FUSE': '1'},
+                                 {'POCO_B200_OUT_LANES': '1'}, {'POCO_B200_LANES': '0'}])
+def test_plan_level_switches_keep_the_schedule_correct(env, monkeypatch):
+    """the opt-in plan structures (fuse + next branches in one fork / join region, reversed lane emission, output-stage
+    lanes, no lanes at all) emit the same network: replayed by the CPU interpreter they reproduce the default schedule's
+    outputs exactly, with as many forks as joins and every lane index inside its fork"""
+    def run():
+        m = build_model('cliff_w32')
+        batch = synthetic_batch('cliff_w32')
+        eng = m._build_engine(2, torch.device('cpu'))
+        eng.img.copy_(batch['img'][:2])
+        if eng.bbox is not None:
+            eng.bbox.copy_(batch['bbox_info'][:2])
+        emu.run_plan_ops(eng.plan.ops, eng.plan.keep)
+        return {k: eng.out[k].clone() for k in GATED}, eng.plan.ops
+    base, _ = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got, ops = run()
+    for k in GATED:
+        assert torch.equal(got[k], base[k]), k
+    open_lanes = 0
+    for op in ops:
+        if op.kind == _lib.OP_FORK:
+            assert open_lanes == 0
+            open_lanes = op.u.sync.n_lanes
+        elif op.kind == _lib.OP_JOIN:
+            assert open_lanes == op.u.sync.n_lanes
+            open_lanes = 0
+        else:
+            assert op.lane == 0 if open_lanes == 0 else 0 <= op.lane < open_lanes
+    assert open_lanes == 0
+
+
 def test_buffer_pool_keeps_zero_halo():
     """pool reuse never hands a buffer to a tensor of different spatial geometry"""
     b = engine.PlanBuilder({}, 2, 'cpu')
